@@ -1,0 +1,206 @@
+"""Pin the oracle against the reference and (re)generate tests/golden/*.npz.
+
+Runs ONLY in the build container (needs /root/reference). It imports the unmodified reference
+(`nicediffusion.model`, `nicediffusion.diffusion`) with a stub for the missing `matplotlib`
+(nicediffusion/utils.py:3 imports it at module top), then for every case:
+
+  1. runs the reference on CPU fp32,
+  2. runs the oracle restatement on the same weights / inputs / injected noise,
+  3. asserts they agree BIT-EXACTLY (same torch ops in the same order), and
+  4. stores the reference's outputs as a fixture.
+
+    python -m oracle.make_golden          # from the repo root
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF_ROOT = '/root/reference'
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+
+def import_reference():
+    for name in ('matplotlib', 'matplotlib.pyplot'):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    import nicediffusion.model as rm
+    import nicediffusion.diffusion as rd
+    return rm, rd
+
+
+def make_inputs(cfg, batch, seed):
+    rs = np.random.RandomState(seed)
+    x = torch.from_numpy(rs.standard_normal((batch, cfg['in_channels'], cfg['resolution'],
+                                             cfg['resolution'])).astype(np.float32))
+    t = torch.from_numpy(rs.randint(0, 1000, size=(batch,)).astype(np.int64))
+    y = None
+    if cfg.get('num_classes') is not None:
+        y = torch.from_numpy(rs.randint(0, cfg['num_classes'], size=(batch,)).astype(np.int64))
+    return x, t, y
+
+
+class DummyClassifier(torch.nn.Module):
+    """Deterministic stand-in for the noisy-image classifier (the reference ships none,
+    utils.py:171-172): logits = W . [avgpool4(x) flattened, t/10]."""
+
+    def __init__(self, in_ch, res, num_classes, seed):
+        super().__init__()
+        rs = np.random.RandomState(seed)
+        feat = in_ch * (res // 4) ** 2 + 1
+        self.w = torch.nn.Parameter(torch.from_numpy(
+            (rs.standard_normal((num_classes, feat)) / np.sqrt(feat)).astype(np.float32)))
+
+    def forward(self, x, t):
+        f = torch.nn.functional.avg_pool2d(x, 4).flatten(1)
+        f = torch.cat([f, t.float()[:, None] / 10.0], dim=1)
+        return torch.tanh(f @ self.w.t()) * 3.0
+
+
+SAMPLER_CASES = {
+    # name: (cfg, diffusion kwargs, classifier?)
+    'ddpm_interp': ('tiny', dict(original_num_steps=1000, rescaled_num_steps=10, beta_schedule='cosine',
+                                 sampling_var_type='learned_interpolation'), False),
+    'ddpm_interp_cfg': ('tiny', dict(original_num_steps=1000, rescaled_num_steps=10, beta_schedule='cosine',
+                                     sampling_var_type='learned_interpolation',
+                                     guidance_method='classifier_free', guidance_strength=0.8), False),
+    'ddpm_learned': ('tiny', dict(original_num_steps=1000, rescaled_num_steps=10, beta_schedule='linear',
+                                  sampling_var_type='learned'), False),
+    'ddpm_small': ('tiny_legacy', dict(original_num_steps=1000, rescaled_num_steps=10, beta_schedule='linear',
+                                       sampling_var_type='small'), False),
+    'ddpm_large': ('tiny_legacy', dict(original_num_steps=1000, rescaled_num_steps=10, beta_schedule='cosine',
+                                       sampling_var_type='large'), False),
+    'ddim_eta0': ('tiny', dict(original_num_steps=1000, rescaled_num_steps=10, beta_schedule='linear',
+                               sampling_var_type='learned_interpolation', use_ddim=True, ddim_eta=0.0), False),
+    'ddim_eta05_cfg': ('tiny', dict(original_num_steps=1000, rescaled_num_steps=10, beta_schedule='cosine',
+                                    sampling_var_type='learned_interpolation', use_ddim=True, ddim_eta=0.5,
+                                    guidance_method='classifier_free', guidance_strength=1.5), False),
+    'ddpm_classifier': ('tiny', dict(original_num_steps=1000, rescaled_num_steps=10, beta_schedule='cosine',
+                                     sampling_var_type='learned_interpolation',
+                                     guidance_method='classifier', guidance_strength=2.0), True),
+    'ddim_classifier': ('tiny', dict(original_num_steps=1000, rescaled_num_steps=10, beta_schedule='cosine',
+                                     sampling_var_type='learned_interpolation', use_ddim=True, ddim_eta=0.0,
+                                     guidance_method='classifier', guidance_strength=2.0), True),
+}
+
+SCHEDULE_CASES = [(1000, 250, 'cosine'), (1000, 25, 'cosine'), (1000, 50, 'linear'), (1000, 1000, 'linear'),
+                  (1000, 300, 'cosine'), (100, 10, 'constant'), (4000, 100, 'cosine')]
+
+
+def main():
+    from oracle import CONFIGS
+    from oracle.schedule import Tables
+    from oracle.unet import unet_forward
+    from oracle.weights import random_state_dict
+    from oracle.sampler import Sampler
+
+    rm, rd = import_reference()
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    dev = torch.device('cpu')
+
+    # ---- 1. schedules / respacing / tables ------------------------------------------------
+    sched = {}
+    dummy = rm.DiffusionModel(**{k: v for k, v in CONFIGS['tiny'].items()})
+    for (T, R, name) in SCHEDULE_CASES:
+        ref = rd.Diffusion(model=dummy, original_num_steps=T, rescaled_num_steps=R,
+                           sampling_var_type='learned_interpolation', loss_type='hybrid',
+                           beta_schedule=name, device=dev)
+        tab = Tables(T, R, name)
+        key = 'T{}_R{}_{}'.format(T, R, name)
+        assert np.array_equal(ref.timestep_map.numpy(), tab.timestep_map), key
+        sched[key + '/timestep_map'] = ref.timestep_map.numpy()
+        for n in Tables.NAMES:
+            a, b = getattr(ref, n), getattr(tab, n)
+            assert a.dtype == np.float64 and np.array_equal(a, b), (key, n)
+            sched[key + '/' + n] = a
+        print('schedule', key, 'len', len(tab.betas), 'bit-exact')
+    np.savez_compressed(os.path.join(OUT, 'schedule.npz'), **sched)
+
+    # ---- 2. UNet forward ---------------------------------------------------------------------
+    for cname, batch in (('tiny', 2), ('tiny_legacy', 2), ('tiny_pool', 2), ('emnist', 2), ('in64', 1)):
+        cfg = CONFIGS[cname]
+        sd = random_state_dict(cfg, seed=1234)
+        ref_model = rm.DiffusionModel(**cfg).eval()
+        ref_model.load_state_dict(sd, strict=True)
+        assert list(ref_model.state_dict().keys()) == list(sd.keys()), 'state-dict order differs: ' + cname
+        x, t, y = make_inputs(cfg, batch, seed=99)
+        with torch.no_grad():
+            ref_out = ref_model(x, t, y) if y is not None else ref_model(x, t)
+        ora_out = unet_forward(cfg, sd, x, t, y)
+        assert torch.equal(ref_out, ora_out), cname
+        print('unet', cname, 'B', batch, 'bit-exact; |out|max', float(ref_out.abs().max()))
+        save = dict(x=x.numpy(), t=t.numpy(), out=ref_out.numpy())
+        if y is not None:
+            save['y'] = y.numpy()
+        if cname == 'in64':  # keep the fixture small: one image, eps+var output only (98 KB)
+            pass
+        np.savez_compressed(os.path.join(OUT, 'unet_{}.npz'.format(cname)), **save)
+
+    # ---- 3. sampler trajectories ------------------------------------------------------------
+    for name, (cname, dkw, use_clf) in SAMPLER_CASES.items():
+        cfg = CONFIGS[cname]
+        sd = random_state_dict(cfg, seed=4321)
+        ref_model = rm.DiffusionModel(**cfg).eval()
+        ref_model.load_state_dict(sd, strict=True)
+        B = 2
+        rs = np.random.RandomState(7)
+        R = dkw['rescaled_num_steps']
+        x_T = torch.from_numpy(rs.standard_normal((B, cfg['in_channels'], cfg['resolution'],
+                                                   cfg['resolution'])).astype(np.float32))
+        noises = torch.from_numpy(rs.standard_normal((R,) + tuple(x_T.shape)).astype(np.float32))
+        y = None
+        if cfg.get('num_classes') is not None:
+            y = torch.from_numpy(rs.randint(1, cfg['num_classes'], size=(B,)).astype(np.int64))
+        clf = DummyClassifier(cfg['in_channels'], cfg['resolution'], cfg['num_classes'], seed=5) if use_clf else None
+
+        ref = rd.Diffusion(model=ref_model, loss_type='hybrid', classifier=clf, device=dev, **dkw)
+        # inject noise: the reference draws torch.randn_like(x_t) once per step, t = R-1 ... 0
+        order = list(reversed(range(R)))
+        it = iter(order)
+        real = torch.randn_like
+        torch.randn_like = lambda ref_t, *a, **k: noises[next(it)].clone()
+        try:
+            ref_x = ref.denoise(x=x_T.clone(), kwargs={'y': y} if y is not None else None,
+                                batch_size=B, progress=False)
+        finally:
+            torch.randn_like = real
+
+        def model_fn(xx, tt, y=None, _cfg=cfg, _sd=sd):
+            return unet_forward(_cfg, _sd, xx, tt, y)
+        ora = Sampler(model_fn, classifier=clf, **dkw)
+        traj = []
+        ora_x = ora.denoise(x_T.clone(), {'y': y} if y is not None else {}, lambda t: noises[t], trajectory=traj)
+        assert torch.equal(ref_x, ora_x), name
+        print('sampler', name, 'bit-exact; final |x|max', float(ref_x.abs().max()))
+        save = dict(x_T=x_T.numpy(), noises=noises.numpy(), final=ref_x.numpy(),
+                    traj_x=np.stack([s[1].numpy() for s in traj]),
+                    traj_x0=np.stack([s[2].numpy() for s in traj]))
+        if y is not None:
+            save['y'] = y.numpy()
+        np.savez_compressed(os.path.join(OUT, 'traj_{}.npz'.format(name)), **save)
+
+    # ---- 4. q-sample (diffuse) ------------------------------------------------------------------
+    cfg = CONFIGS['tiny']
+    ref_model = rm.DiffusionModel(**cfg).eval()
+    ref = rd.Diffusion(model=ref_model, original_num_steps=1000, rescaled_num_steps=50,
+                       sampling_var_type='learned_interpolation', loss_type='hybrid',
+                       beta_schedule='cosine', device=dev)
+    rs = np.random.RandomState(3)
+    x0 = torch.from_numpy(rs.uniform(-1, 1, (2, 3, 16, 16)).astype(np.float32))
+    nz = torch.from_numpy(rs.standard_normal((2, 3, 16, 16)).astype(np.float32))
+    ref_xt = ref.diffuse(x0, steps_to_do=20, noise=nz)
+    ora = Sampler(None, 1000, 50, 'learned_interpolation', beta_schedule='cosine')
+    assert torch.equal(ref_xt, ora.diffuse(x0, 20, nz))
+    np.savez_compressed(os.path.join(OUT, 'diffuse.npz'), x0=x0.numpy(), noise=nz.numpy(), x_t=ref_xt.numpy())
+    print('diffuse bit-exact')
+    print('golden fixtures written to', OUT)
+
+
+if __name__ == '__main__':
+    main()
