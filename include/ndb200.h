@@ -1,0 +1,211 @@
+/* ndb200 -- C-ABI of the B200-native nice-diffusion sampling hot path.
+ *
+ * The reference (edogariu/nice-diffusion) is pure Python/PyTorch and has NO FFI / plugin layer
+ * (SURVEY.md section 8b); what the reference "binds" for this path is a set of torch ops called from
+ * nicediffusion/model.py and nicediffusion/diffusion.py. Each entry point below replaces the group of
+ * reference ops cited next to it. The Python host (nice-diffusion_b200/*.py) mirrors the reference's
+ * classes and reaches these symbols through ctypes with raw device pointers.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated; `stream` is a cudaStream_t passed as void*;
+ *   - kernels are enqueued on `stream`, never synchronise, never allocate: CUDA-graph capturable;
+ *   - return value: NDB_OK (0) or a negative NDB_ERR_* code; no C++ exception crosses the boundary;
+ *   - activations inside the UNet are NHWC ("channels last"): fp32 for the residual stream,
+ *     fp16 for tensor-core operands. Model inputs/outputs are NCHW fp32 like the reference's.
+ */
+#ifndef NDB200_H
+#define NDB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NDB_OK 0
+#define NDB_ERR_INVALID (-1)
+#define NDB_ERR_CUDA (-2)
+#define NDB_ERR_UNSUPPORTED (-3)
+
+#define NDB_MAX_SEGMENTS 9
+
+/* library / device queries ------------------------------------------------------------------ */
+int ndb_version(void);                     /* ABI version, currently 1 */
+int ndb_device_supported(void);            /* 1 when the current CUDA device is sm_100 (B200), else 0 */
+const char* ndb_last_error(void);          /* last CUDA error string seen by the library (host pointer) */
+
+/* ---- implicit-GEMM convolution on tcgen05 / TMEM / TMA -------------------------------------------
+ * Replaces nn.Conv2d 3x3 s1 p1 and 1x1 (model.py:72,103,166-178,367,448), nn.Conv1d k=1 qkv / proj_out
+ * (model.py:247,253), the step-embedding nn.Linear of every ResBlock (model.py:180-182,197) and, through
+ * the `residual` / extra-segment arguments, the ops fused around them: bias add, `h + self.skip(x)`
+ * (model.py:211), `h + x` (model.py:291), x_resample (model.py:193) and torch.cat skip concat (model.py:474).
+ *
+ *   out[n,h,w,co] = bias[co] + residual(n,h,w,co)
+ *                 + sum_seg sum_tap sum_ci  a_seg[n, h+dy(tap), w+dx(tap), ci] * w_seg[tap][co][ci]
+ *
+ * Every segment is one K-range of the GEMM: its own NHWC fp16 activation tensor (all segments share
+ * N,H,W) and its own packed weight block [taps][cout_pad][C] (fp16, K-major). Zero padding comes from TMA
+ * out-of-bounds fill. C must be a multiple of 64, cout_pad a multiple of 16.
+ */
+typedef struct {
+    const void* act;     /* fp16 NHWC [N,H,W,C] */
+    const void* weight;  /* fp16 [taps][cout_pad][C] (ndb_pack_conv_weight) */
+    int32_t C;
+    int32_t taps;        /* 1 (1x1) or 9 (3x3, pad 1) */
+} ndb_conv_segment;
+
+#define NDB_RES_NONE 0
+#define NDB_RES_SAME 1   /* residual is fp32 NHWC [N,H,W,cout] */
+#define NDB_RES_UP2 2    /* residual is [N,H/2,W/2,cout], nearest-neighbour x2 (F.interpolate, model.py:77) */
+#define NDB_RES_DOWN2 3  /* residual is [N,2H,2W,cout], 2x2 mean (F.avg_pool2d, model.py:111) */
+
+#define NDB_OUT_F32_NHWC 0
+#define NDB_OUT_F16_NHWC 1
+#define NDB_OUT_F32_NCHW 2
+
+typedef struct {
+    int32_t N, H, W;
+    int32_t cout;        /* valid output channels */
+    int32_t cout_pad;    /* rows of every weight block (>= cout, multiple of 16) */
+    int32_t num_segments;
+    ndb_conv_segment seg[NDB_MAX_SEGMENTS];
+    const float* bias;       /* [cout] or NULL */
+    const float* residual;   /* see NDB_RES_* or NULL */
+    int32_t residual_mode;
+    int32_t out_kind;        /* NDB_OUT_* */
+    void* out;
+    int32_t operand_format;  /* 0 = fp16, 1 = bf16 (both: fp32 accumulation in TMEM) */
+    int32_t block_n;         /* 0 = auto */
+    double* gn_stats;        /* optional [N][32][2] fp64 (sum, sum of squares) of `out` per GroupNorm group,
+                                accumulated by the epilogue (must be zeroed by the caller); NULL = off */
+} ndb_conv_params;
+
+int ndb_conv_gemm(const ndb_conv_params* p, void* stream);
+
+/* OIHW fp32 (nn.Conv2d / Conv1d / Linear weight, kernel 1 or 3) -> [taps][cout_pad][cin] 16-bit, rows >= cout zero.
+ * `cin_off`/`cin_len` select an input-channel range (used to split a weight over concat segments). */
+int ndb_pack_conv_weight(const float* w_oihw, void* dst, int cout, int cin_total, int ksize, int cout_pad,
+                         int cin_off, int cin_len, int operand_format, void* stream);
+
+/* ---- GroupNorm(32) statistics + apply ------------------------------------------------------------------
+ * Replaces nn.GroupNorm(32, C, eps=1e-5) + SiLU + AdaGN scale/shift + h_resample + torch.cat
+ * (model.py:172,176,190-193,199-207,250,264,446-447).
+ * Input is the (virtual) channel concat of up to two fp32 NHWC tensors [N,H,W,C0] ++ [N,H,W,C1].
+ * `pre_add` ([N][ld_pre], optional) is added per (n, channel) before normalisation (the non-adaptive
+ * `h += embedding` path, model.py:205). */
+int ndb_gn_stats(const float* x0, int C0, const float* x1, int C1, int N, int HW, const float* pre_add,
+                 int ld_pre, double* stats /* [N][32][2], zeroed */, void* stream);
+
+#define NDB_RESAMPLE_NONE 0
+#define NDB_RESAMPLE_UP2 1
+#define NDB_RESAMPLE_DOWN2 2
+
+typedef struct {
+    const float* x0; int32_t C0;
+    const float* x1; int32_t C1;       /* optional second concat source */
+    int32_t N, H, W;                   /* input spatial size */
+    const double* stats;               /* [N][32][2] from ndb_gn_stats / conv epilogue */
+    const float* gamma; const float* beta;   /* [C0+C1] */
+    const float* scale; const float* shift;  /* optional AdaGN [N][ld_ss] rows: y = gn*(1+scale)+shift */
+    int32_t ld_ss;
+    const float* pre_add; int32_t ld_pre;    /* optional */
+    int32_t silu;                      /* apply SiLU after the affine */
+    int32_t resample;                  /* NDB_RESAMPLE_* applied after the activation */
+    void* out;                         /* 16-bit NHWC [N,H',W',C0+C1] */
+    void* raw16;                       /* optional 16-bit copy of the un-normalised (resampled) input, same shape */
+    int32_t operand_format;
+    float eps;
+} ndb_gn_apply_params;
+
+int ndb_gn_apply(const ndb_gn_apply_params* p, void* stream);
+
+/* ---- fused multi-head attention (tcgen05) ------------------------------------------------------------------
+ * Replaces q@k^T * scale, softmax, w@v and the head split / merge reshapes (model.py:266-287).
+ * qkv: fp16 [B][T][3C] as produced by the qkv 1x1 conv; out: fp16 [B][T][C], channel = head*d + j.
+ * order 0: channels laid out [3][heads][d] (split_qkv_first=True); order 1: [heads][3][d] (legacy). */
+int ndb_attention(const void* qkv, void* out, int B, int T, int heads, int d, int order, int operand_format,
+                  void* stream);
+
+/* ---- timestep / class embedding front end ------------------------------------------------------------------
+ * Replaces timestep_embedding + step_embed MLP + class_embedding add + the SiLU in front of every
+ * ResBlock's step_embedding Linear (model.py:456-459,514-523,197).
+ * freqs: [mc/2] fp32 (built by the host with the reference formula); t: [B] fp32 timesteps;
+ * y: [B] int64 labels or NULL. emb_out: [B][4mc] fp32 (optional); act_out: 16-bit SiLU(emb) [B][4mc]. */
+int ndb_embed(const float* t, const int64_t* y, const float* freqs, int B, int mc,
+              const float* w0, const float* b0, const float* w2, const float* b2, const float* class_emb,
+              float* emb_out, void* act_out, int operand_format, void* stream);
+
+/* ---- stem conv / small direct convs ------------------------------------------------------------------
+ * conv3x3 s1 p1 with tiny Cin (model.py:367): x NCHW fp32 [N,Cin,H,W] -> NHWC fp32 [N,H,W,Cout]. */
+int ndb_stem_conv(const float* x_nchw, const float* w_oihw, const float* bias, float* out_nhwc, int N, int Cin,
+                  int H, int W, int Cout, void* stream);
+
+/* generic fp32 NHWC resample (standalone Upsample / Downsample without conv, model.py:77,111) and layout casts */
+int ndb_resample_f32(const float* x, float* out, int N, int H, int W, int C, int mode, void* stream);
+int ndb_cast_nhwc16(const float* x, void* out, int64_t numel, int operand_format, void* stream);
+/* strided conv3x3 s2 p1 input gather for Downsample(with_conv) (model.py:103-105): builds the 9-tap
+ * tap-major operand [9][N,Ho,Wo,C] (Ho=(H-1)/2+1) so the GEMM runs it as nine 1x1 K-segments. */
+int ndb_im2col_s2(const float* x, void* out, int N, int H, int W, int C, int operand_format, void* stream);
+
+/* ---- fused sampler step ------------------------------------------------------------------------------
+ * Replaces get_eps_and_log_var, the CFG combine, pred_x0 + clamp, posterior mean, classifier-guidance
+ * shift, noise add and the t==0 mask (diffusion.py:242-316) or the DDIM update (diffusion.py:318-369).
+ * All image tensors NCHW fp32. model_out: [B][Cm][H][W] with Cm = 2C when the variance is learned, else C.
+ * null_out: unconditional model output for classifier-free guidance or NULL. t: [B] fp32 respaced step
+ * index per sample. tables: [NDB_TAB_COUNT][R] fp32 (fp64 numpy tables cast to fp32 as diffusion.py:492).
+ * noise: injected N(0,1) tensor, or NULL to draw Philox4x32-10 + Box-Muller noise in-kernel keyed by
+ * (seed, sample_ids[b], step t, element). grad: classifier gradient d log p(y|x)/dx or NULL. */
+#define NDB_TAB_SQRT_RECIP_ABAR 0
+#define NDB_TAB_SQRT_RECIPM1_ABAR 1
+#define NDB_TAB_POST_COEF_X0 2
+#define NDB_TAB_POST_COEF_XT 3
+#define NDB_TAB_LOGVAR_MIN 4   /* log_posterior_var_clipped (interp) or the fixed log-variance (small/large) */
+#define NDB_TAB_LOGVAR_MAX 5   /* log(betas) */
+#define NDB_TAB_ABAR 6
+#define NDB_TAB_ABAR_PREV 7
+#define NDB_TAB_SQRT_1M_ABAR 8
+#define NDB_TAB_COUNT 9
+
+#define NDB_VAR_FIXED 0          /* 'small' / 'large': log_var = tables[LOGVAR_MIN][t] */
+#define NDB_VAR_LEARNED 1        /* log_var = v */
+#define NDB_VAR_LEARNED_INTERP 2 /* log_var = frac*max + (1-frac)*min, frac=(v+1)/2 */
+
+typedef struct {
+    const float* x_t;
+    const float* model_out;
+    const float* null_out;
+    const float* t;
+    const float* tables;
+    int32_t R;                /* table row length */
+    int32_t B, C, HW, Cm;
+    int32_t var_type;
+    int32_t ddim;             /* 0 = DDPM step, 1 = DDIM step */
+    double eta;               /* DDIM eta (python float in the reference) */
+    double cfg_strength;      /* used when null_out != NULL */
+    const float* grad;        /* classifier guidance gradient or NULL */
+    double clf_strength;
+    int32_t clip_x0;
+    const float* noise;       /* NULL -> Philox */
+    uint64_t seed;
+    const int64_t* sample_ids; /* [B] global sample indices for Philox keying (NULL -> b) */
+    float* x_prev;            /* out (may alias x_t) */
+    float* pred_x0;           /* out, optional */
+} ndb_step_params;
+
+int ndb_sampler_step(const ndb_step_params* p, void* stream);
+
+/* x_T ~ N(0,1) from the same Philox stream family: element e of sample id s at "step" = R (diffusion.py:202). */
+int ndb_philox_normal(float* out, int B, int64_t per_sample, uint64_t seed, const int64_t* sample_ids,
+                      int32_t step, void* stream);
+
+/* q-sample: x_t = sqrt(abar_t) x0 + sqrt(1-abar_t) noise (diffusion.py:232-240); coefficient tables fp32 [R]. */
+int ndb_qsample(const float* x0, const float* noise, const float* t, const float* sqrt_abar,
+                const float* sqrt_1m_abar, float* out, int B, int64_t per_sample, void* stream);
+
+/* [-1,1] float NCHW -> uint8 NHWC image, ((x+1)*127.5).clamp(0,255) truncated (sample.py:94,149). */
+int ndb_to_uint8(const float* x_nchw, uint8_t* out_nhwc, int B, int C, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NDB200_H */

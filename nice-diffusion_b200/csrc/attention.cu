@@ -1,0 +1,317 @@
+// Fused multi-head self-attention on tcgen05: S = Q K^T and O += P V run on the tensor cores with fp32
+// accumulators in TMEM; the online softmax runs in registers, one query row per thread. The [T,T] score
+// matrix never touches HBM (the reference materialises it: model.py:273-277).
+//
+// One CTA = one (batch, head, 128-query block). Q/K/V tiles are read straight out of the qkv 1x1-conv
+// output ([B][T][3C], fp16) with 4-D TMA boxes {d, column-block, rows, batch}; the inner extent is the true
+// head dim d, so head dims that are not a multiple of 64 are zero-filled up to the next 64 by TMA.
+//   warps 0-3 : softmax + correction + epilogue (thread i owns query row i / TMEM lane i)
+//   warp  4   : one thread issues TMA loads and tcgen05.mma
+// TMEM: S at columns [0,128), O at [128,128+Dp).
+// K/V tiles are double-buffered; with d <= 64 two CTAs fit per SM so one CTA's softmax overlaps the other's MMAs.
+#include "common.cuh"
+#include "ptx.cuh"
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+namespace ndb {
+
+constexpr int kAttnBM = 128;  // queries per CTA
+constexpr int kAttnBN = 128;  // keys per iteration
+constexpr int kChunkBytes = 128 * 128;  // one [128 rows x 64 x 16-bit] swizzled tile
+
+struct AttnArgs {
+    int B, T, heads, d, order;
+    int dp_chunks;   // ceil(d / 64)
+    int kv_stages;
+    int fmt;
+    uint32_t tmem_cols;
+    uint32_t idesc_qk, idesc_pv;
+    float scale_log2e;
+    uint16_t* out;
+    int C;
+};
+
+template <int FMT>
+__device__ __forceinline__ uint32_t pack2a(float a, float b) {
+    if (FMT == 0) {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    } else {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(160)
+attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int q0 = qb * kAttnBM;
+    const int nkv = (p.T + kAttnBN - 1) / kAttnBN;
+    const int dpc = p.dp_chunks;
+    const int Dp = dpc * 64;
+
+    // smem carve-up
+    uint8_t* sQ = smem;                                   // dpc chunks
+    uint8_t* sK = sQ + dpc * kChunkBytes;                 // kv_stages * dpc chunks
+    uint8_t* sV = sK + p.kv_stages * dpc * kChunkBytes;   // kv_stages * dpc chunks
+    uint8_t* sP = sV + p.kv_stages * dpc * kChunkBytes;   // 2 chunks (128 keys)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kChunkBytes);
+    uint64_t* q_full = bars + 0;
+    uint64_t* k_full = bars + 1;   // [2]
+    uint64_t* v_full = bars + 3;   // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* p_full = bars + 6;
+    uint64_t* pv_done = bars + 7;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+
+    if (threadIdx.x == 128) {
+        prefetch_tmap(&qkv_map);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&v_full[i], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(p_full, 128);
+        mbar_init(pv_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(tmem_ptr_smem, p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_S = tmem_base;
+    const uint32_t tmem_O = tmem_base + kAttnBN;
+
+    // column-block indices of q / k / v for this head inside the 3C channel axis (units of d)
+    int cq, ck, cv;
+    if (p.order == 0) { cq = h; ck = p.heads + h; cv = 2 * p.heads + h; }
+    else { cq = 3 * h; ck = 3 * h + 1; cv = 3 * h + 2; }
+
+    if (warp == 4) {
+        if (lane == 0) {
+            const uint32_t tile_bytes = (uint32_t)dpc * kChunkBytes;
+            auto load_tile = [&](uint8_t* dst, uint64_t* bar, int colblk, int row0) {
+                mbar_arrive_expect_tx(bar, tile_bytes);
+                for (int c = 0; c < dpc; ++c)
+                    tma_load_4d(dst + c * kChunkBytes, &qkv_map, bar, c * 64, colblk, row0, b);
+            };
+            load_tile(sQ, q_full, cq, q0);
+            load_tile(sK, &k_full[0], ck, 0);
+            load_tile(sV, &v_full[0], cv, 0);
+            mbar_wait(q_full, 0);
+            for (int j = 0; j < nkv; ++j) {
+                const int st = (p.kv_stages == 2) ? (j & 1) : 0;
+                const uint32_t use_parity = (p.kv_stages == 2) ? ((j >> 1) & 1) : (j & 1);
+                // ---- S = Q K_j^T ----
+                mbar_wait(&k_full[st], use_parity);
+                tc_fence_after();
+                {
+                    const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + st * dpc * kChunkBytes);
+                    for (int i = 0; i < Dp / 16; ++i) {
+                        const uint32_t off = (i >> 2) * kChunkBytes + (i & 3) * 32;
+                        umma_f16(tmem_S, make_desc_k_sw128(qa + off), make_desc_k_sw128(ka + off), p.idesc_qk, i ? 1u : 0u);
+                    }
+                    umma_commit(s_full);
+                }
+                // ---- prefetch K/V for block j+1 ----
+                if (j + 1 < nkv) {
+                    const int st2 = (p.kv_stages == 2) ? ((j + 1) & 1) : 0;
+                    if (p.kv_stages == 2) {
+                        if (j >= 1) mbar_wait(pv_done, (j - 1) & 1);  // stage st2 was last read by block j-1
+                        load_tile(sK + st2 * dpc * kChunkBytes, &k_full[st2], ck, (j + 1) * kAttnBN);
+                        load_tile(sV + st2 * dpc * kChunkBytes, &v_full[st2], cv, (j + 1) * kAttnBN);
+                    }
+                }
+                // ---- O += P_j V_j ----
+                mbar_wait(p_full, j & 1);
+                mbar_wait(&v_full[st], use_parity);
+                tc_fence_after();
+                {
+                    const uint32_t pa = smem_u32(sP), va = smem_u32(sV + st * dpc * kChunkBytes);
+                    for (int i = 0; i < kAttnBN / 16; ++i) {
+                        const uint64_t adesc = make_desc_k_sw128(pa + (i >> 2) * kChunkBytes + (i & 3) * 32);
+                        // V tile: rows = keys (K dim), 64 d-elements contiguous per row (MN-major), 16 keys = 2048 B
+                        const uint64_t bdesc = make_desc_mn_sw128(va + i * 2048, kChunkBytes);
+                        umma_f16(tmem_O, adesc, bdesc, p.idesc_pv, (j | i) ? 1u : 0u);
+                    }
+                    umma_commit(pv_done);
+                }
+                if (j + 1 < nkv && p.kv_stages == 1) {
+                    // single-buffered K/V (large head dims): reload only after both MMAs of block j retired
+                    mbar_wait(pv_done, j & 1);
+                    load_tile(sK, &k_full[0], ck, (j + 1) * kAttnBN);
+                    load_tile(sV, &v_full[0], cv, (j + 1) * kAttnBN);
+                }
+            }
+        }
+    } else {
+        // ===================== softmax / correction / epilogue =====================
+        const int row = warp * 32 + lane;
+        const uint32_t lane_addr = uint32_t(warp * 32) << 16;
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int j = 0; j < nkv; ++j) {
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            const int kv_valid = p.T - j * kAttnBN;  // keys >= kv_valid in this block are padding
+            // pass 1: row max
+            float m_blk = -INFINITY;
+#pragma unroll 1
+            for (int c0 = 0; c0 < kAttnBN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_S + lane_addr + c0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (c0 + i < kv_valid) m_blk = fmaxf(m_blk, __uint_as_float(r[i]));
+            }
+            const float m_new = fmaxf(m_run, m_blk);
+            const float alpha = exp2f((m_run - m_new) * p.scale_log2e);  // 0 when m_run = -inf
+            const bool need_fix = (j > 0) && (m_new > m_run);
+            // previous block's P V must have retired before P (smem) and O (TMEM) are touched
+            if (j > 0) {
+                mbar_wait(pv_done, (j - 1) & 1);
+                tc_fence_after();
+            }
+            if (__any_sync(0xffffffffu, need_fix)) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < Dp; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_O + lane_addr + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                    tmem_st32(tmem_O + lane_addr + c0, r);
+                }
+                tmem_st_wait();
+            }
+            l_run *= alpha;
+            m_run = m_new;
+            // pass 2: p = exp2((s - m) * scale*log2e) -> fp16 P tile in the K-major SWIZZLE_128B layout
+            const float mb = m_new * p.scale_log2e;
+            float l_blk = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < kAttnBN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_S + lane_addr + c0, r);
+                tmem_ld_wait();
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float p0 = (c0 + i < kv_valid) ? exp2f(__uint_as_float(r[i]) * p.scale_log2e - mb) : 0.f;
+                    float p1 = (c0 + i + 1 < kv_valid) ? exp2f(__uint_as_float(r[i + 1]) * p.scale_log2e - mb) : 0.f;
+                    l_blk += p0 + p1;
+                    pk[i >> 1] = pack2a<FMT>(p0, p1);
+                }
+                // 32 keys = 64 bytes = four 16-byte chunks of this row's 128-byte line in K-chunk (c0 / 64)
+                uint8_t* line = sP + (c0 >> 6) * kChunkBytes + row * 128;
+                const int chunk0 = (c0 & 63) >> 3;  // first 16-byte chunk index (0 or 4)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int phys = (chunk0 + q) ^ (row & 7);
+                    *reinterpret_cast<uint4*>(line + phys * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                }
+            }
+            l_run += l_blk;
+            fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+            tc_fence_before();
+            mbar_arrive(p_full);
+        }
+        // ---- epilogue: O / l -> fp16 [B][T][C] ----
+        mbar_wait(pv_done, (nkv - 1) & 1);
+        tc_fence_after();
+        const float inv_l = 1.f / l_run;
+        const int qrow = q0 + row;
+        uint16_t* orow = p.out + ((size_t)b * p.T + qrow) * p.C + (size_t)h * p.d;
+#pragma unroll 1
+        for (int c0 = 0; c0 < Dp; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_O + lane_addr + c0, r);
+            tmem_ld_wait();
+            if (qrow < p.T) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    if (c0 + i + 8 <= p.d) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            w[k] = pack2a<FMT>(__uint_as_float(r[i + 2 * k]) * inv_l, __uint_as_float(r[i + 2 * k + 1]) * inv_l);
+                        *reinterpret_cast<uint4*>(orow + c0 + i) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+}  // namespace ndb
+
+using namespace ndb;
+
+extern "C" int ndb_attention(const void* qkv, void* out, int B, int T, int heads, int d, int order, int operand_format,
+                             void* stream) {
+    NDB_CHECK_ARG(qkv && out && B > 0 && T > 0 && heads > 0);
+    NDB_CHECK_ARG(d % 8 == 0 && d >= 8 && d <= 256);
+    NDB_CHECK_ARG(order == 0 || order == 1);
+    NDB_CHECK_ARG(operand_format == 0 || operand_format == 1);
+    const int C = heads * d;
+    AttnArgs a{};
+    a.B = B; a.T = T; a.heads = heads; a.d = d; a.order = order;
+    a.dp_chunks = (d + 63) / 64;
+    const int Dp = a.dp_chunks * 64;
+    a.kv_stages = (a.dp_chunks <= 2) ? 2 : 1;
+    // smem: Q + kv_stages*(K+V) + P(2 chunks) + barriers
+    size_t smem = (size_t)(a.dp_chunks * (1 + 2 * a.kv_stages) + 2) * kChunkBytes + 128;
+    if (smem > 227 * 1024) {
+        a.kv_stages = 1;
+        smem = (size_t)(a.dp_chunks * 3 + 2) * kChunkBytes + 128;
+    }
+    NDB_CHECK_ARG(smem <= 227 * 1024);
+    a.fmt = operand_format;
+    const int cols = kAttnBN + Dp;
+    a.tmem_cols = cols <= 256 ? 256 : 512;
+    a.idesc_qk = make_idesc_f16(kAttnBM, kAttnBN, operand_format, 0, 0);
+    a.idesc_pv = make_idesc_f16(kAttnBM, Dp, operand_format, 0, 1);
+    a.scale_log2e = (float)(1.4426950408889634 / sqrt((double)d));
+    a.out = (uint16_t*)out;
+    a.C = C;
+
+    CUtensorMap map;
+    {
+        // view [B][T][3*heads][d]
+        uint64_t dims[4] = {(uint64_t)d, (uint64_t)(3 * heads), (uint64_t)T, (uint64_t)B};
+        uint64_t strides[3] = {(uint64_t)d * 2, (uint64_t)3 * C * 2, (uint64_t)T * 3 * C * 2};
+        uint32_t box[4] = {64u, 1u, (uint32_t)kAttnBM, 1u};
+        int rc = encode_tmap_16bit(&map, qkv, 4, dims, strides, box);
+        if (rc != NDB_OK) return rc;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(attention_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_set = true;
+    }
+    dim3 grid((T + kAttnBM - 1) / kAttnBM, heads, B);
+    if (operand_format == 0)
+        attention_kernel<0><<<grid, 160, smem, (cudaStream_t)stream>>>(map, a);
+    else
+        attention_kernel<1><<<grid, 160, smem, (cudaStream_t)stream>>>(map, a);
+    return launch_status("ndb_attention");
+}

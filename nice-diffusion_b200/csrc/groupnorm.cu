@@ -1,0 +1,274 @@
+// GroupNorm(32) for NHWC fp32 activations: statistics pass + fused apply pass.
+//
+// Bandwidth-bound kernels (roofline = HBM): the stats pass reads the tensor once (float4, fully coalesced
+// along C) and leaves fp64 (sum, sum of squares) per (sample, group); the apply pass reads it a second
+// time, folds mean / rstd / gamma / beta / AdaGN (1+scale), shift into one per-channel FMA, applies SiLU,
+// optionally 2x nearest-upsamples or 2x2 average-pools, optionally concatenates two sources, and writes the
+// 16-bit NHWC tensor-core operand (16-byte stores).
+#include "common.cuh"
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+namespace ndb {
+
+constexpr int kGroups = 32;
+constexpr int kGnThreads = 256;
+constexpr int kMaxVecPerThread = 4;  // supports C <= 4 * 4 * 256 = 4096
+
+// ------------------------------------------------------------------------------------------------------
+// statistics
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGnThreads)
+gn_stats_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, int HW,
+                const float* __restrict__ pre_add, int ld_pre, double* __restrict__ stats, int pix_per_block,
+                int threads_per_row, int rows_per_block) {
+    extern __shared__ float sm[];  // [2][C]
+    const int C = C0 + C1;
+    const int V = C >> 2;
+    const int n = blockIdx.y;
+    const int p_begin = blockIdx.x * pix_per_block;
+    int p_end = p_begin + pix_per_block;
+    if (p_end > HW) p_end = HW;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+
+    const int r = threadIdx.x / threads_per_row;
+    const int tv = threadIdx.x - r * threads_per_row;
+    if (r < rows_per_block) {
+        float s[kMaxVecPerThread][4], ss[kMaxVecPerThread][4];
+#pragma unroll
+        for (int j = 0; j < kMaxVecPerThread; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s[j][k] = ss[j][k] = 0.f;
+
+#pragma unroll
+        for (int j = 0; j < kMaxVecPerThread; ++j) {
+            const int v = tv + j * threads_per_row;
+            if (v < V) {
+                const int c = v << 2;
+                const float* src;
+                int ldc, cc;
+                if (c < C0) { src = x0; ldc = C0; cc = c; } else { src = x1; ldc = C1; cc = c - C0; }
+                float4 add = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pre_add != nullptr) add = __ldg(reinterpret_cast<const float4*>(pre_add + (size_t)n * ld_pre + c));
+                const float* base = src + ((size_t)n * HW) * ldc + cc;
+                for (int p = p_begin + r; p < p_end; p += rows_per_block) {
+                    float4 a = __ldg(reinterpret_cast<const float4*>(base + (size_t)p * ldc));
+                    a.x += add.x; a.y += add.y; a.z += add.z; a.w += add.w;
+                    s[j][0] += a.x; s[j][1] += a.y; s[j][2] += a.z; s[j][3] += a.w;
+                    ss[j][0] += a.x * a.x; ss[j][1] += a.y * a.y; ss[j][2] += a.z * a.z; ss[j][3] += a.w * a.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kMaxVecPerThread; ++j) {
+            const int v = tv + j * threads_per_row;
+            if (v < V) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    atomicAdd(&sm[(v << 2) + k], s[j][k]);
+                    atomicAdd(&sm[C + (v << 2) + k], ss[j][k]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * kGroups) {
+        const int g = threadIdx.x & (kGroups - 1);
+        const int which = threadIdx.x >> 5;
+        const int cpg = C / kGroups;
+        double acc = 0.0;
+        for (int k = 0; k < cpg; ++k) acc += (double)sm[which * C + g * cpg + k];
+        atomicAdd(&stats[((size_t)n * kGroups + g) * 2 + which], acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// apply
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float silu_f(float v) { return v / (1.f + expf(-v)); }
+
+template <int FMT>
+__device__ __forceinline__ uint32_t pack2h(float a, float b) {
+    if (FMT == 0) {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    } else {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+}
+
+struct GnApplyArgs {
+    const float* x0; int C0;
+    const float* x1; int C1;
+    int N, H, W, Ho, Wo;
+    const double* stats;
+    const float* gamma; const float* beta;
+    const float* scale; const float* shift; int ld_ss;
+    const float* pre_add; int ld_pre;
+    int silu, resample;
+    uint16_t* out; uint16_t* raw16;
+    float eps;
+    int items_per_block;
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(kGnThreads)
+gn_apply_kernel(const GnApplyArgs p) {
+    extern __shared__ float sm[];  // a[C], b[C], pre[C]
+    const int C = p.C0 + p.C1;
+    const int n = blockIdx.y;
+    float* sa = sm;
+    float* sb = sm + C;
+    float* sp = sm + 2 * C;
+    const int cpg = C / kGroups;
+    const double inv_cnt = 1.0 / ((double)cpg * p.H * p.W);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const double s = p.stats[((size_t)n * kGroups + g) * 2 + 0];
+        const double ss = p.stats[((size_t)n * kGroups + g) * 2 + 1];
+        const double mean = s * inv_cnt;
+        double var = ss * inv_cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+        const float ga = p.gamma[c], be = p.beta[c];
+        float a = rstd * ga;
+        float b = be - (float)mean * a;
+        const float pre = p.pre_add ? p.pre_add[(size_t)n * p.ld_pre + c] : 0.f;
+        b += a * pre;
+        if (p.scale != nullptr) {
+            const float sc = 1.f + p.scale[(size_t)n * p.ld_ss + c];
+            const float sh = p.shift[(size_t)n * p.ld_ss + c];
+            a *= sc;
+            b = b * sc + sh;
+        }
+        sa[c] = a;
+        sb[c] = b;
+        sp[c] = pre;
+    }
+    __syncthreads();
+
+    const int V8 = C >> 3;
+    const long long items = (long long)p.Ho * p.Wo * V8;
+    long long i0 = (long long)blockIdx.x * p.items_per_block;
+    long long i1 = i0 + p.items_per_block;
+    if (i1 > items) i1 = items;
+    for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const int v = (int)(i % V8);
+        const long long po = i / V8;
+        const int wo = (int)(po % p.Wo);
+        const int ho = (int)(po / p.Wo);
+        const int c = v << 3;
+        const float* src;
+        int ldc, cc;
+        if (c < p.C0) { src = p.x0; ldc = p.C0; cc = c; } else { src = p.x1; ldc = p.C1; cc = c - p.C0; }
+        float y[8], raw[8];
+        if (p.resample == NDB_RESAMPLE_DOWN2) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) y[k] = raw[k] = 0.f;
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const float* px = src + (((size_t)n * p.H + (2 * ho + dy)) * p.W + (2 * wo + dx)) * ldc + cc;
+                    const float4 lo = __ldg(reinterpret_cast<const float4*>(px));
+                    const float4 hi = __ldg(reinterpret_cast<const float4*>(px + 4));
+                    const float xv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        float t = sa[c + k] * xv[k] + sb[c + k];
+                        if (p.silu) t = silu_f(t);
+                        y[k] += t;
+                        raw[k] += xv[k] + sp[c + k];
+                    }
+                }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { y[k] *= 0.25f; raw[k] *= 0.25f; }
+        } else {
+            const int hi_ = (p.resample == NDB_RESAMPLE_UP2) ? (ho >> 1) : ho;
+            const int wi_ = (p.resample == NDB_RESAMPLE_UP2) ? (wo >> 1) : wo;
+            const float* px = src + (((size_t)n * p.H + hi_) * p.W + wi_) * ldc + cc;
+            const float4 lo = __ldg(reinterpret_cast<const float4*>(px));
+            const float4 hi = __ldg(reinterpret_cast<const float4*>(px + 4));
+            const float xv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float t = sa[c + k] * xv[k] + sb[c + k];
+                if (p.silu) t = silu_f(t);
+                y[k] = t;
+                raw[k] = xv[k] + sp[c + k];
+            }
+        }
+        const size_t o = (((size_t)n * p.Ho + ho) * p.Wo + wo) * C + c;
+        *reinterpret_cast<uint4*>(p.out + o) =
+            make_uint4(pack2h<FMT>(y[0], y[1]), pack2h<FMT>(y[2], y[3]), pack2h<FMT>(y[4], y[5]), pack2h<FMT>(y[6], y[7]));
+        if (p.raw16 != nullptr)
+            *reinterpret_cast<uint4*>(p.raw16 + o) = make_uint4(pack2h<FMT>(raw[0], raw[1]), pack2h<FMT>(raw[2], raw[3]),
+                                                                pack2h<FMT>(raw[4], raw[5]), pack2h<FMT>(raw[6], raw[7]));
+    }
+}
+
+}  // namespace ndb
+
+using namespace ndb;
+
+extern "C" int ndb_gn_stats(const float* x0, int C0, const float* x1, int C1, int N, int HW, const float* pre_add,
+                            int ld_pre, double* stats, void* stream) {
+    NDB_CHECK_ARG(x0 && stats && N > 0 && HW > 0);
+    if (x1 == nullptr) C1 = 0;
+    const int C = C0 + C1;
+    NDB_CHECK_ARG(C % kGroups == 0 && C0 % 4 == 0 && C1 % 4 == 0);
+    const int V = C / 4;
+    NDB_CHECK_ARG(V <= kMaxVecPerThread * kGnThreads);
+    int threads_per_row = V < kGnThreads ? V : kGnThreads;
+    int rows_per_block = kGnThreads / threads_per_row;
+    // enough blocks to fill the machine, but at least ~8 pixels per row-slot
+    int target_blocks_per_sample = (4 * num_sms() + N - 1) / N;
+    if (target_blocks_per_sample < 1) target_blocks_per_sample = 1;
+    int pix_per_block = (HW + target_blocks_per_sample - 1) / target_blocks_per_sample;
+    const int min_pix = rows_per_block * 8;
+    if (pix_per_block < min_pix) pix_per_block = min_pix;
+    const int chunks = (HW + pix_per_block - 1) / pix_per_block;
+    dim3 grid(chunks, N);
+    gn_stats_kernel<<<grid, kGnThreads, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+        x0, C0, x1, C1, HW, pre_add, ld_pre, stats, pix_per_block, threads_per_row, rows_per_block);
+    return launch_status("ndb_gn_stats");
+}
+
+extern "C" int ndb_gn_apply(const ndb_gn_apply_params* q, void* stream) {
+    NDB_CHECK_ARG(q && q->x0 && q->stats && q->gamma && q->beta && q->out);
+    GnApplyArgs a{};
+    a.x0 = q->x0; a.C0 = q->C0;
+    a.x1 = q->x1; a.C1 = q->x1 ? q->C1 : 0;
+    const int C = a.C0 + a.C1;
+    NDB_CHECK_ARG(C % kGroups == 0 && a.C0 % 8 == 0 && a.C1 % 8 == 0);
+    NDB_CHECK_ARG((q->scale == nullptr) == (q->shift == nullptr));
+    a.N = q->N; a.H = q->H; a.W = q->W;
+    a.Ho = q->H; a.Wo = q->W;
+    if (q->resample == NDB_RESAMPLE_UP2) { a.Ho = 2 * q->H; a.Wo = 2 * q->W; }
+    if (q->resample == NDB_RESAMPLE_DOWN2) {
+        NDB_CHECK_ARG(q->H % 2 == 0 && q->W % 2 == 0);
+        a.Ho = q->H / 2; a.Wo = q->W / 2;
+    }
+    a.stats = q->stats; a.gamma = q->gamma; a.beta = q->beta;
+    a.scale = q->scale; a.shift = q->shift; a.ld_ss = q->ld_ss;
+    a.pre_add = q->pre_add; a.ld_pre = q->ld_pre;
+    a.silu = q->silu; a.resample = q->resample;
+    a.out = (uint16_t*)q->out; a.raw16 = (uint16_t*)q->raw16;
+    a.eps = q->eps;
+    const long long items = (long long)a.Ho * a.Wo * (C / 8);
+    int blocks_per_sample = (8 * num_sms() + q->N - 1) / q->N;
+    long long ipb = (items + blocks_per_sample - 1) / blocks_per_sample;
+    const long long min_items = 4LL * kGnThreads;
+    if (ipb < min_items) ipb = min_items;
+    a.items_per_block = (int)ipb;
+    const int chunks = (int)((items + ipb - 1) / ipb);
+    dim3 grid(chunks, q->N);
+    const size_t smem = 3 * (size_t)C * sizeof(float);
+    if (q->operand_format == 0)
+        gn_apply_kernel<0><<<grid, kGnThreads, smem, (cudaStream_t)stream>>>(a);
+    else
+        gn_apply_kernel<1><<<grid, kGnThreads, smem, (cudaStream_t)stream>>>(a);
+    return launch_status("ndb_gn_apply");
+}

@@ -1,0 +1,216 @@
+"""`DiffusionModel` -- drop-in for nicediffusion.model.DiffusionModel (reference model.py:294-476) whose forward
+pass runs entirely on hand-written sm_100a kernels (libndb200.so).
+
+What is mirrored from the reference:
+  * constructor signature and defaults (model.py:322-340), attributes `.conditional .num_classes .in_channels
+    .resolution .model_channels`;
+  * the parameter tree / state-dict schema (`step_embed.{0,2}`, `class_embedding`, `downsampling.i.j.*`,
+    `middle_block.k.*`, `upsampling.i.j.*`, `out.{0,2}`; ResBlock: skip, in_norm, in_conv, out_norm, out_conv,
+    step_embedding; attention: qkv_nin, norm, proj_out), default initialisation (torch's layer defaults +
+    zero-initialised out_conv / proj_out / head conv, model.py:177,253,448,507-510);
+  * `forward(x, timestep, y=None)`: NCHW fp32 in, `[B,out_channels,H,W]` fp32 out, the same two AssertionErrors.
+
+What is different: torch layers below are *parameter containers only* -- their forward is never called.
+`forward` executes a static plan of ndb200 kernels (NHWC, fp16 tensor-core operands, fp32 accumulate / residual
+stream), captured into a CUDA graph per batch size. Parameters are snapshotted into a packed weight arena; the
+snapshot is refreshed automatically when any parameter's storage or version changes (load_state_dict, EMA
+`param.data` swap of diffusion.py:185-189, optimizer steps).
+There is no CPU / eager fallback: calling forward on a CPU tensor raises.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+
+
+class UsesSteps(nn.Module):
+    """Marker base class (model.py:31-36): children that take the step embedding."""
+
+
+class UsesStepsSequential(nn.Sequential, UsesSteps):
+    """Container with the reference's name (model.py:40-48); only used for the state-dict structure."""
+
+
+def zero_module(module):
+    """model.py:507-510."""
+    for p in module.parameters():
+        p.detach().zero_()
+    return module
+
+
+def timestep_embedding_freqs(embedding_dim, max_period=10000):
+    """Frequency vector of model.py:515-517, built on the CPU in fp32 exactly like the reference."""
+    half = embedding_dim // 2
+    return torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(max_period) / half))
+
+
+class Upsample(nn.Module):
+    """Parameter container for model.py:51-80."""
+
+    def __init__(self, in_channels, with_conv, out_channels=None):
+        super().__init__()
+        self.with_conv = with_conv
+        if with_conv:
+            self.conv = nn.Conv2d(in_channels, out_channels if out_channels is not None else in_channels,
+                                  kernel_size=(3, 3), stride=(1, 1), padding=(1, 1))
+
+
+class Downsample(nn.Module):
+    """Parameter container for model.py:83-112."""
+
+    def __init__(self, in_channels, with_conv, out_channels=None):
+        super().__init__()
+        self.with_conv = with_conv
+        if with_conv:
+            self.conv = nn.Conv2d(in_channels, out_channels if out_channels is not None else in_channels,
+                                  kernel_size=(3, 3), stride=(2, 2), padding=(1, 1))
+
+
+class ResidualBlock(UsesSteps):
+    """Parameter container for model.py:117-211 (same attribute names and registration order)."""
+
+    def __init__(self, in_channels, step_channels, dropout, upsample=False, downsample=False, use_conv=False,
+                 out_channels=None, use_adaptive_gn=False, use_grad_checkpoints=False):
+        super().__init__()
+        out_channels = out_channels if out_channels is not None else in_channels
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.use_adaptive_gn = use_adaptive_gn
+        self.mode = 'up' if upsample else ('down' if downsample else 'same')
+        if out_channels == in_channels:
+            self.skip = nn.Identity()
+        elif use_conv:
+            self.skip = nn.Conv2d(in_channels, out_channels, kernel_size=(3, 3), stride=(1, 1), padding=(1, 1))
+        else:
+            self.skip = nn.Conv2d(in_channels, out_channels, kernel_size=(1, 1), stride=(1, 1))
+        self.in_norm = nn.GroupNorm(num_groups=32, num_channels=in_channels, eps=1e-5)
+        self.in_conv = nn.Conv2d(in_channels, out_channels, kernel_size=(3, 3), stride=(1, 1), padding=(1, 1))
+        self.out_norm = nn.GroupNorm(num_groups=32, num_channels=out_channels, eps=1e-5)
+        self.out_conv = zero_module(nn.Conv2d(out_channels, out_channels, kernel_size=(3, 3), stride=(1, 1),
+                                              padding=(1, 1)))
+        self.step_embedding = nn.Linear(step_channels, 2 * out_channels if use_adaptive_gn else out_channels)
+
+
+class AttentionBlock(nn.Module):
+    """Parameter container for model.py:214-291."""
+
+    def __init__(self, channels, num_heads=1, num_head_channels=None, split_qkv_first=True):
+        super().__init__()
+        if num_head_channels is None:
+            self.num_heads = num_heads
+        else:
+            assert channels % num_head_channels == 0, \
+                "channels {} is not divisible by num_head_channels {}".format(channels, num_head_channels)
+            self.num_heads = channels // num_head_channels
+        self.channels = channels
+        self.split_qkv_first = split_qkv_first
+        self.qkv_nin = nn.Conv1d(channels, 3 * channels, kernel_size=(1,), stride=(1,))
+        self.norm = nn.GroupNorm(num_groups=32, num_channels=channels, eps=1e-5)
+        self.proj_out = zero_module(nn.Conv1d(channels, channels, kernel_size=(1,), stride=(1,)))
+
+
+class DiffusionModel(nn.Module):
+    def __init__(self, resolution, in_channels, model_channels, out_channels, num_res_blocks,
+                 attention_resolutions, dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True,
+                 num_classes=None, num_heads=1, num_head_channels=None, resblock_updown=False,
+                 use_adaptive_gn=False, split_qkv_first=True, use_grad_checkpoints=False):
+        super().__init__()
+        self.resolution = resolution
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        step_embed_dim = 4 * model_channels
+        self.model_channels = model_channels
+        self.use_adaptive_gn = use_adaptive_gn
+        self.step_embed = nn.Sequential(nn.Linear(model_channels, step_embed_dim), nn.SiLU(),
+                                        nn.Linear(step_embed_dim, step_embed_dim))
+        if num_classes is not None:
+            self.class_embedding = nn.Embedding(num_classes, embedding_dim=step_embed_dim)
+            self.conditional = True
+            self.num_classes = num_classes
+        else:
+            self.conditional = False
+            self.num_classes = None
+
+        def res(cin, cout, **kw):
+            return ResidualBlock(in_channels=cin, step_channels=step_embed_dim, dropout=dropout, out_channels=cout,
+                                 use_adaptive_gn=use_adaptive_gn, use_grad_checkpoints=use_grad_checkpoints, **kw)
+
+        def attn(c):
+            return AttentionBlock(channels=c, split_qkv_first=split_qkv_first, num_heads=num_heads,
+                                  num_head_channels=num_head_channels)
+
+        cur = first = int(model_channels * channel_mult[0])
+        cur_res = resolution
+        self.downsampling = nn.ModuleList([UsesStepsSequential(
+            nn.Conv2d(in_channels, cur, kernel_size=(3, 3), stride=(1, 1), padding=(1, 1)))])
+        chans = [cur]
+        for level, mult in enumerate(channel_mult):
+            for _ in range(num_res_blocks):
+                layers = [res(cur, int(model_channels * mult))]
+                cur = int(model_channels * mult)
+                if cur_res in attention_resolutions:
+                    layers.append(attn(cur))
+                chans.append(cur)
+                self.downsampling.append(UsesStepsSequential(*layers))
+            cur = int(model_channels * mult)
+            if level != len(channel_mult) - 1:
+                if resblock_updown:
+                    self.downsampling.append(UsesStepsSequential(res(cur, cur, downsample=True)))
+                else:
+                    self.downsampling.append(UsesStepsSequential(
+                        Downsample(in_channels=cur, out_channels=cur, with_conv=conv_resample)))
+                chans.append(cur)
+                cur_res //= 2
+        self.middle_block = UsesStepsSequential(res(cur, cur), attn(cur), res(cur, cur))
+        self.upsampling = nn.ModuleList([])
+        for level, mult in list(enumerate(channel_mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                skip_channels = chans.pop()
+                layers = [res(cur + skip_channels, int(model_channels * mult))]
+                cur = int(model_channels * mult)
+                if cur_res in attention_resolutions:
+                    layers.append(attn(cur))
+                if level != 0 and i == num_res_blocks:
+                    if resblock_updown:
+                        layers.append(res(cur, cur, upsample=True))
+                    else:
+                        layers.append(Upsample(in_channels=cur, out_channels=cur, with_conv=conv_resample))
+                    cur_res *= 2
+                self.upsampling.append(UsesStepsSequential(*layers))
+        self.out = nn.Sequential(nn.GroupNorm(num_groups=32, num_channels=cur), nn.SiLU(),
+                                 zero_module(nn.Conv2d(first, out_channels, kernel_size=(3, 3), stride=(1, 1),
+                                                       padding=(1, 1))))
+        # engine state (not part of the state dict)
+        self.operand_format = L.FMT_FP16
+        self.use_cuda_graph = True
+        self._engines = {}
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, x, timestep, y=None):
+        assert (y is not None) == self.conditional, 'pass y iff class-conditional model'
+        assert x.shape[2] == self.resolution and x.shape[3] == self.resolution, \
+            'incorrect resolution: {}'.format(x.shape[2:])
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError('ndb200 implements the sampling (inference) forward only; '
+                                      'call model.eval() / torch.no_grad()')
+        return self.engine_for(x).forward(x, timestep, y)
+
+    def engine_for(self, x):
+        from .engine import UNetEngine
+        L.require_device(x, 'DiffusionModel.forward')
+        key = (x.device.index, x.shape[0])
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = UNetEngine(self, x.shape[0], x.device)
+            self._engines[key] = eng
+        return eng
+
+    def release_engines(self):
+        """Drop cached plans / CUDA graphs / packed weights (e.g. before moving the model)."""
+        self._engines = {}
+
+    def _apply(self, fn, *a, **k):
+        self._engines = {}
+        return super()._apply(fn, *a, **k)

@@ -1,0 +1,270 @@
+"""Tensor-level wrappers of the ndb200 kernels: allocate outputs with torch (device memory + stream plumbing
+only), pass raw pointers through ctypes. Every function launches exactly one CUDA kernel of this library
+on the current stream; `LAUNCHES` counts them (bench.py reports it as gpu_launches).
+
+Layouts: activations NHWC. `*16` tensors are 16-bit tensor-core operands (torch.float16 by default,
+torch.bfloat16 when fmt == FMT_BF16).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+LAUNCHES = 0
+
+
+def _count():
+    global LAUNCHES
+    LAUNCHES += 1
+
+
+def dtype16(fmt):
+    return torch.float16 if fmt == L.FMT_FP16 else torch.bfloat16
+
+
+def pad16(n):
+    return (n + 15) // 16 * 16
+
+
+def pack_conv_weight(w, cout_pad=None, cin_off=0, cin_len=None, fmt=L.FMT_FP16, out=None):
+    """nn.Conv2d / Conv1d / Linear weight (fp32, [cout, cin, k, k] | [cout, cin, 1] | [cout, cin]) ->
+    [taps][cout_pad][cin_len] 16-bit."""
+    L.require_device(w, 'pack_conv_weight')
+    w = w.detach().contiguous().float()
+    cout, cin = w.shape[0], w.shape[1]
+    k = w.shape[2] if w.dim() >= 3 else 1
+    if w.dim() == 4:
+        assert w.shape[2] == w.shape[3]
+    cout_pad = pad16(cout) if cout_pad is None else cout_pad
+    cin_len = cin - cin_off if cin_len is None else cin_len
+    if out is None:
+        out = torch.empty((k * k, cout_pad, cin_len), dtype=dtype16(fmt), device=w.device)
+    L.check(L.load().ndb_pack_conv_weight(L.ptr(w), L.ptr(out), cout, cin, k, cout_pad, cin_off, cin_len, fmt,
+                                          L.stream_ptr()), 'ndb_pack_conv_weight')
+    _count()
+    return out
+
+
+def conv_gemm(segments, N, H, W, cout, bias=None, residual=None, residual_mode=L.RES_NONE,
+              out_kind=L.OUT_F32_NHWC, out=None, fmt=L.FMT_FP16, block_n=0, cout_pad=None):
+    """segments: list of (act16 [N,H,W,C], packed_weight [taps,cout_pad,C]).  Returns `out`."""
+    p = L.ConvParams()
+    p.N, p.H, p.W = N, H, W
+    p.cout = cout
+    p.cout_pad = segments[0][1].shape[1] if cout_pad is None else cout_pad
+    p.num_segments = len(segments)
+    assert 1 <= len(segments) <= L.MAX_SEGMENTS
+    dev = segments[0][0].device
+    for i, (a, w) in enumerate(segments):
+        L.require_device(a, 'conv_gemm')
+        assert a.dtype == dtype16(fmt) and w.dtype == dtype16(fmt)
+        assert a.is_contiguous() and w.is_contiguous()
+        assert w.shape[1] == p.cout_pad and w.shape[2] == a.shape[-1], (w.shape, a.shape)
+        p.seg[i].act = a.data_ptr()
+        p.seg[i].weight = w.data_ptr()
+        p.seg[i].C = a.shape[-1]
+        p.seg[i].taps = w.shape[0]
+    p.bias = bias.data_ptr() if bias is not None else None
+    p.residual = residual.data_ptr() if residual is not None else None
+    p.residual_mode = residual_mode if residual is not None else L.RES_NONE
+    p.out_kind = out_kind
+    if out is None:
+        if out_kind == L.OUT_F32_NHWC:
+            out = torch.empty((N, H, W, cout), dtype=torch.float32, device=dev)
+        elif out_kind == L.OUT_F16_NHWC:
+            out = torch.empty((N, H, W, cout), dtype=dtype16(fmt), device=dev)
+        else:
+            out = torch.empty((N, cout, H, W), dtype=torch.float32, device=dev)
+    p.out = out.data_ptr()
+    p.operand_format = fmt
+    p.block_n = block_n
+    p.gn_stats = None
+    L.check(L.load().ndb_conv_gemm(C.byref(p), L.stream_ptr()), 'ndb_conv_gemm')
+    _count()
+    return out
+
+
+def gn_stats(x0, x1=None, pre_add=None, stats=None):
+    """x0 [N,H,W,C0] (+ x1 [N,H,W,C1]) fp32 -> fp64 [N,32,2] (sum, sumsq). `stats` must be zeroed."""
+    L.require_device(x0, 'gn_stats')
+    N = x0.shape[0]
+    HW = x0.shape[1] * x0.shape[2]
+    if stats is None:
+        stats = torch.zeros((N, 32, 2), dtype=torch.float64, device=x0.device)
+    L.check(L.load().ndb_gn_stats(L.ptr(x0), x0.shape[-1], L.ptr(x1), x1.shape[-1] if x1 is not None else 0, N, HW,
+                                  L.ptr(pre_add), pre_add.stride(0) if pre_add is not None else 0,
+                                  L.ptr(stats), L.stream_ptr()), 'ndb_gn_stats')
+    _count()
+    return stats
+
+
+def gn_apply(x0, stats, gamma, beta, x1=None, scale=None, shift=None, pre_add=None, silu=True,
+             resample=L.RESAMPLE_NONE, out=None, raw16=None, want_raw16=False, fmt=L.FMT_FP16, eps=1e-5):
+    L.require_device(x0, 'gn_apply')
+    N, H, W, C0 = x0.shape
+    C1 = x1.shape[-1] if x1 is not None else 0
+    Ho, Wo = H, W
+    if resample == L.RESAMPLE_UP2:
+        Ho, Wo = 2 * H, 2 * W
+    elif resample == L.RESAMPLE_DOWN2:
+        Ho, Wo = H // 2, W // 2
+    if out is None:
+        out = torch.empty((N, Ho, Wo, C0 + C1), dtype=dtype16(fmt), device=x0.device)
+    if want_raw16 and raw16 is None:
+        raw16 = torch.empty_like(out)
+    p = L.GnApplyParams()
+    p.x0, p.C0 = x0.data_ptr(), C0
+    p.x1, p.C1 = (x1.data_ptr() if x1 is not None else None), C1
+    p.N, p.H, p.W = N, H, W
+    p.stats = stats.data_ptr()
+    p.gamma, p.beta = gamma.data_ptr(), beta.data_ptr()
+    if scale is not None:
+        assert scale.stride(0) == shift.stride(0) and scale.stride(1) == 1
+        p.scale, p.shift, p.ld_ss = scale.data_ptr(), shift.data_ptr(), scale.stride(0)
+    if pre_add is not None:
+        p.pre_add, p.ld_pre = pre_add.data_ptr(), pre_add.stride(0)
+    p.silu = 1 if silu else 0
+    p.resample = resample
+    p.out = out.data_ptr()
+    p.raw16 = raw16.data_ptr() if raw16 is not None else None
+    p.operand_format = fmt
+    p.eps = eps
+    L.check(L.load().ndb_gn_apply(C.byref(p), L.stream_ptr()), 'ndb_gn_apply')
+    _count()
+    return (out, raw16) if (want_raw16 or raw16 is not None) else out
+
+
+def attention(qkv16, B, T, heads, d, order=0, out=None, fmt=L.FMT_FP16):
+    """qkv16 [B,T,3C] -> [B,T,C]."""
+    L.require_device(qkv16, 'attention')
+    assert qkv16.is_contiguous() and qkv16.dtype == dtype16(fmt)
+    if out is None:
+        out = torch.empty((B, T, heads * d), dtype=qkv16.dtype, device=qkv16.device)
+    L.check(L.load().ndb_attention(L.ptr(qkv16), L.ptr(out), B, T, heads, d, order, fmt, L.stream_ptr()),
+            'ndb_attention')
+    _count()
+    return out
+
+
+def embed(t, y, freqs, w0, b0, w2, b2, class_emb, emb_out=None, act_out=None, fmt=L.FMT_FP16):
+    L.require_device(t, 'embed')
+    B = t.shape[0]
+    mc = w0.shape[1]
+    E = 4 * mc
+    assert t.dtype == torch.float32 and (y is None or y.dtype == torch.int64)
+    if emb_out is None:
+        emb_out = torch.empty((B, E), dtype=torch.float32, device=t.device)
+    if act_out is None:
+        act_out = torch.empty((B, E), dtype=dtype16(fmt), device=t.device)
+    L.check(L.load().ndb_embed(L.ptr(t), L.ptr(y), L.ptr(freqs), B, mc, L.ptr(w0), L.ptr(b0), L.ptr(w2), L.ptr(b2),
+                               L.ptr(class_emb) if y is not None else None, L.ptr(emb_out), L.ptr(act_out), fmt,
+                               L.stream_ptr()), 'ndb_embed')
+    _count()
+    return emb_out, act_out
+
+
+def stem_conv(x_nchw, w, bias, out=None):
+    L.require_device(x_nchw, 'stem_conv')
+    N, Cin, H, W = x_nchw.shape
+    Cout = w.shape[0]
+    if out is None:
+        out = torch.empty((N, H, W, Cout), dtype=torch.float32, device=x_nchw.device)
+    L.check(L.load().ndb_stem_conv(L.ptr(x_nchw), L.ptr(w), L.ptr(bias), L.ptr(out), N, Cin, H, W, Cout,
+                                   L.stream_ptr()), 'ndb_stem_conv')
+    _count()
+    return out
+
+
+def resample_f32(x, mode, out=None):
+    N, H, W, Cc = x.shape
+    Ho, Wo = (2 * H, 2 * W) if mode == L.RESAMPLE_UP2 else (H // 2, W // 2)
+    if out is None:
+        out = torch.empty((N, Ho, Wo, Cc), dtype=torch.float32, device=x.device)
+    L.check(L.load().ndb_resample_f32(L.ptr(x), L.ptr(out), N, H, W, Cc, mode, L.stream_ptr()), 'ndb_resample_f32')
+    _count()
+    return out
+
+
+def cast16(x, out=None, fmt=L.FMT_FP16):
+    if out is None:
+        out = torch.empty(x.shape, dtype=dtype16(fmt), device=x.device)
+    L.check(L.load().ndb_cast_nhwc16(L.ptr(x), L.ptr(out), x.numel(), fmt, L.stream_ptr()), 'ndb_cast_nhwc16')
+    _count()
+    return out
+
+
+def im2col_s2(x, out=None, fmt=L.FMT_FP16):
+    N, H, W, Cc = x.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    if out is None:
+        out = torch.empty((9, N, Ho, Wo, Cc), dtype=dtype16(fmt), device=x.device)
+    L.check(L.load().ndb_im2col_s2(L.ptr(x), L.ptr(out), N, H, W, Cc, fmt, L.stream_ptr()), 'ndb_im2col_s2')
+    _count()
+    return out
+
+
+def sampler_step(x_t, model_out, t, tables, var_type, ddim=False, eta=0.0, null_out=None, cfg_strength=0.0,
+                 grad=None, clf_strength=0.0, clip_x0=True, noise=None, seed=0, sample_ids=None,
+                 x_prev=None, pred_x0=None):
+    L.require_device(x_t, 'sampler_step')
+    B, Cc, H, W = x_t.shape
+    p = L.StepParams()
+    assert x_t.is_contiguous() and model_out.is_contiguous() and t.dtype == torch.float32
+    assert tables.dtype == torch.float32 and tables.shape[0] == L.TAB_COUNT and tables.is_contiguous()
+    p.x_t, p.model_out = x_t.data_ptr(), model_out.data_ptr()
+    p.null_out = null_out.data_ptr() if null_out is not None else None
+    p.t, p.tables = t.data_ptr(), tables.data_ptr()
+    p.R = tables.shape[1]
+    p.B, p.C, p.HW, p.Cm = B, Cc, H * W, model_out.shape[1]
+    p.var_type = var_type
+    p.ddim = 1 if ddim else 0
+    p.eta = float(eta)
+    p.cfg_strength = float(cfg_strength)
+    p.grad = grad.data_ptr() if grad is not None else None
+    p.clf_strength = float(clf_strength)
+    p.clip_x0 = 1 if clip_x0 else 0
+    p.noise = noise.data_ptr() if noise is not None else None
+    p.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    p.sample_ids = sample_ids.data_ptr() if sample_ids is not None else None
+    if x_prev is None:
+        x_prev = torch.empty_like(x_t)
+    p.x_prev = x_prev.data_ptr()
+    p.pred_x0 = pred_x0.data_ptr() if pred_x0 is not None else None
+    L.check(L.load().ndb_sampler_step(C.byref(p), L.stream_ptr()), 'ndb_sampler_step')
+    _count()
+    return x_prev
+
+
+def philox_normal(shape, seed, sample_ids, step, device, out=None):
+    B = shape[0]
+    per = 1
+    for s in shape[1:]:
+        per *= s
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=device)
+    L.check(L.load().ndb_philox_normal(L.ptr(out), B, per, int(seed) & 0xFFFFFFFFFFFFFFFF, L.ptr(sample_ids), step,
+                                       L.stream_ptr()), 'ndb_philox_normal')
+    _count()
+    return out
+
+
+def qsample(x0, noise, t, sqrt_abar, sqrt_1m_abar, out=None):
+    L.require_device(x0, 'qsample')
+    B = x0.shape[0]
+    per = x0.numel() // B
+    if out is None:
+        out = torch.empty_like(x0)
+    L.check(L.load().ndb_qsample(L.ptr(x0), L.ptr(noise), L.ptr(t), L.ptr(sqrt_abar), L.ptr(sqrt_1m_abar),
+                                 L.ptr(out), B, per, L.stream_ptr()), 'ndb_qsample')
+    _count()
+    return out
+
+
+def to_uint8(x_nchw, out=None):
+    B, Cc, H, W = x_nchw.shape
+    if out is None:
+        out = torch.empty((B, H, W, Cc), dtype=torch.uint8, device=x_nchw.device)
+    L.check(L.load().ndb_to_uint8(L.ptr(x_nchw), L.ptr(out), B, Cc, H, W, L.stream_ptr()), 'ndb_to_uint8')
+    _count()
+    return out

@@ -1,0 +1,244 @@
+"""GPU parity of every ndb200 kernel against the torch op(s) of the reference it replaces (fp32, TF32 off).
+
+Tolerances: tensor-core kernels take fp16 operands with fp32 accumulation, so they are compared against the
+same torch op fed with the fp16-rounded operands (tight bound: accumulation order only) and against the
+un-rounded fp32 op (loose bound: operand rounding, 2^-11 relative per operand).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from nice_diffusion_b200 import ops, _lib
+    return ops, _lib
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def rel_err(a, b):
+    return float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30))
+
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, k
+    (2, 64, 64, 64, 64, 3),
+    (2, 32, 32, 128, 192, 3),
+    (3, 16, 16, 192, 384, 3),
+    (5, 8, 8, 256, 256, 3),
+    (2, 28, 28, 64, 64, 3),
+    (3, 14, 14, 128, 128, 3),
+    (5, 7, 7, 256, 256, 3),
+    (2, 32, 32, 192, 576, 1),
+    (1, 64, 64, 192, 6, 3),
+    (1, 128, 128, 64, 64, 3),
+    (1, 4, 256, 64, 64, 3),
+]
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout,k', CONV_CASES)
+def test_conv_gemm_vs_conv2d(cuda_dev, N, H, W, Cin, Cout, k):
+    ops, L = _ops()
+    g = torch.Generator(device='cpu').manual_seed(N * 1000 + H + Cin + Cout)
+    x = torch.randn(N, Cin, H, W, generator=g).to(cuda_dev)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)).to(cuda_dev)
+    b = (0.1 * torch.randn(Cout, generator=g)).to(cuda_dev)
+    x16 = nhwc(x).half()
+    wp = ops.pack_conv_weight(w)
+    out = ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b)
+    torch.cuda.synchronize()
+    ref16 = F.conv2d(x.half().float(), w.half().float(), b, padding=k // 2)
+    ref32 = F.conv2d(x, w, b, padding=k // 2)
+    got = out.permute(0, 3, 1, 2)
+    assert rel_err(got, ref16) < 2e-5, 'accumulation mismatch'
+    assert rel_err(got, ref32) < 3e-3
+
+
+def test_conv_gemm_outputs_and_residuals(cuda_dev):
+    ops, L = _ops()
+    g = torch.Generator(device='cpu').manual_seed(5)
+    N, H, W, Cin, Cout = 2, 16, 16, 128, 192
+    x = torch.randn(N, Cin, H, W, generator=g).to(cuda_dev)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)).to(cuda_dev)
+    b = (0.1 * torch.randn(Cout, generator=g)).to(cuda_dev)
+    x16 = nhwc(x).half()
+    wp = ops.pack_conv_weight(w)
+    base = F.conv2d(x.half().float(), w.half().float(), b, padding=1)
+    # same-size residual
+    r = torch.randn(N, Cout, H, W, generator=g).to(cuda_dev)
+    out = ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, residual=nhwc(r), residual_mode=L.RES_SAME)
+    assert rel_err(out.permute(0, 3, 1, 2), base + r) < 2e-5
+    # nearest-up residual (x_resample of an up ResBlock)
+    r = torch.randn(N, Cout, H // 2, W // 2, generator=g).to(cuda_dev)
+    out = ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, residual=nhwc(r), residual_mode=L.RES_UP2)
+    assert rel_err(out.permute(0, 3, 1, 2), base + F.interpolate(r, scale_factor=2.0, mode='nearest')) < 2e-5
+    # avg-pool residual (x_resample of a down ResBlock)
+    r = torch.randn(N, Cout, 2 * H, 2 * W, generator=g).to(cuda_dev)
+    out = ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, residual=nhwc(r), residual_mode=L.RES_DOWN2)
+    assert rel_err(out.permute(0, 3, 1, 2), base + F.avg_pool2d(r, 2)) < 2e-5
+    # fp16 NHWC and fp32 NCHW outputs
+    out = ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, out_kind=L.OUT_F16_NHWC)
+    assert rel_err(out.permute(0, 3, 1, 2), base) < 1e-3
+    out = ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, out_kind=L.OUT_F32_NCHW)
+    assert rel_err(out, base) < 2e-5
+    # forced small N tile (more tiles than SMs -> persistent loop, both TMEM accumulator stages)
+    out = ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, block_n=32)
+    assert rel_err(out.permute(0, 3, 1, 2), base) < 2e-5
+
+
+def test_conv_gemm_segments_fuse_concat_and_skip(cuda_dev):
+    """out_conv(a2) + skip_1x1(cat(xa, xb)) as one GEMM with three K segments (model.py:209-211,474)."""
+    ops, L = _ops()
+    g = torch.Generator(device='cpu').manual_seed(11)
+    N, H, W, Ca, Cb, Cout = 2, 16, 16, 128, 64, 128
+    a2 = torch.randn(N, Cout, H, W, generator=g).to(cuda_dev)
+    xa = torch.randn(N, Ca, H, W, generator=g).to(cuda_dev)
+    xb = torch.randn(N, Cb, H, W, generator=g).to(cuda_dev)
+    w_out = (torch.randn(Cout, Cout, 3, 3, generator=g) / math.sqrt(Cout * 9)).to(cuda_dev)
+    w_skip = (torch.randn(Cout, Ca + Cb, 1, 1, generator=g) / math.sqrt(Ca + Cb)).to(cuda_dev)
+    b = (0.1 * torch.randn(Cout, generator=g)).to(cuda_dev)
+    segs = [(nhwc(a2).half(), ops.pack_conv_weight(w_out)),
+            (nhwc(xa).half(), ops.pack_conv_weight(w_skip, cin_off=0, cin_len=Ca)),
+            (nhwc(xb).half(), ops.pack_conv_weight(w_skip, cin_off=Ca, cin_len=Cb))]
+    out = ops.conv_gemm(segs, N, H, W, Cout, bias=b)
+    ref = F.conv2d(a2.half().float(), w_out.half().float(), b, padding=1) + \
+        F.conv2d(torch.cat([xa, xb], 1).half().float(), w_skip.half().float())
+    assert rel_err(out.permute(0, 3, 1, 2), ref) < 2e-5
+
+
+def test_linear_as_gemm(cuda_dev):
+    """The per-ResBlock step_embedding Linear layers run as one 1x1 'conv' over a [1,1,B,E] image."""
+    ops, L = _ops()
+    g = torch.Generator(device='cpu').manual_seed(3)
+    B, E, O = 6, 256, 1184
+    a = torch.randn(B, E, generator=g).to(cuda_dev)
+    w = (torch.randn(O, E, generator=g) / math.sqrt(E)).to(cuda_dev)
+    b = torch.randn(O, generator=g).to(cuda_dev)
+    out = ops.conv_gemm([(a.half().view(1, 1, B, E), ops.pack_conv_weight(w))], 1, 1, B, O, bias=b)
+    ref = F.linear(a.half().float(), w.half().float(), b)
+    assert rel_err(out.view(B, O), ref) < 2e-5
+
+
+GN_CASES = [(2, 16, 16, 64, 0), (3, 8, 8, 192, 0), (2, 32, 32, 384, 0), (2, 16, 16, 768, 576), (2, 28, 28, 128, 64),
+            (1, 8, 8, 1536, 0)]
+
+
+@pytest.mark.parametrize('N,H,W,C0,C1', GN_CASES)
+@pytest.mark.parametrize('resample', [0, 1, 2])
+def test_groupnorm_apply(cuda_dev, N, H, W, C0, C1, resample):
+    ops, L = _ops()
+    g = torch.Generator(device='cpu').manual_seed(C0 + C1 + H)
+    C = C0 + C1
+    x0 = (torch.randn(N, C0, H, W, generator=g) * 2 + 0.5).to(cuda_dev)
+    x1 = (torch.randn(N, C1, H, W, generator=g) * 0.5 - 1).to(cuda_dev) if C1 else None
+    gamma = (1 + 0.1 * torch.randn(C, generator=g)).to(cuda_dev)
+    beta = (0.1 * torch.randn(C, generator=g)).to(cuda_dev)
+    ss = (0.3 * torch.randn(N, 2 * C, generator=g)).to(cuda_dev)
+    scale, shift = ss[:, :C], ss[:, C:]
+    xin = torch.cat([x0, x1], 1) if C1 else x0
+    stats = ops.gn_stats(nhwc(x0), nhwc(x1) if C1 else None)
+    out, raw = ops.gn_apply(nhwc(x0), stats, gamma, beta, x1=nhwc(x1) if C1 else None, scale=scale, shift=shift,
+                            silu=True, resample=resample, want_raw16=True)
+    ref = F.silu(F.group_norm(xin, 32, gamma, beta, eps=1e-5) * (1 + scale[:, :, None, None]) + shift[:, :, None, None])
+    rraw = xin
+    if resample == 1:
+        ref, rraw = F.interpolate(ref, scale_factor=2.0, mode='nearest'), F.interpolate(xin, scale_factor=2.0, mode='nearest')
+    elif resample == 2:
+        ref, rraw = F.avg_pool2d(ref, 2), F.avg_pool2d(xin, 2)
+    assert rel_err(out.permute(0, 3, 1, 2), ref) < 1.5e-3   # fp16 output rounding
+    assert rel_err(raw.permute(0, 3, 1, 2), rraw) < 1.5e-3
+    # statistics themselves: fp64 sums against torch
+    cpg = C // 32
+    xs = xin.double().reshape(N, 32, cpg * H * W)
+    assert torch.allclose(stats[:, :, 0], xs.sum(-1), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(stats[:, :, 1], (xs * xs).sum(-1), rtol=1e-5, atol=1e-3)
+
+
+def test_groupnorm_plain_preadd_nosilu(cuda_dev):
+    """non-adaptive path: h += emb; GroupNorm(h) (model.py:204-206) and the attention norm (no SiLU)."""
+    ops, L = _ops()
+    g = torch.Generator(device='cpu').manual_seed(9)
+    N, H, W, C = 2, 8, 8, 128
+    x = torch.randn(N, C, H, W, generator=g).to(cuda_dev)
+    e = torch.randn(N, C, generator=g).to(cuda_dev)
+    gamma = (1 + 0.1 * torch.randn(C, generator=g)).to(cuda_dev)
+    beta = (0.1 * torch.randn(C, generator=g)).to(cuda_dev)
+    stats = ops.gn_stats(nhwc(x), pre_add=e)
+    out = ops.gn_apply(nhwc(x), stats, gamma, beta, pre_add=e, silu=False)
+    ref = F.group_norm(x + e[:, :, None, None], 32, gamma, beta, eps=1e-5)
+    assert rel_err(out.permute(0, 3, 1, 2), ref) < 1.5e-3
+
+
+ATTN_CASES = [(2, 64, 4, 64, 0), (2, 256, 3, 64, 0), (1, 1024, 2, 64, 0), (2, 196, 4, 32, 0), (3, 49, 4, 64, 0),
+              (2, 256, 2, 64, 1), (1, 256, 2, 128, 0), (1, 64, 2, 256, 0), (1, 320, 1, 192, 1)]
+
+
+@pytest.mark.parametrize('B,T,heads,d,order', ATTN_CASES)
+def test_attention(cuda_dev, B, T, heads, d, order):
+    ops, L = _ops()
+    g = torch.Generator(device='cpu').manual_seed(T + d)
+    C = heads * d
+    qkv = torch.randn(B, T, 3 * C, generator=g).to(cuda_dev).half()
+    out = ops.attention(qkv, B, T, heads, d, order=order)
+    f = qkv.float()
+    if order == 0:
+        q, k, v = f.reshape(B, T, 3, heads, d).permute(2, 0, 3, 1, 4).unbind(0)
+    else:
+        q, k, v = f.reshape(B, T, heads, 3, d).permute(3, 0, 2, 1, 4).unbind(0)
+    w = torch.softmax((q @ k.transpose(2, 3)) * d ** -0.5, dim=-1)
+    ref = (w @ v).transpose(1, 2).reshape(B, T, C)
+    assert rel_err(out, ref) < 2e-3
+
+
+def test_embed(cuda_dev):
+    ops, L = _ops()
+    from oracle.unet import timestep_embedding
+    g = torch.Generator(device='cpu').manual_seed(1)
+    B, mc, ncls = 5, 192, 17
+    E = 4 * mc
+    t = torch.tensor([2., 998., 500., 6., 0.])
+    y = torch.randint(0, ncls, (B,), generator=g)
+    w0 = torch.randn(E, mc, generator=g) / math.sqrt(mc); b0 = 0.1 * torch.randn(E, generator=g)
+    w2 = torch.randn(E, E, generator=g) / math.sqrt(E); b2 = 0.1 * torch.randn(E, generator=g)
+    ce = torch.randn(ncls, E, generator=g)
+    freqs = torch.exp(torch.arange(mc // 2, dtype=torch.float32) * -(math.log(10000) / (mc // 2)))
+    ref = F.linear(F.silu(F.linear(timestep_embedding(t, mc), w0, b0)), w2, b2) + ce[y]
+    d = cuda_dev
+    emb, act = ops.embed(t.to(d), y.to(d), freqs.to(d), w0.to(d), b0.to(d), w2.to(d), b2.to(d), ce.to(d))
+    assert rel_err(emb.cpu(), ref) < 1e-5
+    assert rel_err(act.cpu(), F.silu(ref)) < 1e-3
+
+
+def test_stem_resample_cast_im2col_uint8(cuda_dev):
+    ops, L = _ops()
+    g = torch.Generator(device='cpu').manual_seed(2)
+    x = torch.randn(2, 3, 16, 16, generator=g).to(cuda_dev)
+    w = torch.randn(64, 3, 3, 3, generator=g).to(cuda_dev) / 5
+    b = torch.randn(64, generator=g).to(cuda_dev)
+    assert rel_err(ops.stem_conv(x, w, b).permute(0, 3, 1, 2), F.conv2d(x, w, b, padding=1)) < 1e-5
+    x1 = torch.randn(2, 1, 28, 28, generator=g).to(cuda_dev)
+    w1 = torch.randn(64, 1, 3, 3, generator=g).to(cuda_dev)
+    assert rel_err(ops.stem_conv(x1, w1, b).permute(0, 3, 1, 2), F.conv2d(x1, w1, b, padding=1)) < 1e-5
+    a = torch.randn(2, 64, 8, 8, generator=g).to(cuda_dev)
+    assert torch.equal(ops.resample_f32(nhwc(a), L.RESAMPLE_UP2).permute(0, 3, 1, 2),
+                       F.interpolate(a, scale_factor=2.0, mode='nearest'))
+    assert rel_err(ops.resample_f32(nhwc(a), L.RESAMPLE_DOWN2).permute(0, 3, 1, 2), F.avg_pool2d(a, 2)) < 1e-6
+    assert torch.equal(ops.cast16(nhwc(a)), nhwc(a).half())
+    # strided conv through im2col + nine 1x1 segments (Downsample(with_conv=True), model.py:103-109)
+    wd = (torch.randn(64, 64, 3, 3, generator=g) / 24).to(cuda_dev)
+    cols = ops.im2col_s2(nhwc(a))
+    wp = ops.pack_conv_weight(wd)
+    segs = [(cols[tap], wp[tap:tap + 1]) for tap in range(9)]
+    out = ops.conv_gemm(segs, 2, 4, 4, 64, bias=b)
+    ref = F.conv2d(a.half().float(), wd.half().float(), b, stride=2, padding=1)
+    assert rel_err(out.permute(0, 3, 1, 2), ref) < 2e-5
+    img = torch.rand(2, 3, 8, 8, generator=g).to(cuda_dev) * 2.4 - 1.2
+    ref8 = ((img + 1) * 127.5).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1)
+    assert torch.equal(ops.to_uint8(img), ref8)
