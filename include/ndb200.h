@@ -94,7 +94,12 @@ int ndb_pack_conv_weight(const float* w_oihw, void* dst, int cout, int cin_total
  * `pre_add` ([N][ld_pre], optional) is added per (n, channel) before normalisation (the non-adaptive
  * `h += embedding` path, model.py:205). */
 int ndb_gn_stats(const float* x0, int C0, const float* x1, int C1, int N, int HW, const float* pre_add,
-                 int ld_pre, double* stats /* [N][32][2], zeroed */, void* stream);
+                 int ld_pre, double* stats /* [N][32][2] (sum, sum of squares), overwritten */,
+                 void* workspace, void* stream);
+/* Scratch for the deterministic cross-block reduction (no floating-point atomics: results are bit-identical from
+ * run to run). Must be zero-filled ONCE before first use; it is left clean by every call and may be shared by all
+ * GroupNorm launches of a stream. */
+int64_t ndb_gn_stats_workspace_bytes(int N, int HW, int C);
 
 #define NDB_RESAMPLE_NONE 0
 #define NDB_RESAMPLE_UP2 1
@@ -189,10 +194,15 @@ typedef struct {
     uint64_t seed;
     const int64_t* sample_ids; /* [B] global sample indices for Philox keying (NULL -> b) */
     float* x_prev;            /* out (may alias x_t) */
+    float* x_prev2;           /* optional second copy of the output (the unconditional half of a doubled CFG batch) */
     float* pred_x0;           /* out, optional */
 } ndb_step_params;
 
 int ndb_sampler_step(const ndb_step_params* p, void* stream);
+
+/* Device-side loop counter for CUDA-graph replay of whole steps: t_step[b] <- max(t_step[0]-1, 0) for b < B and
+ * t_model[b] <- timestep_map_f32[t_step] for b < Bm (diffusion.py:215-216,246). One tiny launch per step. */
+int ndb_advance_step(float* t_step, int B, float* t_model, int Bm, const float* timestep_map_f32, void* stream);
 
 /* x_T ~ N(0,1) from the same Philox stream family: element e of sample id s at "step" = R (diffusion.py:202). */
 int ndb_philox_normal(float* out, int B, int64_t per_sample, uint64_t seed, const int64_t* sample_ids,

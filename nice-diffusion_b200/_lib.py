@@ -61,7 +61,7 @@ class StepParams(C.Structure):
                 ('grad', C.c_void_p), ('clf_strength', C.c_double),
                 ('clip_x0', C.c_int32),
                 ('noise', C.c_void_p), ('seed', C.c_uint64), ('sample_ids', C.c_void_p),
-                ('x_prev', C.c_void_p), ('pred_x0', C.c_void_p)]
+                ('x_prev', C.c_void_p), ('x_prev2', C.c_void_p), ('pred_x0', C.c_void_p)]
 
 
 # name -> (restype, argtypes); must list every symbol include/ndb200.h declares (tests check this)
@@ -72,7 +72,8 @@ SIGNATURES = {
     'ndb_last_error': (C.c_char_p, []),
     'ndb_conv_gemm': (_I, [C.POINTER(ConvParams), _P]),
     'ndb_pack_conv_weight': (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
-    'ndb_gn_stats': (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _P]),
+    'ndb_gn_stats': (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _P, _P]),
+    'ndb_gn_stats_workspace_bytes': (_I64, [_I, _I, _I]),
     'ndb_gn_apply': (_I, [C.POINTER(GnApplyParams), _P]),
     'ndb_attention': (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'ndb_embed': (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
@@ -81,6 +82,7 @@ SIGNATURES = {
     'ndb_cast_nhwc16': (_I, [_P, _P, _I64, _I, _P]),
     'ndb_im2col_s2': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     'ndb_sampler_step': (_I, [C.POINTER(StepParams), _P]),
+    'ndb_advance_step': (_I, [_P, _I, _P, _I, _P, _P]),
     'ndb_philox_normal': (_I, [_P, _I, _I64, _U64, _P, C.c_int32, _P]),
     'ndb_qsample': (_I, [_P, _P, _P, _P, _P, _P, _I, _I64, _P]),
     'ndb_to_uint8': (_I, [_P, _P, _I, _I, _I, _I, _P]),

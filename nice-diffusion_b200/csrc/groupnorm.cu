@@ -20,27 +20,27 @@ constexpr int kMaxVecPerThread = 4;  // supports C <= 4 * 4 * 256 = 4096
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kGnThreads)
 gn_stats_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, int HW,
-                const float* __restrict__ pre_add, int ld_pre, double* __restrict__ stats, int pix_per_block,
+                const float* __restrict__ pre_add, int ld_pre, double* __restrict__ stats,
+                double* __restrict__ partials, unsigned int* __restrict__ counters, int pix_per_block,
                 int threads_per_row, int rows_per_block) {
-    extern __shared__ float sm[];  // [2][C]
+    // Deterministic two-level reduction (no floating-point atomics): per-thread partials -> fixed-order block
+    // reduction in shared memory -> per-block fp64 partials in global scratch -> the last block of each sample
+    // (ticket counter) sums the per-block partials in block order and writes the final (sum, sumsq).
+    extern __shared__ float sm[];  // [2][rows_per_block][C]
+    __shared__ bool is_last;
     const int C = C0 + C1;
     const int V = C >> 2;
     const int n = blockIdx.y;
+    const int chunks = gridDim.x;
     const int p_begin = blockIdx.x * pix_per_block;
     int p_end = p_begin + pix_per_block;
     if (p_end > HW) p_end = HW;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-    __syncthreads();
+    float* red_s = sm;
+    float* red_ss = sm + rows_per_block * C;
 
     const int r = threadIdx.x / threads_per_row;
     const int tv = threadIdx.x - r * threads_per_row;
     if (r < rows_per_block) {
-        float s[kMaxVecPerThread][4], ss[kMaxVecPerThread][4];
-#pragma unroll
-        for (int j = 0; j < kMaxVecPerThread; ++j)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) s[j][k] = ss[j][k] = 0.f;
-
 #pragma unroll
         for (int j = 0; j < kMaxVecPerThread; ++j) {
             const int v = tv + j * threads_per_row;
@@ -52,34 +52,48 @@ gn_stats_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ 
                 float4 add = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (pre_add != nullptr) add = __ldg(reinterpret_cast<const float4*>(pre_add + (size_t)n * ld_pre + c));
                 const float* base = src + ((size_t)n * HW) * ldc + cc;
+                float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int p = p_begin + r; p < p_end; p += rows_per_block) {
                     float4 a = __ldg(reinterpret_cast<const float4*>(base + (size_t)p * ldc));
                     a.x += add.x; a.y += add.y; a.z += add.z; a.w += add.w;
-                    s[j][0] += a.x; s[j][1] += a.y; s[j][2] += a.z; s[j][3] += a.w;
-                    ss[j][0] += a.x * a.x; ss[j][1] += a.y * a.y; ss[j][2] += a.z * a.z; ss[j][3] += a.w * a.w;
+                    s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+                    ss.x += a.x * a.x; ss.y += a.y * a.y; ss.z += a.z * a.z; ss.w += a.w * a.w;
                 }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < kMaxVecPerThread; ++j) {
-            const int v = tv + j * threads_per_row;
-            if (v < V) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    atomicAdd(&sm[(v << 2) + k], s[j][k]);
-                    atomicAdd(&sm[C + (v << 2) + k], ss[j][k]);
-                }
+                *reinterpret_cast<float4*>(red_s + r * C + c) = s;
+                *reinterpret_cast<float4*>(red_ss + r * C + c) = ss;
             }
         }
     }
     __syncthreads();
+    double* my_part = partials + ((size_t)n * chunks + blockIdx.x) * (2 * kGroups);
     if (threadIdx.x < 2 * kGroups) {
         const int g = threadIdx.x & (kGroups - 1);
         const int which = threadIdx.x >> 5;
         const int cpg = C / kGroups;
+        const float* red = which ? red_ss : red_s;
         double acc = 0.0;
-        for (int k = 0; k < cpg; ++k) acc += (double)sm[which * C + g * cpg + k];
-        atomicAdd(&stats[((size_t)n * kGroups + g) * 2 + which], acc);
+        for (int k = 0; k < cpg; ++k)
+            for (int rr = 0; rr < rows_per_block; ++rr) acc += (double)red[rr * C + g * cpg + k];
+        my_part[which * kGroups + g] = acc;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicAdd(&counters[n], 1u);
+        is_last = (ticket == (unsigned int)(chunks - 1));
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        if (threadIdx.x < 2 * kGroups) {
+            const int g = threadIdx.x & (kGroups - 1);
+            const int which = threadIdx.x >> 5;
+            double tot = 0.0;
+            for (int ch = 0; ch < chunks; ++ch)
+                tot += __ldcg(partials + ((size_t)n * chunks + ch) * (2 * kGroups) + which * kGroups + g);
+            stats[((size_t)n * kGroups + g) * 2 + which] = tot;
+        }
+        if (threadIdx.x == 0) counters[n] = 0u;  // self-resetting: the workspace needs zeroing only once
     }
 }
 
@@ -213,26 +227,49 @@ gn_apply_kernel(const GnApplyArgs p) {
 
 using namespace ndb;
 
+struct GnStatsGeom {
+    int threads_per_row, rows_per_block, pix_per_block, chunks;
+};
+
+static GnStatsGeom gn_stats_geom(int N, int HW, int C) {
+    GnStatsGeom g;
+    const int V = C / 4;
+    g.threads_per_row = V < kGnThreads ? V : kGnThreads;
+    g.rows_per_block = kGnThreads / g.threads_per_row;
+    // enough blocks to fill the machine, but at least ~8 pixels per row-slot
+    int target_blocks_per_sample = (4 * num_sms() + N - 1) / N;
+    if (target_blocks_per_sample < 1) target_blocks_per_sample = 1;
+    g.pix_per_block = (HW + target_blocks_per_sample - 1) / target_blocks_per_sample;
+    const int min_pix = g.rows_per_block * 8;
+    if (g.pix_per_block < min_pix) g.pix_per_block = min_pix;
+    g.chunks = (HW + g.pix_per_block - 1) / g.pix_per_block;
+    return g;
+}
+
+static size_t gn_counter_bytes(int N) { return (((size_t)N * sizeof(unsigned int)) + 255) / 256 * 256; }
+
+extern "C" int64_t ndb_gn_stats_workspace_bytes(int N, int HW, int C) {
+    if (N <= 0 || HW <= 0 || C <= 0) return 0;
+    const GnStatsGeom g = gn_stats_geom(N, HW, C);
+    return (int64_t)(gn_counter_bytes(N) + (size_t)N * g.chunks * 2 * kGroups * sizeof(double));
+}
+
 extern "C" int ndb_gn_stats(const float* x0, int C0, const float* x1, int C1, int N, int HW, const float* pre_add,
-                            int ld_pre, double* stats, void* stream) {
-    NDB_CHECK_ARG(x0 && stats && N > 0 && HW > 0);
+                            int ld_pre, double* stats, void* workspace, void* stream) {
+    NDB_CHECK_ARG(x0 && stats && workspace && N > 0 && HW > 0);
     if (x1 == nullptr) C1 = 0;
     const int C = C0 + C1;
     NDB_CHECK_ARG(C % kGroups == 0 && C0 % 4 == 0 && C1 % 4 == 0);
     const int V = C / 4;
     NDB_CHECK_ARG(V <= kMaxVecPerThread * kGnThreads);
-    int threads_per_row = V < kGnThreads ? V : kGnThreads;
-    int rows_per_block = kGnThreads / threads_per_row;
-    // enough blocks to fill the machine, but at least ~8 pixels per row-slot
-    int target_blocks_per_sample = (4 * num_sms() + N - 1) / N;
-    if (target_blocks_per_sample < 1) target_blocks_per_sample = 1;
-    int pix_per_block = (HW + target_blocks_per_sample - 1) / target_blocks_per_sample;
-    const int min_pix = rows_per_block * 8;
-    if (pix_per_block < min_pix) pix_per_block = min_pix;
-    const int chunks = (HW + pix_per_block - 1) / pix_per_block;
-    dim3 grid(chunks, N);
-    gn_stats_kernel<<<grid, kGnThreads, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
-        x0, C0, x1, C1, HW, pre_add, ld_pre, stats, pix_per_block, threads_per_row, rows_per_block);
+    const GnStatsGeom g = gn_stats_geom(N, HW, C);
+    unsigned int* counters = reinterpret_cast<unsigned int*>(workspace);
+    double* partials = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(workspace) + gn_counter_bytes(N));
+    dim3 grid(g.chunks, N);
+    const size_t smem = 2 * (size_t)g.rows_per_block * C * sizeof(float);
+    gn_stats_kernel<<<grid, kGnThreads, smem, (cudaStream_t)stream>>>(
+        x0, C0, x1, C1, HW, pre_add, ld_pre, stats, partials, counters, g.pix_per_block, g.threads_per_row,
+        g.rows_per_block);
     return launch_status("ndb_gn_stats");
 }
 

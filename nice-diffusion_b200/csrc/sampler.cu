@@ -132,6 +132,7 @@ sampler_step_kernel(const ndb_step_params p) {
                 out = add(mean, mul(mul(mask, sqrtf(var)), nz));
             }
             p.x_prev[xi] = out;
+            if (p.x_prev2 != nullptr) p.x_prev2[xi] = out;
             if (p.pred_x0 != nullptr) p.pred_x0[xi] = x0;
         }
     }
@@ -164,6 +165,15 @@ __global__ void qsample_kernel(const float* __restrict__ x0, const float* __rest
         const int ti = (int)t[b];
         out[i] = __fadd_rn(__fmul_rn(sa[ti], x0[i]), __fmul_rn(s1[ti], noise[i]));
     }
+}
+
+__global__ void advance_step_kernel(float* t_step, int B, float* t_model, int Bm, const float* __restrict__ tmap) {
+    const float cur = t_step[0];
+    __syncthreads();
+    const float nxt = cur > 0.f ? cur - 1.f : 0.f;
+    const float tm = tmap[(int)nxt];
+    for (int i = threadIdx.x; i < B; i += blockDim.x) t_step[i] = nxt;
+    for (int i = threadIdx.x; i < Bm; i += blockDim.x) t_model[i] = tm;
 }
 
 static inline int grid1d(long long work, int threads) {
@@ -203,4 +213,11 @@ extern "C" int ndb_qsample(const float* x0, const float* noise, const float* t, 
     qsample_kernel<<<grid1d((long long)B * per_sample, 256), 256, 0, (cudaStream_t)stream>>>(x0, noise, t, sqrt_abar,
                                                                                            sqrt_1m_abar, out, B, per_sample);
     return launch_status("ndb_qsample");
+}
+
+extern "C" int ndb_advance_step(float* t_step, int B, float* t_model, int Bm, const float* timestep_map_f32,
+                                void* stream) {
+    NDB_CHECK_ARG(t_step && t_model && timestep_map_f32 && B > 0 && Bm > 0);
+    advance_step_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(t_step, B, t_model, Bm, timestep_map_f32);
+    return launch_status("ndb_advance_step");
 }

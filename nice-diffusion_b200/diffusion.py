@@ -1,0 +1,387 @@
+"""`Diffusion` -- drop-in for nicediffusion.diffusion.Diffusion (reference diffusion.py:22-369) on ndb200 kernels.
+
+Same constructor, public numpy tables and `timestep_map`, `denoise / diffuse / diffusion_step /
+get_eps_and_log_var / denoising_step / ddim_denoising_step` with the reference's signatures, return values and
+assertion behaviour. Underneath:
+
+  * the schedule / respacing / posterior tables are computed on the host in numpy fp64 with the reference's
+    arithmetic (bit-exact, tests/test_schedule.py) and uploaded ONCE as fp32 rows (the reference re-uploads a
+    table on every `extract`, diffusion.py:492);
+  * each step is one fused kernel (`ndb_sampler_step`) after the UNet forward(s);
+  * `denoise` replays ONE CUDA graph per step (UNet plan + step kernel + device-side step counter), with the
+    classifier-free-guidance pair evaluated as a doubled batch [y ; 0] in a single forward;
+  * noise: `noise='torch'` (default) draws `torch.randn_like` per step like the reference; `noise='philox'`
+    generates it inside the step kernel keyed by (seed, global sample id, step) so that sharding the batch over
+    GPUs does not change any sample; an explicit `[R,B,C,H,W]` tensor injects noise (parity tests).
+
+Training (`loss`) is not part of this path yet and raises NotImplementedError.
+"""
+import math
+
+import numpy as np
+import torch
+import tqdm
+
+from . import _lib as L
+from . import ops
+
+
+def get_beta_schedule(schedule_method, num_steps, beta_0, beta_T):
+    """diffusion.py:445-475 (numpy fp64; bit-exact)."""
+    if schedule_method == 'linear':
+        return np.linspace(beta_0, beta_T, num_steps, dtype=np.float64)
+    elif schedule_method == 'constant':
+        return beta_0 * np.ones(num_steps, dtype=np.float64)
+    elif schedule_method == 'cosine':
+        def f(t):
+            return math.cos((t + 0.008) / (1.0 + 0.008) * math.pi / 2) ** 2
+        return np.array([min(1 - f((s + 1) / num_steps) / f(s / num_steps), 0.999) for s in range(num_steps)])
+    raise NotImplementedError("unimplemented variance scheduling method: {}".format(schedule_method))
+
+
+_VAR_TYPES = ('small', 'large', 'learned', 'learned_interpolation')
+_LOSS_TYPES = ('simple', 'KL', 'KL_rescaled', 'hybrid')
+
+
+class Diffusion:
+    def __init__(self, model, original_num_steps, rescaled_num_steps, sampling_var_type, loss_type,
+                 betas=None, beta_schedule='linear', guidance_method=None, guidance_strength=None, classifier=None,
+                 use_ddim=False, ddim_eta=None, device=None):
+        self.model = model
+        if device is None:
+            self.device = torch.device('cuda') if torch.cuda.is_available() else torch.device('cpu')
+        else:
+            self.device = device
+        self.model.to(self.device)
+        self.model.eval()
+
+        self.guidance = guidance_method
+        if guidance_method not in (None, 'classifier', 'classifier_free'):
+            raise NotImplementedError(guidance_method)
+        assert guidance_method is None or self.model.conditional, 'can only use guidance if model is conditional'
+        self.strength = guidance_strength
+        self.classifier = classifier
+        if self.classifier is not None:
+            self.classifier.float().to(self.device)
+            self.classifier.eval()
+
+        self.original_num_steps = original_num_steps
+        self.rescaled_num_steps = rescaled_num_steps
+        if sampling_var_type not in _VAR_TYPES:
+            raise NotImplementedError(sampling_var_type)
+        if loss_type not in _LOSS_TYPES:
+            raise NotImplementedError(loss_type)
+        self.sampling_var_type = sampling_var_type
+        self.loss_type = loss_type
+        if use_ddim:
+            assert ddim_eta is not None, 'please supply eta if you want to use ddim'
+        self.use_ddim = use_ddim
+        self.ddim_eta = ddim_eta
+
+        T, R = original_num_steps, rescaled_num_steps
+        if betas is None:
+            betas = get_beta_schedule(beta_schedule, T, 0.0001 * 1000 / T, 0.02 * 1000 / T)
+        else:
+            assert len(betas) == T, 'betas must be the right length!'
+            betas = np.array(betas, dtype=np.float64)
+        # respacing (diffusion.py:94-107): keep every (T//R)-th step starting at T//(2R); new betas from the
+        # ratios of the kept cumulative products. If R does not divide T the list is not of length R (kept).
+        abar_full = np.cumprod(1.0 - betas, axis=0)
+        kept = list(range(T // (2 * R), T + T // (2 * R), T // R))
+        kept_lookup = set(kept)
+        prev, new_betas = 1.0, []
+        for i, a in enumerate(abar_full):
+            if i in kept_lookup:
+                new_betas.append(1.0 - a / prev)
+                prev = a
+        betas = np.array(new_betas)
+        assert (betas > 0).all() and (betas <= 1).all(), 'betas in invalid range'
+
+        self.betas = betas
+        self.timestep_map = torch.tensor(kept, device=self.device, dtype=torch.long)
+        alphas = 1.0 - betas
+        self.alphas_cumprod = abar = np.cumprod(alphas, axis=0)
+        self.alphas_cumprod_prev = abar_prev = np.append(1.0, abar[:-1])
+        self.sqrt_alphas_cumprod = np.sqrt(abar)
+        self.sqrt_one_minus_alphas_cumprod = np.sqrt(1.0 - abar)
+        self.sqrt_reciprocal_alphas_cumprod = np.sqrt(1.0 / abar)
+        self.sqrt_reciprocal_alphas_minus_one_cumprod = np.sqrt(1.0 / abar - 1)
+        self.posterior_mean_coef_x0 = np.sqrt(abar_prev) * betas / (1.0 - abar)
+        self.posterior_mean_coef_xt = np.sqrt(alphas) * (1.0 - abar_prev) / (1.0 - abar)
+        self.posterior_variance = betas * (1.0 - abar_prev) / (1.0 - abar)
+        self.log_posterior_var_clipped = np.log(np.append(self.posterior_variance[1], self.posterior_variance[1:]))
+
+        # sampling options that are additions to the reference API
+        self.noise = 'torch'      # 'torch' | 'philox'
+        self.seed = 0             # philox seed
+        self.sample_ids = None    # LongTensor [B] of global sample indices (philox keying); default arange(B)
+        self._tables_dev = None
+        self._step_graphs = {}
+
+    # ------------------------------------------------------------------------------------------
+    # device tables
+    # ------------------------------------------------------------------------------------------
+    def _var_code(self):
+        return {'small': L.VAR_FIXED, 'large': L.VAR_FIXED, 'learned': L.VAR_LEARNED,
+                'learned_interpolation': L.VAR_LEARNED_INTERP}[self.sampling_var_type]
+
+    def _tables(self):
+        """[TAB_COUNT][n] fp32 on the device: each fp64 table cast to fp32 exactly as `extract` does."""
+        if self._tables_dev is None:
+            n = len(self.betas)
+            if self.sampling_var_type == 'large':
+                logvar_min = np.log(np.append(self.posterior_variance[1], self.betas[1:]))   # diffusion.py:259
+            elif self.sampling_var_type == 'small':
+                logvar_min = np.log(np.maximum(self.posterior_variance, 1e-20))               # diffusion.py:261
+            else:
+                logvar_min = self.log_posterior_var_clipped
+            rows = [None] * L.TAB_COUNT
+            rows[L.TAB_SQRT_RECIP_ABAR] = self.sqrt_reciprocal_alphas_cumprod
+            rows[L.TAB_SQRT_RECIPM1_ABAR] = self.sqrt_reciprocal_alphas_minus_one_cumprod
+            rows[L.TAB_POST_COEF_X0] = self.posterior_mean_coef_x0
+            rows[L.TAB_POST_COEF_XT] = self.posterior_mean_coef_xt
+            rows[L.TAB_LOGVAR_MIN] = logvar_min
+            rows[L.TAB_LOGVAR_MAX] = np.log(self.betas)
+            rows[L.TAB_ABAR] = self.alphas_cumprod
+            rows[L.TAB_ABAR_PREV] = self.alphas_cumprod_prev
+            rows[L.TAB_SQRT_1M_ABAR] = self.sqrt_one_minus_alphas_cumprod
+            tab = np.stack([np.asarray(r, dtype=np.float64) for r in rows]).reshape(L.TAB_COUNT, n)
+            self._tables_dev = dict(
+                tab=torch.from_numpy(tab).float().to(self.device).contiguous(),
+                sqrt_abar=torch.from_numpy(self.sqrt_alphas_cumprod).float().to(self.device),
+                sqrt_1m_abar=torch.from_numpy(self.sqrt_one_minus_alphas_cumprod).float().to(self.device),
+                tmap_f32=self.timestep_map.float().contiguous())
+        return self._tables_dev
+
+    # ------------------------------------------------------------------------------------------
+    # forward process
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def diffuse(self, x_0, steps_to_do=None, noise=None):
+        """diffusion.py:132-153."""
+        if steps_to_do is None or steps_to_do > self.rescaled_num_steps:
+            steps_to_do = self.rescaled_num_steps
+        timestep = ((steps_to_do - 1) * torch.ones(x_0.shape[0])).to(self.device)
+        return self.diffusion_step(x_0, t=timestep, noise=noise)
+
+    def diffusion_step(self, x_0, t, noise=None):
+        """q(x_t | x_0), diffusion.py:232-240."""
+        if noise is None:
+            noise = torch.randn_like(x_0).to(self.device)
+        tabs = self._tables()
+        x_0 = x_0.to(self.device, torch.float32).contiguous()
+        noise = noise.to(self.device, torch.float32).contiguous()
+        return ops.qsample(x_0, noise, t.to(self.device).float().contiguous(), tabs['sqrt_abar'], tabs['sqrt_1m_abar'])
+
+    # ------------------------------------------------------------------------------------------
+    # reverse process: per-step API (same signatures / returns as the reference)
+    # ------------------------------------------------------------------------------------------
+    def get_eps_and_log_var(self, x_t, t, kwargs):
+        """diffusion.py:242-264 -- returned as separate tensors for API parity (the sampling loop itself never
+        materialises log_var; it is folded into the step kernel)."""
+        out = self.model(x_t, self.timestep_map[t.long()], **(kwargs or {}))
+        tabs = self._tables()['tab']
+        ti = t.long()
+        shape = (x_t.shape[0],) + (1,) * (x_t.dim() - 1)
+        if self.sampling_var_type in ('learned', 'learned_interpolation'):
+            eps, v = torch.split(out, int(out.shape[1] / 2), dim=1)
+            if self.sampling_var_type == 'learned':
+                return eps, v
+            min_log = tabs[L.TAB_LOGVAR_MIN][ti].reshape(shape)
+            max_log = tabs[L.TAB_LOGVAR_MAX][ti].reshape(shape)
+            frac = (v + 1) / 2
+            return eps, frac * max_log + (1 - frac) * min_log
+        return out, tabs[L.TAB_LOGVAR_MIN][ti].reshape(shape).expand(x_t.shape)
+
+    def _model_pair(self, x_t, t, kwargs):
+        """UNet output for the step at respaced index tensor `t`; with classifier-free guidance the conditional
+        and the null-class (label 0, diffusion.py:281) evaluations run as ONE doubled batch."""
+        kwargs = kwargs or {}
+        ts = self.timestep_map[t.long()]
+        if self.guidance == 'classifier_free':
+            y = kwargs['y']
+            B = x_t.shape[0]
+            out = self.model(torch.cat([x_t, x_t], 0), torch.cat([ts, ts], 0), y=torch.cat([y, torch.zeros_like(y)], 0))
+            return out[:B], out[B:]
+        return self.model(x_t, ts, **kwargs), None
+
+    def _classifier_grad(self, x_t, t, y):
+        """grad_x log p(y | x_t, t) through the user's classifier (diffusion.py:298-304 / 330-336). The classifier
+        receives the RESPACED index t, as in the reference."""
+        with torch.enable_grad():
+            x = x_t.detach().requires_grad_(True)
+            log_probs = torch.log_softmax(self.classifier(x, t), dim=-1)
+            grabbed = log_probs[range(log_probs.shape[0]), torch.flatten(y)]
+            return torch.autograd.grad(grabbed.sum(), x)[0].float().contiguous()
+
+    def _step(self, x_t, t, kwargs, clip_x, ddim, noise=None):
+        x_t = x_t.contiguous()
+        t = t.to(self.device).float().contiguous()
+        with torch.no_grad():
+            out, null = self._model_pair(x_t, t, kwargs)
+        grad = None
+        if self.guidance == 'classifier':
+            grad = self._classifier_grad(x_t, t, kwargs['y'])
+        seed, ids = 0, None
+        if noise is None:
+            if self.noise == 'philox':
+                seed = self.seed
+                ids = self.sample_ids
+            else:
+                noise = torch.randn_like(x_t)
+        sample = torch.empty_like(x_t)
+        pred_x0 = torch.empty_like(x_t)
+        with torch.no_grad():
+            ops.sampler_step(x_t, out.contiguous(), t, self._tables()['tab'], self._var_code(), ddim=ddim,
+                             eta=self.ddim_eta if ddim else 0.0,
+                             null_out=null.contiguous() if null is not None else None,
+                             cfg_strength=self.strength if null is not None else 0.0,
+                             grad=grad, clf_strength=self.strength if grad is not None else 0.0,
+                             clip_x0=clip_x, noise=noise, seed=seed, sample_ids=ids, x_prev=sample, pred_x0=pred_x0)
+        return sample, pred_x0
+
+    def denoising_step(self, x_t, t, kwargs=None, clip_x=True, noise=None):
+        """p(x_{t-1} | x_t): DDPM step with learned / fixed variance (diffusion.py:266-316). Returns
+        (sample, pred_x0). `noise` optionally injects the N(0,1) draw."""
+        return self._step(x_t, t, kwargs, clip_x, ddim=False, noise=noise)
+
+    def ddim_denoising_step(self, x_t, t, kwargs=None, clip_x=True, noise=None):
+        """DDIM step (diffusion.py:318-369). Returns (sample, pred_x0)."""
+        return self._step(x_t, t, kwargs, clip_x, ddim=True, noise=noise)
+
+    # ------------------------------------------------------------------------------------------
+    # reverse process: the loop
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def denoise(self, x=None, kwargs=None, start_step=None, steps_to_do=None, batch_size=1, ema_params=None,
+                progress=True, noise=None):
+        """diffusion.py:155-226. Extra keyword `noise`: tensor [n_steps_total, B, C, H, W] whose row t is the
+        N(0,1) draw used at respaced step t (parity tests); default follows `self.noise`."""
+        if kwargs is None:
+            kwargs = {}
+        assert ('y' in kwargs.keys() and kwargs['y'] is not None) == self.model.conditional, \
+            'pass label iff model is class-conditional'
+        if self.model.conditional:
+            assert len(kwargs['y']) == batch_size, 'len(labels) != batch size'
+        original_params = None
+        if ema_params is not None:
+            original_params = {}
+            for name, param in self.model.named_parameters():
+                original_params[name] = param.data
+                param.data = ema_params[name].to(self.device)
+        try:
+            if start_step is None:
+                start_step = self.rescaled_num_steps
+            if steps_to_do is None or steps_to_do > start_step:
+                steps_to_do = start_step
+            if x is None:
+                assert start_step == self.rescaled_num_steps, 'cannot start from noise with current step that is not T'
+                shape = (batch_size, self.model.in_channels, self.model.resolution, self.model.resolution)
+                if self.noise == 'philox':
+                    ids = self.sample_ids if self.sample_ids is not None else \
+                        torch.arange(batch_size, device=self.device, dtype=torch.long)
+                    x = ops.philox_normal(shape, self.seed, ids, len(self.betas), self.device)
+                else:
+                    x = torch.randn(*shape).to(self.device)
+            x = x.to(self.device, torch.float32).contiguous()
+            if steps_to_do == 0:
+                return x
+            if self.guidance == 'classifier':
+                x = self._denoise_stepwise(x, kwargs, steps_to_do, progress, noise)
+            else:
+                x = self._denoise_graph(x, kwargs, steps_to_do, progress, noise)
+        finally:
+            if original_params is not None:
+                for name, param in self.model.named_parameters():
+                    param.data = original_params[name]
+        return x
+
+    def _denoise_stepwise(self, x, kwargs, steps_to_do, progress, noise):
+        """Reference-shaped loop over the public step functions (needed for classifier guidance, whose gradient
+        goes through the user's torch classifier every step)."""
+        indices = reversed(range(steps_to_do))
+        if progress:
+            indices = tqdm.tqdm(indices, total=steps_to_do)
+        for t in indices:
+            timestep = torch.full((x.shape[0],), float(t), device=self.device)
+            nz = noise[t].to(self.device).contiguous() if noise is not None else None
+            step = self.ddim_denoising_step if self.use_ddim else self.denoising_step
+            x, _ = step(x, t=timestep, kwargs=kwargs, noise=nz)
+        return x
+
+    def _denoise_graph(self, x, kwargs, steps_to_do, progress, noise):
+        """One CUDA-graph replay per step: [UNet plan (doubled batch under CFG) -> fused step kernel (writes x_{t-1}
+        straight into the UNet's input buffer) -> device-side step counter]. No host<->device traffic inside the loop."""
+        B = x.shape[0]
+        cfg = self.guidance == 'classifier_free'
+        Bm = 2 * B if cfg else B
+        model = self.model
+        eng = model.engine_for(torch.empty((Bm, 0), device=self.device))
+        eng.refresh_weights()
+        tabs = self._tables()
+        key = (B, cfg, id(eng), self.use_ddim)
+        st = self._step_graphs.get(key)
+        if st is None:
+            st = dict(t_step=torch.zeros((B,), dtype=torch.float32, device=self.device),
+                      noise=torch.zeros_like(x), ids=torch.arange(B, device=self.device, dtype=torch.long),
+                      graphs={})
+            self._step_graphs[key] = st
+        # inputs of this run
+        eng.x_in[:B].copy_(x)
+        if cfg:
+            eng.x_in[B:].copy_(x)
+        if model.conditional:
+            eng.y_in[:B].copy_(kwargs['y'])
+            if cfg:
+                eng.y_in[B:].zero_()
+        t0 = steps_to_do - 1
+        st['t_step'].fill_(float(t0))
+        eng.t_in.fill_(float(self.timestep_map[t0].item()))
+        if self.sample_ids is not None:
+            st['ids'].copy_(self.sample_ids)
+        else:
+            st['ids'].copy_(torch.arange(B, device=self.device, dtype=torch.long))
+        use_philox = noise is None and self.noise == 'philox'
+        gkey = (use_philox, int(self.seed) if use_philox else 0)
+        g = st['graphs'].get(gkey)
+
+        def launch_step():
+            eng._launch_all()
+            out = eng.out
+            ops.sampler_step(eng.x_in[:B], out[:B], st['t_step'], tabs['tab'], self._var_code(), ddim=self.use_ddim,
+                             eta=self.ddim_eta if self.use_ddim else 0.0,
+                             null_out=out[B:] if cfg else None, cfg_strength=self.strength if cfg else 0.0,
+                             clip_x0=True, noise=None if use_philox else st['noise'], seed=self.seed,
+                             sample_ids=st['ids'], x_prev=eng.x_in[:B], x_prev2=eng.x_in[B:] if cfg else None)
+            ops.advance_step(st['t_step'], eng.t_in, tabs['tmap_f32'])
+
+        indices = reversed(range(steps_to_do))
+        if progress:
+            indices = tqdm.tqdm(indices, total=steps_to_do)
+        for t in indices:
+            if not use_philox:
+                if noise is not None:
+                    st['noise'].copy_(noise[t])
+                else:
+                    st['noise'].normal_()
+            if not model.use_cuda_graph:
+                launch_step()
+                continue
+            if g is None:
+                # first step of the first run doubles as warm-up; capture from the second launch on
+                saved = (eng.x_in.clone(), st['t_step'].clone(), eng.t_in.clone())
+                launch_step()
+                torch.cuda.synchronize(self.device)
+                eng.x_in.copy_(saved[0]); st['t_step'].copy_(saved[1]); eng.t_in.copy_(saved[2])
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    launch_step()
+                st['graphs'][gkey] = g
+            g.replay()
+            ops.LAUNCHES += eng.num_kernels + 2
+        return eng.x_in[:B].clone()
+
+    # ------------------------------------------------------------------------------------------
+    def loss(self, x_0, t, kwargs=None, noise=None):
+        raise NotImplementedError('training loss (reference diffusion.py:375-438) is outside the sampling hot path '
+                                  'built so far (SURVEY.md section 8 f-1)')

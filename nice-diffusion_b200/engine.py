@@ -1,0 +1,374 @@
+"""UNet execution plan: turns a `DiffusionModel` parameter tree into a static list of ndb200 kernel launches
+for one (device, batch size), with all intermediates preallocated, weights packed for the tensor cores, and the
+whole forward captured in a CUDA graph.
+
+Dataflow per block (reference: model.py:188-211 ResidualBlock, :260-291 AttentionBlock):
+
+  ResBlock   gn_stats(x) -> gn_apply[SiLU, up/down, concat] -> conv3x3 GEMM (+bias) -> gn_stats
+             -> gn_apply[AdaGN scale/shift, SiLU] -> conv3x3 GEMM (+bias, + residual x | + 1x1 skip as an extra
+             K segment, x_resample folded into the epilogue)
+  Attention  gn_stats -> gn_apply -> qkv GEMM (fp16 out) -> fused attention -> proj GEMM (+bias +x)
+
+The residual stream is fp32 NHWC; every tensor-core operand is written once in 16-bit NHWC by the producing
+GroupNorm kernel. `torch.cat` of the up path never materialises in fp32: the GroupNorm kernels read both
+sources (model.py:474). All step-embedding Linear layers run as ONE GEMM per forward.
+"""
+import torch
+
+from . import _lib as L
+from . import ops
+from .model import (AttentionBlock, Downsample, ResidualBlock, Upsample, timestep_embedding_freqs)
+
+
+class _Pool:
+    """Static buffer assignment: exact-size free lists, so temporaries of equal shape share memory."""
+
+    def __init__(self, device):
+        self.device = device
+        self.free = {}
+        self.total_bytes = 0
+
+    def get(self, shape, dtype):
+        key = (tuple(shape), dtype)
+        lst = self.free.get(key)
+        if lst:
+            return lst.pop()
+        t = torch.empty(shape, dtype=dtype, device=self.device)
+        self.total_bytes += t.numel() * t.element_size()
+        return t
+
+    def put(self, t):
+        self.free.setdefault((tuple(t.shape), t.dtype), []).append(t)
+
+
+class UNetEngine:
+    def __init__(self, model, batch, device):
+        self.model = model
+        self.B = batch
+        self.device = device
+        self.fmt = model.operand_format
+        self.dt16 = ops.dtype16(self.fmt)
+        self.steps = []          # list of zero-arg callables, one kernel launch each
+        self.packers = []        # callables that (re)fill the weight arena from the live parameters
+        self.graph = None
+        self.sig = None
+        self.pool = _Pool(device)
+        with torch.no_grad():
+            self._build()
+
+    # ------------------------------------------------------------------------------------------
+    # weight arena
+    # ------------------------------------------------------------------------------------------
+    def _copy_param(self, p, dtype=torch.float32):
+        buf = torch.empty(p.shape, dtype=dtype, device=self.device)
+        self.packers.append(lambda: buf.copy_(p.detach()))
+        return buf
+
+    def _packed(self, p, cout_pad=None):
+        w = p
+        cout = w.shape[0]
+        k = w.shape[2] if w.dim() >= 3 else 1
+        cp = ops.pad16(cout) if cout_pad is None else cout_pad
+        buf = torch.empty((k * k, cp, w.shape[1]), dtype=self.dt16, device=self.device)
+        self.packers.append(lambda: ops.pack_conv_weight(p.detach().to(self.device), cout_pad=cp, fmt=self.fmt, out=buf))
+        return buf
+
+    def _bias_sum(self, p1, p2):
+        buf = torch.empty(p1.shape, dtype=torch.float32, device=self.device)
+        self.packers.append(lambda: torch.add(p1.detach(), p2.detach(), out=buf))
+        return buf
+
+    def _signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self.model.parameters())
+
+    def refresh_weights(self, force=False):
+        sig = self._signature()
+        if force or sig != self.sig:
+            with torch.no_grad():
+                for f in self.packers:
+                    f()
+            self.sig = sig
+
+    # ------------------------------------------------------------------------------------------
+    # plan construction
+    # ------------------------------------------------------------------------------------------
+    def _build(self):
+        m, B, dev, fmt = self.model, self.B, self.device, self.fmt
+        R = m.resolution
+        E = 4 * m.model_channels
+        for c in self._all_channels():
+            if c % 64 != 0:
+                raise L.NdbError('ndb200 needs every feature-map width to be a multiple of 64 (got {})'.format(c))
+
+        # static inputs / output
+        self.x_in = torch.zeros((B, m.in_channels, R, R), dtype=torch.float32, device=dev)
+        self.t_in = torch.zeros((B,), dtype=torch.float32, device=dev)
+        self.y_in = torch.zeros((B,), dtype=torch.int64, device=dev) if m.conditional else None
+        self.out = torch.empty((B, m.out_channels, R, R), dtype=torch.float32, device=dev)
+
+        # ---- embedding front end + one GEMM for every ResBlock's step_embedding Linear ----
+        freqs = timestep_embedding_freqs(m.model_channels).to(dev)
+        w0 = self._copy_param(m.step_embed[0].weight); b0 = self._copy_param(m.step_embed[0].bias)
+        w2 = self._copy_param(m.step_embed[2].weight); b2 = self._copy_param(m.step_embed[2].bias)
+        ce = self._copy_param(m.class_embedding.weight) if m.conditional else None
+        act16 = torch.empty((B, E), dtype=self.dt16, device=dev)
+        self.emb = torch.empty((B, E), dtype=torch.float32, device=dev)
+        self.steps.append(lambda: ops.embed(self.t_in, self.y_in, freqs, w0, b0, w2, b2, ce, emb_out=self.emb,
+                                            act_out=act16, fmt=fmt))
+        resblocks = [mod for mod in m.modules() if isinstance(mod, ResidualBlock)]
+        total = sum(rb.step_embedding.out_features for rb in resblocks)
+        assert total % 16 == 0
+        w_all = torch.empty((1, total, E), dtype=self.dt16, device=dev)
+        b_all = torch.empty((total,), dtype=torch.float32, device=dev)
+        self.emb_all = torch.empty((B, total), dtype=torch.float32, device=dev)
+        self.emb_off = {}
+        off = 0
+        for rb in resblocks:
+            n = rb.step_embedding.out_features
+            self.emb_off[id(rb)] = off
+            wv, bv, lin = w_all[:, off:off + n, :], b_all[off:off + n], rb.step_embedding
+            self.packers.append(lambda wv=wv, lin=lin, n=n: wv.copy_(
+                lin.weight.detach().to(self.dt16).view(1, n, E)))
+            self.packers.append(lambda bv=bv, lin=lin: bv.copy_(lin.bias.detach()))
+            off += n
+        a_view = act16.view(1, 1, B, E)
+        self.steps.append(lambda: ops.conv_gemm([(a_view, w_all)], 1, 1, B, total, bias=b_all,
+                                                out=self.emb_all, fmt=fmt, cout_pad=total))
+
+        # ---- GroupNorm statistics: one [B,32,2] fp64 slot per norm + one shared reduction workspace ----
+        n_gn = sum(1 for mod in m.modules() if isinstance(mod, torch.nn.GroupNorm))
+        self.stats_pool = torch.zeros((n_gn, B, 32, 2), dtype=torch.float64, device=dev)
+        self._stats_i = 0
+        ws_bytes = 0
+        res = R
+        while res >= 1:
+            for c in (64, 4096):
+                ws_bytes = max(ws_bytes, int(L.load().ndb_gn_stats_workspace_bytes(B, res * res, c)))
+            res //= 2
+        self.gn_ws = torch.zeros((ws_bytes + 7) // 8, dtype=torch.int64, device=dev)
+
+        # ---- trunk ----
+        stem = m.downsampling[0][0]
+        stem_w = self._copy_param(stem.weight); stem_b = self._copy_param(stem.bias)
+        C0 = stem.weight.shape[0]
+        x = self.pool.get((B, R, R, C0), torch.float32)
+        self.steps.append(lambda x=x: ops.stem_conv(self.x_in, stem_w, stem_b, out=x))
+        xs = [x]
+        cur = x
+        for seq in list(m.downsampling)[1:]:
+            cur = self._run_sequential(seq, cur, None, input_saved=True)
+            xs.append(cur)
+        cur = self._run_sequential(m.middle_block, cur, None, input_saved=True)
+        for seq in m.upsampling:
+            skip = xs.pop()
+            new = self._run_sequential(seq, cur, skip, input_saved=False)
+            self.pool.put(skip)
+            cur = new
+        # head: GroupNorm -> SiLU -> conv3x3 to out_channels (model.py:446-449), NCHW fp32 out
+        gn, conv = m.out[0], m.out[2]
+        C = cur.shape[-1]
+        st = self._next_stats()
+        g = self._copy_param(gn.weight); bt = self._copy_param(gn.bias)
+        a = self.pool.get(tuple(cur.shape), self.dt16)
+        wp = self._packed(conv.weight); bp = self._copy_param(conv.bias)
+        H = cur.shape[1]
+        self.steps.append(lambda cur=cur, st=st: ops.gn_stats(cur, stats=st, workspace=self.gn_ws))
+        self.steps.append(lambda cur=cur, st=st, a=a: ops.gn_apply(cur, st, g, bt, silu=True, out=a, fmt=fmt, eps=gn.eps))
+        self.steps.append(lambda a=a: ops.conv_gemm([(a, wp)], B, H, H, m.out_channels, bias=bp,
+                                                    out_kind=L.OUT_F32_NCHW, out=self.out, fmt=fmt))
+        self.num_kernels = len(self.steps)
+
+    def _all_channels(self):
+        m = self.model
+        cs = set()
+        for mod in m.modules():
+            if isinstance(mod, ResidualBlock):
+                cs.add(mod.in_channels); cs.add(mod.out_channels)
+            elif isinstance(mod, AttentionBlock):
+                cs.add(mod.channels)
+        return cs
+
+    def _next_stats(self):
+        s = self.stats_pool[self._stats_i]
+        self._stats_i += 1
+        return s
+
+    def _run_sequential(self, seq, x, skip, input_saved):
+        """Emit the launches of one UsesStepsSequential (model.py:40-48). `x` (+ optional concat partner `skip`
+        for the first layer, model.py:474) is the input; returns the output tensor. Buffers of consumed
+        intermediates go back to the pool; `input_saved` says the input is still referenced by the skip stack."""
+        cur, cur_saved, first = x, input_saved, True
+        for layer in seq:
+            if isinstance(layer, ResidualBlock):
+                out = self._resblock(layer, cur, skip if first else None)
+            elif isinstance(layer, AttentionBlock):
+                out = self._attention(layer, cur)
+            elif isinstance(layer, Upsample):
+                out = self._upsample(layer, cur)
+            elif isinstance(layer, Downsample):
+                out = self._downsample(layer, cur)
+            else:
+                raise L.NdbError('unexpected layer {}'.format(type(layer)))
+            if not cur_saved:
+                self.pool.put(cur)
+            cur, cur_saved, first = out, False, False
+        return cur
+
+    # ---- blocks ---------------------------------------------------------------------------
+    def _resblock(self, rb, x, skip):
+        B, fmt, pool = self.B, self.fmt, self.pool
+        _, H, W, C0 = x.shape
+        C1 = skip.shape[-1] if skip is not None else 0
+        Cin, Cout = rb.in_channels, rb.out_channels
+        assert C0 + C1 == Cin, (C0, C1, Cin)
+        mode = {'same': L.RESAMPLE_NONE, 'up': L.RESAMPLE_UP2, 'down': L.RESAMPLE_DOWN2}[rb.mode]
+        Ho, Wo = (H, W) if rb.mode == 'same' else ((2 * H, 2 * W) if rb.mode == 'up' else (H // 2, W // 2))
+        conv_skip = not isinstance(rb.skip, torch.nn.Identity)
+        if not conv_skip and skip is not None:
+            raise L.NdbError('identity skip over a concatenated input is not supported')
+
+        g1 = self._copy_param(rb.in_norm.weight); b1 = self._copy_param(rb.in_norm.bias)
+        g2 = self._copy_param(rb.out_norm.weight); b2 = self._copy_param(rb.out_norm.bias)
+        w_in = self._packed(rb.in_conv.weight); bias_in = self._copy_param(rb.in_conv.bias)
+        w_out = self._packed(rb.out_conv.weight)
+        if conv_skip:
+            w_skip = self._packed(rb.skip.weight)
+            bias_out = self._bias_sum(rb.out_conv.bias, rb.skip.bias)
+        else:
+            bias_out = self._copy_param(rb.out_conv.bias)
+        off = self.emb_off[id(rb)]
+        if rb.use_adaptive_gn:
+            scale = self.emb_all[:, off:off + Cout]
+            shift = self.emb_all[:, off + Cout:off + 2 * Cout]
+            pre = None
+        else:
+            scale = shift = None
+            pre = self.emb_all[:, off:off + Cout]
+
+        st1, st2 = self._next_stats(), self._next_stats()
+        a1 = pool.get((B, Ho, Wo, Cin), self.dt16)
+        raw = pool.get((B, Ho, Wo, Cin), self.dt16) if conv_skip else None
+        h = pool.get((B, Ho, Wo, Cout), torch.float32)
+        a2 = pool.get((B, Ho, Wo, Cout), self.dt16)
+        out = pool.get((B, Ho, Wo, Cout), torch.float32)
+        eps1, eps2 = rb.in_norm.eps, rb.out_norm.eps
+
+        self.steps.append(lambda: ops.gn_stats(x, skip, stats=st1, workspace=self.gn_ws))
+        self.steps.append(lambda: ops.gn_apply(x, st1, g1, b1, x1=skip, silu=True, resample=mode, out=a1, raw16=raw,
+                                               fmt=fmt, eps=eps1))
+        self.steps.append(lambda: ops.conv_gemm([(a1, w_in)], B, Ho, Wo, Cout, bias=bias_in, out=h, fmt=fmt))
+        self.steps.append(lambda: ops.gn_stats(h, pre_add=pre, stats=st2, workspace=self.gn_ws))
+        self.steps.append(lambda: ops.gn_apply(h, st2, g2, b2, scale=scale, shift=shift, pre_add=pre, silu=True,
+                                               out=a2, fmt=fmt, eps=eps2))
+        if conv_skip:
+            segs = [(a2, w_out), (raw, w_skip)]  # 1x1 (or 3x3 when use_conv) skip conv as extra K range
+            self.steps.append(lambda: ops.conv_gemm(segs, B, Ho, Wo, Cout, bias=bias_out, out=out, fmt=fmt))
+        else:
+            rmode = {'same': L.RES_SAME, 'up': L.RES_UP2, 'down': L.RES_DOWN2}[rb.mode]
+            self.steps.append(lambda: ops.conv_gemm([(a2, w_out)], B, Ho, Wo, Cout, bias=bias_out, residual=x,
+                                                    residual_mode=rmode, out=out, fmt=fmt))
+        for t in (a1, raw, h, a2):
+            if t is not None:
+                pool.put(t)
+        return out
+
+    def _attention(self, ab, x):
+        B, fmt, pool = self.B, self.fmt, self.pool
+        _, H, W, C = x.shape
+        T = H * W
+        heads = ab.num_heads
+        d = C // heads
+        g = self._copy_param(ab.norm.weight); bt = self._copy_param(ab.norm.bias)
+        w_qkv = self._packed(ab.qkv_nin.weight); b_qkv = self._copy_param(ab.qkv_nin.bias)
+        w_proj = self._packed(ab.proj_out.weight); b_proj = self._copy_param(ab.proj_out.bias)
+        st = self._next_stats()
+        n16 = pool.get((B, H, W, C), self.dt16)
+        qkv = pool.get((B, H, W, 3 * C), self.dt16)
+        o16 = pool.get((B, H, W, C), self.dt16)
+        out = pool.get((B, H, W, C), torch.float32)
+        order = 0 if ab.split_qkv_first else 1
+        eps = ab.norm.eps
+        self.steps.append(lambda: ops.gn_stats(x, stats=st, workspace=self.gn_ws))
+        self.steps.append(lambda: ops.gn_apply(x, st, g, bt, silu=False, out=n16, fmt=fmt, eps=eps))
+        self.steps.append(lambda: ops.conv_gemm([(n16, w_qkv)], B, H, W, 3 * C, bias=b_qkv,
+                                                out_kind=L.OUT_F16_NHWC, out=qkv, fmt=fmt))
+        self.steps.append(lambda: ops.attention(qkv.view(B, T, 3 * C), B, T, heads, d, order=order,
+                                                out=o16.view(B, T, C), fmt=fmt))
+        self.steps.append(lambda: ops.conv_gemm([(o16, w_proj)], B, H, W, C, bias=b_proj, residual=x,
+                                                residual_mode=L.RES_SAME, out=out, fmt=fmt))
+        for t in (n16, qkv, o16):
+            pool.put(t)
+        return out
+
+    def _upsample(self, layer, x):
+        """Standalone Upsample (resblock_updown=False): nearest x2 [+ conv3x3] (model.py:76-80)."""
+        B, fmt, pool = self.B, self.fmt, self.pool
+        _, H, W, C = x.shape
+        up = pool.get((B, 2 * H, 2 * W, C), torch.float32)
+        self.steps.append(lambda: ops.resample_f32(x, L.RESAMPLE_UP2, out=up))
+        if not layer.with_conv:
+            return up
+        Cout = layer.conv.weight.shape[0]
+        a = pool.get((B, 2 * H, 2 * W, C), self.dt16)
+        out = pool.get((B, 2 * H, 2 * W, Cout), torch.float32)
+        wp = self._packed(layer.conv.weight); bp = self._copy_param(layer.conv.bias)
+        self.steps.append(lambda: ops.cast16(up, out=a, fmt=fmt))
+        self.steps.append(lambda: ops.conv_gemm([(a, wp)], B, 2 * H, 2 * W, Cout, bias=bp, out=out, fmt=fmt))
+        pool.put(up); pool.put(a)
+        return out
+
+    def _downsample(self, layer, x):
+        """Standalone Downsample: conv3x3 stride 2 (as nine 1x1 K-segments over a gathered operand) or avg-pool."""
+        B, fmt, pool = self.B, self.fmt, self.pool
+        _, H, W, C = x.shape
+        if not layer.with_conv:
+            out = pool.get((B, H // 2, W // 2, C), torch.float32)
+            self.steps.append(lambda: ops.resample_f32(x, L.RESAMPLE_DOWN2, out=out))
+            return out
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        Cout = layer.conv.weight.shape[0]
+        cols = pool.get((9, B, Ho, Wo, C), self.dt16)
+        out = pool.get((B, Ho, Wo, Cout), torch.float32)
+        wp = self._packed(layer.conv.weight); bp = self._copy_param(layer.conv.bias)
+        segs = [(cols[tap], wp[tap:tap + 1]) for tap in range(9)]
+        self.steps.append(lambda: ops.im2col_s2(x, out=cols, fmt=fmt))
+        self.steps.append(lambda: ops.conv_gemm(segs, B, Ho, Wo, Cout, bias=bp, out=out, fmt=fmt))
+        pool.put(cols)
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    # execution
+    # ------------------------------------------------------------------------------------------
+    def _launch_all(self):
+        for f in self.steps:
+            f()
+
+    def run_static(self):
+        """Run the plan on the static input buffers (x_in, t_in, y_in) -> self.out."""
+        if self.model.use_cuda_graph:
+            if self.graph is None:
+                # warm up eagerly on a side stream (also sets kernel attributes), then capture
+                s = torch.cuda.Stream(device=self.device)
+                s.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(s):
+                    self._launch_all()
+                torch.cuda.current_stream(self.device).wait_stream(s)
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch_all()
+                self.graph = g
+            self.graph.replay()
+            ops.LAUNCHES += self.num_kernels
+        else:
+            self._launch_all()
+        return self.out
+
+    @torch.no_grad()
+    def forward(self, x, timestep, y):
+        self.refresh_weights()
+        self.x_in.copy_(x)
+        self.t_in.copy_(timestep)
+        if self.y_in is not None:
+            self.y_in.copy_(y)
+        return self.run_static().clone()

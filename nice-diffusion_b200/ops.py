@@ -85,16 +85,25 @@ def conv_gemm(segments, N, H, W, cout, bias=None, residual=None, residual_mode=L
     return out
 
 
-def gn_stats(x0, x1=None, pre_add=None, stats=None):
-    """x0 [N,H,W,C0] (+ x1 [N,H,W,C1]) fp32 -> fp64 [N,32,2] (sum, sumsq). `stats` must be zeroed."""
+def gn_workspace(N, HW, C, device):
+    """Zero-filled scratch for gn_stats (see ndb_gn_stats_workspace_bytes)."""
+    nbytes = int(L.load().ndb_gn_stats_workspace_bytes(N, HW, C))
+    return torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device=device)
+
+
+def gn_stats(x0, x1=None, pre_add=None, stats=None, workspace=None):
+    """x0 [N,H,W,C0] (+ x1 [N,H,W,C1]) fp32 -> fp64 [N,32,2] (sum, sumsq). Deterministic (no fp atomics)."""
     L.require_device(x0, 'gn_stats')
     N = x0.shape[0]
     HW = x0.shape[1] * x0.shape[2]
+    C = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
     if stats is None:
-        stats = torch.zeros((N, 32, 2), dtype=torch.float64, device=x0.device)
+        stats = torch.empty((N, 32, 2), dtype=torch.float64, device=x0.device)
+    if workspace is None:
+        workspace = gn_workspace(N, HW, C, x0.device)
     L.check(L.load().ndb_gn_stats(L.ptr(x0), x0.shape[-1], L.ptr(x1), x1.shape[-1] if x1 is not None else 0, N, HW,
                                   L.ptr(pre_add), pre_add.stride(0) if pre_add is not None else 0,
-                                  L.ptr(stats), L.stream_ptr()), 'ndb_gn_stats')
+                                  L.ptr(stats), L.ptr(workspace), L.stream_ptr()), 'ndb_gn_stats')
     _count()
     return stats
 
@@ -206,7 +215,7 @@ def im2col_s2(x, out=None, fmt=L.FMT_FP16):
 
 def sampler_step(x_t, model_out, t, tables, var_type, ddim=False, eta=0.0, null_out=None, cfg_strength=0.0,
                  grad=None, clf_strength=0.0, clip_x0=True, noise=None, seed=0, sample_ids=None,
-                 x_prev=None, pred_x0=None):
+                 x_prev=None, pred_x0=None, x_prev2=None):
     L.require_device(x_t, 'sampler_step')
     B, Cc, H, W = x_t.shape
     p = L.StepParams()
@@ -231,9 +240,16 @@ def sampler_step(x_t, model_out, t, tables, var_type, ddim=False, eta=0.0, null_
         x_prev = torch.empty_like(x_t)
     p.x_prev = x_prev.data_ptr()
     p.pred_x0 = pred_x0.data_ptr() if pred_x0 is not None else None
+    p.x_prev2 = x_prev2.data_ptr() if x_prev2 is not None else None
     L.check(L.load().ndb_sampler_step(C.byref(p), L.stream_ptr()), 'ndb_sampler_step')
     _count()
     return x_prev
+
+
+def advance_step(t_step, t_model, timestep_map_f32):
+    L.check(L.load().ndb_advance_step(L.ptr(t_step), t_step.shape[0], L.ptr(t_model), t_model.shape[0],
+                                      L.ptr(timestep_map_f32), L.stream_ptr()), 'ndb_advance_step')
+    _count()
 
 
 def philox_normal(shape, seed, sample_ids, step, device, out=None):
