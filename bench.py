@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Benchmark of the sampling hot path (BASELINE.json: images/sec, ImageNet-64 UNet, 250-step respaced DDPM with
+learned-interpolated variance, batch 256 sharded over 8 B200 = 32 images per GPU; weak scaling).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config in64|emnist|in128]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one denoising step (UNet forward + fused sampler step) over the rank's batch, replayed as one CUDA
+graph. `value` = images/sec of the whole job for the full chain: N * B / (steps_per_image * t_step), device-timed,
+max over ranks. `e2e` = the same metric through the public API (`Diffusion.denoise`) for one complete chain, with
+x_T / labels coming from pinned host memory and the finished images copied back, all inside the timed region.
+`roofline` = algorithmic FLOPs of every implicit-GEMM conv launch / its measured duration (CUDA events around each
+launch of an eager pass of the same plan) against the measured dense bf16 peak. `cpu_baseline` = the oracle port of
+the reference's --cpu path on the host cores (bounded sample). `--impl reference` times that CPU path alone.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (oracle config key, diffusion kwargs, per-GPU batch, steps per image)
+    'in64': ('in64', dict(original_num_steps=1000, rescaled_num_steps=250, beta_schedule='cosine',
+                          sampling_var_type='learned_interpolation', loss_type='hybrid'), 32, 250),
+    'emnist': ('emnist', dict(original_num_steps=1000, rescaled_num_steps=25, beta_schedule='cosine',
+                              sampling_var_type='learned_interpolation', loss_type='hybrid',
+                              guidance_method='classifier_free', guidance_strength=0.8), 16, 25),
+    'in128': ('in128', dict(original_num_steps=1000, rescaled_num_steps=50, beta_schedule='linear',
+                            sampling_var_type='learned_interpolation', loss_type='hybrid', use_ddim=True, ddim_eta=0.0,
+                            guidance_method='classifier_free', guidance_strength=0.8), 8, 50),
+}
+# algorithmic FLOPs per image per UNet forward (counted on the reference modules)
+FLOPS_PER_FWD = {'in64': 219356037120, 'emnist': 3998584832, 'in128': 613855789056}
+
+
+def model_config(name):
+    from nice_diffusion_b200 import default_args as da
+    cfg = dict({'in64': da.OPENAI_64_MODEL_ARGS, 'emnist': da.EMNIST_MODEL_ARGS, 'in128': da.OPENAI_128_MODEL_ARGS}[name])
+    if name == 'in128':
+        cfg['num_classes'] = 1001  # CFG adds the null class (utils.py:211-212)
+    return cfg
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(bf16=p['bf16_tflops'], bf16_sustained=p.get('bf16_tflops_sustained', p['bf16_tflops']),
+                    hbm=p['hbm_gbs'], source='measured')
+    return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, source='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def cpu_reference_arm(workload, steps, warmup, sample_batch=None):
+    """The reference's own --cpu path (Diffusion.denoise on the host, sample.py:27-28) as restated by the oracle
+    port: `steps` denoising steps on a bounded sample of the workload's batch."""
+    from oracle import CONFIGS
+    from oracle.sampler import Sampler
+    from oracle.unet import unet_forward
+    from oracle.weights import random_state_dict
+    import numpy as np
+    cname, dkw, _, per_image = WORKLOADS[workload]
+    cfg = CONFIGS[cname]
+    if workload == 'in128':
+        cfg = dict(cfg); cfg['num_classes'] = 1001
+    if sample_batch is None:
+        sample_batch = {'in64': 2, 'emnist': 16, 'in128': 1}[workload]
+    sd = random_state_dict(cfg, seed=0)
+    okw = {k: v for k, v in dkw.items() if k != 'loss_type'}
+
+    def model_fn(x, t, y=None):
+        return unet_forward(cfg, sd, x, t, y)
+    s = Sampler(model_fn, **okw)
+    rs = np.random.RandomState(0)
+    x = torch.from_numpy(rs.standard_normal((sample_batch, cfg['in_channels'], cfg['resolution'],
+                                             cfg['resolution'])).astype(np.float32))
+    y = torch.from_numpy(rs.randint(1, cfg['num_classes'], size=(sample_batch,)).astype(np.int64))
+    R = len(s.tab.betas)
+    t_hi = R - 1
+    step = s.ddim_step if okw.get('use_ddim') else s.ddpm_step
+    with torch.no_grad():
+        for i in range(warmup):
+            x, _ = step(x, torch.full((sample_batch,), float(t_hi - i)), {'y': y}, torch.randn_like(x))
+        t0 = time.perf_counter()
+        for i in range(steps):
+            x, _ = step(x, torch.full((sample_batch,), float(max(t_hi - warmup - i, 0))), {'y': y}, torch.randn_like(x))
+        dt = time.perf_counter() - t0
+    t_step = dt / steps
+    return dict(value=sample_batch / (per_image * t_step), ms_per_step=1e3 * t_step, cores=torch.get_num_threads(),
+                sample='{} denoising steps (+{} warm-up) of the {} chain at batch {} on the host, oracle port of the '
+                       'reference --cpu path; images/sec = batch / ({} steps x time per step)'.format(
+                           steps, warmup, workload, sample_batch, per_image), batch=sample_batch)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', type=str, default='ndb200', choices=['ndb200', 'reference'])
+    ap.add_argument('--config', type=str, default='in64', choices=sorted(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=None, help='per-GPU batch (default: the BASELINE value)')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--eager', action='store_true', help='launch kernels one by one instead of replaying CUDA graphs (profiling)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    cname, dkw, B, per_image = WORKLOADS[args.config]
+    if args.batch:
+        B = args.batch
+    metric = 'images/sec ({} UNet, {}-step {} sampling)'.format(
+        {'in64': 'ImageNet-64', 'emnist': 'EMNIST', 'in128': 'ImageNet-128'}[args.config], per_image,
+        'DDIM' if dkw.get('use_ddim') else 'DDPM')
+    config = {'workload': '{}: {} steps/image, {}, per-GPU batch {} (global {}), {}'.format(
+        args.config, per_image, dkw['sampling_var_type'], B, B * world,
+        'classifier-free guidance as a doubled batch' if dkw.get('guidance_method') else 'no guidance'),
+        'global_batch': B * world, 'per_gpu_batch': B, 'steps_per_image': per_image,
+        'parallelism': 'batch-sharded x{} (no collective on the data path)'.format(world),
+        'operands': 'fp16 tensor-core operands, fp32 accumulate, fp32 residual stream',
+        'l2': 'no flush needed: one step touches ~0.6 GB of weights + several GB of activations (>> 126 MB L2)'}
+
+    # ------------------------------------------------------------------ reference (CPU) arm
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        small = args.steps > 40
+        r = cpu_reference_arm(args.config, args.steps, args.warmup,
+                              sample_batch=({'in64': 1, 'emnist': 16, 'in128': 1}[args.config] if small else None))
+        line = {'impl': 'reference', 'metric': metric, 'value': r['value'], 'unit': 'images/sec', 'n_gpus': args.gpus,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+                'cpu_baseline': {'value': r['value'], 'unit': 'images/sec', 'cores': r['cores'], 'kind': 'port',
+                                 'sample': r['sample']},
+                'e2e': {'value': r['value'], 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ ndb200 arm
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the ndb200 path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+
+    from nice_diffusion_b200 import ops
+    from nice_diffusion_b200.diffusion import Diffusion
+    from nice_diffusion_b200.model import DiffusionModel
+    from nice_diffusion_b200.utils import randomize_zero_init_
+
+    torch.manual_seed(0)
+    model = DiffusionModel(**model_config(args.config))
+    randomize_zero_init_(model, seed=0)
+    model = model.to(dev).eval()
+    model.use_cuda_graph = not args.eager
+    diff = Diffusion(model=model, device=dev, **dkw)
+    diff.noise, diff.seed = 'philox', 1234
+    ids = torch.arange(rank * B, (rank + 1) * B, device=dev, dtype=torch.long)   # global sample indices
+    diff.sample_ids = ids
+    g = torch.Generator(device='cpu').manual_seed(1)
+    labels_host = torch.randint(1, 1000 if args.config != 'emnist' else 27, (B * world,), generator=g)[rank * B:(rank + 1) * B]
+    labels_host = labels_host.pin_memory()
+    x_host = torch.randn((B, model.in_channels, model.resolution, model.resolution), generator=g).pin_memory()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- kernel-only timing: K graph replays of one denoising step, inputs resident in HBM ----
+    runner = diff.make_step_runner(x_host.to(dev), {'y': labels_host.to(dev)})
+    for _ in range(args.warmup):
+        runner.step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ops.LAUNCHES
+    ev0.record()
+    for _ in range(args.steps):
+        runner.step()
+    ev1.record()
+    barrier()
+    launches = ops.LAUNCHES - launches0
+    clk = clocks.stop()
+    ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    ms_per_step = ms / args.steps
+    value = world * B / (per_image * ms_per_step * 1e-3)
+
+    # ---- end to end through the public API: one complete chain, host buffers in and out ----
+    e2e = None
+    if not args.no_e2e:
+        diff.noise = 'philox'
+        out_host = torch.empty((B, model.in_channels, model.resolution, model.resolution)).pin_memory()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        x_dev = x_host.to(dev, non_blocking=True)
+        y_dev = labels_host.to(dev, non_blocking=True)
+        out = diff.denoise(x=x_dev, kwargs={'y': y_dev}, batch_size=B, progress=False)
+        out_host.copy_(out, non_blocking=True)
+        e1.record()
+        barrier()
+        ems = e0.elapsed_time(e1)
+        if dist is not None:
+            tmax = torch.tensor([ems], device=dev)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            ems = float(tmax.item())
+        h2d = x_host.numel() * 4 + labels_host.numel() * 8
+        d2h = out_host.numel() * 4
+        e2e = {'value': world * B / (ems * 1e-3), 'unit': 'images/sec', 'h2d_bytes_per_step': h2d / per_image,
+               'd2h_bytes_per_step': d2h / per_image, 'steps_per_call': per_image, 'h2d_bytes_per_call': h2d,
+               'd2h_bytes_per_call': d2h, 'ms_per_call': ems,
+               'what': 'Diffusion.denoise(x=pinned host x_T -> device, labels) for the full chain + D2H of the images'}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (implicit-GEMM conv), measured live with CUDA events per launch ----
+    pk = peaks()
+    prof = runner.profile_kernels()
+    conv = prof['conv_gemm']
+    achieved = conv['flops'] / (conv['ms'] * 1e-3) / 1e12
+    fwd_tflops = FLOPS_PER_FWD[args.config] * runner.model_batch / (ms_per_step * 1e-3) / 1e12
+    roofline = {'bound': 'tensor', 'kernel': 'conv_gemm_kernel (tcgen05 implicit GEMM, all conv / linear layers)',
+                'achieved': achieved, 'peak': pk['bf16_sustained'], 'unit': 'TFLOP/s', 'frac': achieved / pk['bf16_sustained'],
+                'peak_kind': pk['source'] + ' sustained dense bf16 (kernel timed inside a long step)',
+                'frac_of_burst_peak': achieved / pk['bf16'], 'traffic': None,
+                'launches_per_step': conv['launches'], 'ms_per_step_in_kernel': conv['ms'],
+                'share_of_step': conv['ms'] / prof['total_ms'],
+                'unet_forward': {'tflops': fwd_tflops, 'frac': fwd_tflops / pk['bf16_sustained'],
+                                 'what': 'algorithmic FLOPs of one UNet forward x batch / graph-replayed step time'},
+                'other_kernels_ms': {k: v['ms'] for k, v in prof.items() if isinstance(v, dict) and k != 'conv_gemm'}}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        r = cpu_reference_arm(args.config, 2, 1)
+        cpu = {'value': r['value'], 'unit': 'images/sec', 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']}
+
+    line = {'metric': metric, 'value': value, 'unit': 'images/sec', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'fp16', 'data': 'synthetic', 'config': config, 'clocks': clk,
+            'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -310,78 +310,120 @@ class Diffusion:
         return x
 
     def _denoise_graph(self, x, kwargs, steps_to_do, progress, noise):
-        """One CUDA-graph replay per step: [UNet plan (doubled batch under CFG) -> fused step kernel (writes x_{t-1}
-        straight into the UNet's input buffer) -> device-side step counter]. No host<->device traffic inside the loop."""
-        B = x.shape[0]
-        cfg = self.guidance == 'classifier_free'
-        Bm = 2 * B if cfg else B
-        model = self.model
-        eng = model.engine_for(torch.empty((Bm, 0), device=self.device))
+        runner = self.make_step_runner(x, kwargs, steps_to_do=steps_to_do, noise=noise)
+        indices = range(steps_to_do)
+        if progress:
+            indices = tqdm.tqdm(indices, total=steps_to_do)
+        for _ in indices:
+            runner.step()
+        return runner.result()
+
+    def make_step_runner(self, x, kwargs=None, steps_to_do=None, noise=None):
+        """Device-resident sampling state: `.step()` advances the whole batch by one denoising step with a single
+        CUDA-graph replay; `.result()` returns the current x. Used by `denoise` and by bench.py."""
+        if steps_to_do is None:
+            steps_to_do = len(self.betas)
+        return _StepRunner(self, x.to(self.device, torch.float32).contiguous(), kwargs or {}, steps_to_do, noise)
+
+    # ------------------------------------------------------------------------------------------
+    def loss(self, x_0, t, kwargs=None, noise=None):
+        raise NotImplementedError('training loss (reference diffusion.py:375-438) is outside the sampling hot path '
+                                  'built so far (SURVEY.md section 8 f-1)')
+
+
+class _StepRunner:
+    """One CUDA-graph replay per step: [UNet plan (doubled batch under CFG) -> fused step kernel (writes x_{t-1}
+    straight into the UNet's input buffer) -> device-side step counter]. Nothing crosses the host<->device boundary
+    inside the loop (the reference does >= 7 H2D copies per step, diffusion.py:216,492)."""
+
+    def __init__(self, diff, x, kwargs, steps_to_do, noise):
+        self.diff = diff
+        self.B = B = x.shape[0]
+        self.cfg = cfg = diff.guidance == 'classifier_free'
+        if diff.guidance == 'classifier':
+            raise L.NdbError('classifier guidance runs through the step-wise path (needs autograd each step)')
+        self.model_batch = Bm = 2 * B if cfg else B
+        model, dev = diff.model, diff.device
+        self.eng = eng = model.engine_for(torch.empty((Bm, 0), device=dev))
         eng.refresh_weights()
-        tabs = self._tables()
-        key = (B, cfg, id(eng), self.use_ddim)
-        st = self._step_graphs.get(key)
+        self.tabs = diff._tables()
+        key = (B, cfg, id(eng), diff.use_ddim)
+        st = diff._step_graphs.get(key)
         if st is None:
-            st = dict(t_step=torch.zeros((B,), dtype=torch.float32, device=self.device),
-                      noise=torch.zeros_like(x), ids=torch.arange(B, device=self.device, dtype=torch.long),
-                      graphs={})
-            self._step_graphs[key] = st
-        # inputs of this run
+            st = dict(t_step=torch.zeros((B,), dtype=torch.float32, device=dev), noise=torch.zeros_like(x),
+                      ids=torch.arange(B, device=dev, dtype=torch.long), graphs={})
+            diff._step_graphs[key] = st
+        self.st = st
         eng.x_in[:B].copy_(x)
         if cfg:
             eng.x_in[B:].copy_(x)
         if model.conditional:
             eng.y_in[:B].copy_(kwargs['y'])
             if cfg:
-                eng.y_in[B:].zero_()
-        t0 = steps_to_do - 1
-        st['t_step'].fill_(float(t0))
-        eng.t_in.fill_(float(self.timestep_map[t0].item()))
-        if self.sample_ids is not None:
-            st['ids'].copy_(self.sample_ids)
+                eng.y_in[B:].zero_()    # null class 0 (diffusion.py:281)
+        self.t = steps_to_do - 1
+        st['t_step'].fill_(float(self.t))
+        eng.t_in.fill_(float(diff.timestep_map[self.t].item()))
+        if diff.sample_ids is not None:
+            st['ids'].copy_(diff.sample_ids)
         else:
-            st['ids'].copy_(torch.arange(B, device=self.device, dtype=torch.long))
-        use_philox = noise is None and self.noise == 'philox'
-        gkey = (use_philox, int(self.seed) if use_philox else 0)
-        g = st['graphs'].get(gkey)
+            st['ids'].copy_(torch.arange(B, device=dev, dtype=torch.long))
+        self.noise_rows = noise
+        self.use_philox = noise is None and diff.noise == 'philox'
+        self.gkey = (self.use_philox, int(diff.seed) if self.use_philox else 0)
+        self.kernels_per_step = eng.num_kernels + 2
 
-        def launch_step():
-            eng._launch_all()
-            out = eng.out
-            ops.sampler_step(eng.x_in[:B], out[:B], st['t_step'], tabs['tab'], self._var_code(), ddim=self.use_ddim,
-                             eta=self.ddim_eta if self.use_ddim else 0.0,
-                             null_out=out[B:] if cfg else None, cfg_strength=self.strength if cfg else 0.0,
-                             clip_x0=True, noise=None if use_philox else st['noise'], seed=self.seed,
-                             sample_ids=st['ids'], x_prev=eng.x_in[:B], x_prev2=eng.x_in[B:] if cfg else None)
-            ops.advance_step(st['t_step'], eng.t_in, tabs['tmap_f32'])
+    def _launch(self):
+        d, eng, st, B = self.diff, self.eng, self.st, self.B
+        eng._launch_all()
+        out = eng.out
+        ops.sampler_step(eng.x_in[:B], out[:B], st['t_step'], self.tabs['tab'], d._var_code(), ddim=d.use_ddim,
+                         eta=d.ddim_eta if d.use_ddim else 0.0, null_out=out[B:] if self.cfg else None,
+                         cfg_strength=d.strength if self.cfg else 0.0, clip_x0=True,
+                         noise=None if self.use_philox else st['noise'], seed=d.seed, sample_ids=st['ids'],
+                         x_prev=eng.x_in[:B], x_prev2=eng.x_in[B:] if self.cfg else None)
+        ops.advance_step(st['t_step'], eng.t_in, self.tabs['tmap_f32'])
 
-        indices = reversed(range(steps_to_do))
-        if progress:
-            indices = tqdm.tqdm(indices, total=steps_to_do)
-        for t in indices:
-            if not use_philox:
-                if noise is not None:
-                    st['noise'].copy_(noise[t])
-                else:
-                    st['noise'].normal_()
-            if not model.use_cuda_graph:
-                launch_step()
-                continue
-            if g is None:
-                # first step of the first run doubles as warm-up; capture from the second launch on
-                saved = (eng.x_in.clone(), st['t_step'].clone(), eng.t_in.clone())
-                launch_step()
-                torch.cuda.synchronize(self.device)
-                eng.x_in.copy_(saved[0]); st['t_step'].copy_(saved[1]); eng.t_in.copy_(saved[2])
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    launch_step()
-                st['graphs'][gkey] = g
-            g.replay()
-            ops.LAUNCHES += eng.num_kernels + 2
-        return eng.x_in[:B].clone()
+    def step(self):
+        d, eng, st = self.diff, self.eng, self.st
+        if not self.use_philox:
+            if self.noise_rows is not None:
+                st['noise'].copy_(self.noise_rows[max(self.t, 0)])
+            else:
+                st['noise'].normal_()      # torch's generator, like the reference's randn_like per step
+        self.t -= 1
+        if not d.model.use_cuda_graph:
+            self._launch()
+            return
+        g = st['graphs'].get(self.gkey)
+        if g is None:
+            # warm up once eagerly (kernel attributes, lazy allocations), restore the state, then capture
+            saved = (eng.x_in.clone(), st['t_step'].clone(), eng.t_in.clone())
+            self._launch()
+            torch.cuda.synchronize(d.device)
+            eng.x_in.copy_(saved[0]); st['t_step'].copy_(saved[1]); eng.t_in.copy_(saved[2])
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch()
+            st['graphs'][self.gkey] = g
+        g.replay()
+        ops.LAUNCHES += self.kernels_per_step
 
-    # ------------------------------------------------------------------------------------------
-    def loss(self, x_0, t, kwargs=None, noise=None):
-        raise NotImplementedError('training loss (reference diffusion.py:375-438) is outside the sampling hot path '
-                                  'built so far (SURVEY.md section 8 f-1)')
+    def result(self):
+        return self.eng.x_in[:self.B].clone()
+
+    def profile_kernels(self):
+        """Eager pass of one step with CUDA events around every launch (bench.py roofline). Restores the state."""
+        d, eng, st = self.diff, self.eng, self.st
+        saved = (eng.x_in.clone(), st['t_step'].clone(), eng.t_in.clone())
+        self._launch()                      # warm
+        torch.cuda.synchronize(d.device)
+        ops.PROFILE = []
+        try:
+            self._launch()
+            torch.cuda.synchronize(d.device)
+            summary = ops.profile_summary(ops.PROFILE)
+        finally:
+            ops.PROFILE = None
+        eng.x_in.copy_(saved[0]); st['t_step'].copy_(saved[1]); eng.t_in.copy_(saved[2])
+        return summary

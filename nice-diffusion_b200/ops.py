@@ -12,11 +12,38 @@ import torch
 from . import _lib as L
 
 LAUNCHES = 0
+PROFILE = None   # set to a list to record (kernel name, start event, end event, algorithmic flops) per launch
+_pending = None
 
 
-def _count():
+def _begin():
+    global _pending
+    if PROFILE is not None:
+        _pending = torch.cuda.Event(enable_timing=True)
+        _pending.record()
+
+
+def _count(name='kernel', flops=0):
     global LAUNCHES
     LAUNCHES += 1
+    if PROFILE is not None:
+        end = torch.cuda.Event(enable_timing=True)
+        end.record()
+        PROFILE.append((name, _pending, end, flops))
+
+
+def profile_summary(records):
+    """Aggregate PROFILE records (after a device synchronize) -> {name: {ms, launches, flops}, total_ms}."""
+    out, total = {}, 0.0
+    for name, e0, e1, flops in records:
+        ms = e0.elapsed_time(e1)
+        d = out.setdefault(name, {'ms': 0.0, 'launches': 0, 'flops': 0})
+        d['ms'] += ms
+        d['launches'] += 1
+        d['flops'] += flops
+        total += ms
+    out['total_ms'] = total
+    return out
 
 
 def dtype16(fmt):
@@ -40,9 +67,10 @@ def pack_conv_weight(w, cout_pad=None, cin_off=0, cin_len=None, fmt=L.FMT_FP16, 
     cin_len = cin - cin_off if cin_len is None else cin_len
     if out is None:
         out = torch.empty((k * k, cout_pad, cin_len), dtype=dtype16(fmt), device=w.device)
+    _begin()
     L.check(L.load().ndb_pack_conv_weight(L.ptr(w), L.ptr(out), cout, cin, k, cout_pad, cin_off, cin_len, fmt,
                                           L.stream_ptr()), 'ndb_pack_conv_weight')
-    _count()
+    _count('pack_conv_weight')
     return out
 
 
@@ -80,8 +108,9 @@ def conv_gemm(segments, N, H, W, cout, bias=None, residual=None, residual_mode=L
     p.operand_format = fmt
     p.block_n = block_n
     p.gn_stats = None
+    _begin()
     L.check(L.load().ndb_conv_gemm(C.byref(p), L.stream_ptr()), 'ndb_conv_gemm')
-    _count()
+    _count('conv_gemm', 2 * N * H * W * cout * sum(a.shape[-1] * w.shape[0] for a, w in segments))
     return out
 
 
@@ -101,10 +130,11 @@ def gn_stats(x0, x1=None, pre_add=None, stats=None, workspace=None):
         stats = torch.empty((N, 32, 2), dtype=torch.float64, device=x0.device)
     if workspace is None:
         workspace = gn_workspace(N, HW, C, x0.device)
+    _begin()
     L.check(L.load().ndb_gn_stats(L.ptr(x0), x0.shape[-1], L.ptr(x1), x1.shape[-1] if x1 is not None else 0, N, HW,
                                   L.ptr(pre_add), pre_add.stride(0) if pre_add is not None else 0,
                                   L.ptr(stats), L.ptr(workspace), L.stream_ptr()), 'ndb_gn_stats')
-    _count()
+    _count('gn_stats')
     return stats
 
 
@@ -139,8 +169,9 @@ def gn_apply(x0, stats, gamma, beta, x1=None, scale=None, shift=None, pre_add=No
     p.raw16 = raw16.data_ptr() if raw16 is not None else None
     p.operand_format = fmt
     p.eps = eps
+    _begin()
     L.check(L.load().ndb_gn_apply(C.byref(p), L.stream_ptr()), 'ndb_gn_apply')
-    _count()
+    _count('gn_apply')
     return (out, raw16) if (want_raw16 or raw16 is not None) else out
 
 
@@ -150,9 +181,10 @@ def attention(qkv16, B, T, heads, d, order=0, out=None, fmt=L.FMT_FP16):
     assert qkv16.is_contiguous() and qkv16.dtype == dtype16(fmt)
     if out is None:
         out = torch.empty((B, T, heads * d), dtype=qkv16.dtype, device=qkv16.device)
+    _begin()
     L.check(L.load().ndb_attention(L.ptr(qkv16), L.ptr(out), B, T, heads, d, order, fmt, L.stream_ptr()),
             'ndb_attention')
-    _count()
+    _count('attention', 4 * B * heads * T * T * d)
     return out
 
 
@@ -166,10 +198,11 @@ def embed(t, y, freqs, w0, b0, w2, b2, class_emb, emb_out=None, act_out=None, fm
         emb_out = torch.empty((B, E), dtype=torch.float32, device=t.device)
     if act_out is None:
         act_out = torch.empty((B, E), dtype=dtype16(fmt), device=t.device)
+    _begin()
     L.check(L.load().ndb_embed(L.ptr(t), L.ptr(y), L.ptr(freqs), B, mc, L.ptr(w0), L.ptr(b0), L.ptr(w2), L.ptr(b2),
                                L.ptr(class_emb) if y is not None else None, L.ptr(emb_out), L.ptr(act_out), fmt,
                                L.stream_ptr()), 'ndb_embed')
-    _count()
+    _count('embed')
     return emb_out, act_out
 
 
@@ -179,9 +212,10 @@ def stem_conv(x_nchw, w, bias, out=None):
     Cout = w.shape[0]
     if out is None:
         out = torch.empty((N, H, W, Cout), dtype=torch.float32, device=x_nchw.device)
+    _begin()
     L.check(L.load().ndb_stem_conv(L.ptr(x_nchw), L.ptr(w), L.ptr(bias), L.ptr(out), N, Cin, H, W, Cout,
                                    L.stream_ptr()), 'ndb_stem_conv')
-    _count()
+    _count('stem_conv')
     return out
 
 
@@ -190,16 +224,18 @@ def resample_f32(x, mode, out=None):
     Ho, Wo = (2 * H, 2 * W) if mode == L.RESAMPLE_UP2 else (H // 2, W // 2)
     if out is None:
         out = torch.empty((N, Ho, Wo, Cc), dtype=torch.float32, device=x.device)
+    _begin()
     L.check(L.load().ndb_resample_f32(L.ptr(x), L.ptr(out), N, H, W, Cc, mode, L.stream_ptr()), 'ndb_resample_f32')
-    _count()
+    _count('resample_f32')
     return out
 
 
 def cast16(x, out=None, fmt=L.FMT_FP16):
     if out is None:
         out = torch.empty(x.shape, dtype=dtype16(fmt), device=x.device)
+    _begin()
     L.check(L.load().ndb_cast_nhwc16(L.ptr(x), L.ptr(out), x.numel(), fmt, L.stream_ptr()), 'ndb_cast_nhwc16')
-    _count()
+    _count('cast_nhwc16')
     return out
 
 
@@ -208,8 +244,9 @@ def im2col_s2(x, out=None, fmt=L.FMT_FP16):
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     if out is None:
         out = torch.empty((9, N, Ho, Wo, Cc), dtype=dtype16(fmt), device=x.device)
+    _begin()
     L.check(L.load().ndb_im2col_s2(L.ptr(x), L.ptr(out), N, H, W, Cc, fmt, L.stream_ptr()), 'ndb_im2col_s2')
-    _count()
+    _count('im2col_s2')
     return out
 
 
@@ -241,15 +278,17 @@ def sampler_step(x_t, model_out, t, tables, var_type, ddim=False, eta=0.0, null_
     p.x_prev = x_prev.data_ptr()
     p.pred_x0 = pred_x0.data_ptr() if pred_x0 is not None else None
     p.x_prev2 = x_prev2.data_ptr() if x_prev2 is not None else None
+    _begin()
     L.check(L.load().ndb_sampler_step(C.byref(p), L.stream_ptr()), 'ndb_sampler_step')
-    _count()
+    _count('sampler_step')
     return x_prev
 
 
 def advance_step(t_step, t_model, timestep_map_f32):
+    _begin()
     L.check(L.load().ndb_advance_step(L.ptr(t_step), t_step.shape[0], L.ptr(t_model), t_model.shape[0],
                                       L.ptr(timestep_map_f32), L.stream_ptr()), 'ndb_advance_step')
-    _count()
+    _count('advance_step')
 
 
 def philox_normal(shape, seed, sample_ids, step, device, out=None):
@@ -259,9 +298,10 @@ def philox_normal(shape, seed, sample_ids, step, device, out=None):
         per *= s
     if out is None:
         out = torch.empty(shape, dtype=torch.float32, device=device)
+    _begin()
     L.check(L.load().ndb_philox_normal(L.ptr(out), B, per, int(seed) & 0xFFFFFFFFFFFFFFFF, L.ptr(sample_ids), step,
                                        L.stream_ptr()), 'ndb_philox_normal')
-    _count()
+    _count('philox_normal')
     return out
 
 
@@ -271,9 +311,10 @@ def qsample(x0, noise, t, sqrt_abar, sqrt_1m_abar, out=None):
     per = x0.numel() // B
     if out is None:
         out = torch.empty_like(x0)
+    _begin()
     L.check(L.load().ndb_qsample(L.ptr(x0), L.ptr(noise), L.ptr(t), L.ptr(sqrt_abar), L.ptr(sqrt_1m_abar),
                                  L.ptr(out), B, per, L.stream_ptr()), 'ndb_qsample')
-    _count()
+    _count('qsample')
     return out
 
 
@@ -281,6 +322,7 @@ def to_uint8(x_nchw, out=None):
     B, Cc, H, W = x_nchw.shape
     if out is None:
         out = torch.empty((B, H, W, Cc), dtype=torch.uint8, device=x_nchw.device)
+    _begin()
     L.check(L.load().ndb_to_uint8(L.ptr(x_nchw), L.ptr(out), B, Cc, H, W, L.stream_ptr()), 'ndb_to_uint8')
-    _count()
+    _count('to_uint8')
     return out
