@@ -135,10 +135,11 @@ int ndb_attention(const void* qkv, void* out, int B, int T, int heads, int d, in
  * Replaces timestep_embedding + step_embed MLP + class_embedding add + the SiLU in front of every
  * ResBlock's step_embedding Linear (model.py:456-459,514-523,197).
  * freqs: [mc/2] fp32 (built by the host with the reference formula); t: [B] fp32 timesteps;
- * y: [B] int64 labels or NULL. emb_out: [B][4mc] fp32 (optional); act_out: 16-bit SiLU(emb) [B][4mc]. */
+ * y: [B] int64 labels or NULL. h1_scratch: [B][4mc] fp32 workspace. emb_out: [B][4mc] fp32 (optional);
+ * act_out: 16-bit SiLU(emb) [B][4mc]. Two launches (one per Linear layer). */
 int ndb_embed(const float* t, const int64_t* y, const float* freqs, int B, int mc,
               const float* w0, const float* b0, const float* w2, const float* b2, const float* class_emb,
-              float* emb_out, void* act_out, int operand_format, void* stream);
+              float* h1_scratch, float* emb_out, void* act_out, int operand_format, void* stream);
 
 /* ---- stem conv / small direct convs ------------------------------------------------------------------
  * conv3x3 s1 p1 with tiny Cin (model.py:367): x NCHW fp32 [N,Cin,H,W] -> NHWC fp32 [N,H,W,Cout]. */

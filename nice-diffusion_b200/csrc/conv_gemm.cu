@@ -10,8 +10,11 @@
 // tcgen05.mma (128 x BLOCK_N x 16, fp32 accumulate in TMEM); accumulators are double-buffered in TMEM so
 // the epilogue of tile i overlaps the main loop of tile i+1. Persistent CTAs, one per SM.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> bias / residual -> global).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
+// Epilogue: each warp owns 32 accumulator rows (its TMEM lane quarter) and half of the tile's column chunks. Per
+// 32-column chunk it (1) issues the residual loads with lanes along channels (32 independent, fully coalesced 128-byte
+// requests in flight per warp), (2) pulls the chunk out of TMEM (thread = row), (3) transposes it through a padded
+// per-warp smem tile so that (4) bias + residual + the global store also run with lanes along channels.
 #include "common.cuh"
 #include "ptx.cuh"
 #include <cuda_fp16.h>
@@ -23,7 +26,9 @@ constexpr int kMaxSeg = NDB_MAX_SEGMENTS;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                        // 64 x 16-bit = one 128-byte swizzle row
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;
+constexpr int kEpiWarps = 8;
+constexpr int kStageFloats = 32 * 33;               // padded 32x32 transpose tile per epilogue warp
 constexpr int kMaxStages = 8;
 
 struct TmapPack {
@@ -45,6 +50,7 @@ struct ConvArgs {
     int stages;
     uint32_t a_box_bytes;
     uint32_t tmem_cols;
+    int acc_stride;   // TMEM columns between the two accumulator stages
     uint32_t idesc;
     const float* bias;
     const float* residual;
@@ -78,6 +84,8 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
     uint64_t* tmem_full_bar = empty_bar + kMaxStages;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    float* epi_stage = reinterpret_cast<float*>(smem + p.stages * stage_bytes + 256);
+    long long* epi_rows = reinterpret_cast<long long*>(epi_stage + kEpiWarps * kStageFloats);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -94,7 +102,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full_bar[s], 1);
-            mbar_init(&tmem_empty_bar[s], 4);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty_bar[s], kEpiWarps);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -152,7 +160,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * p.block_n;
+                const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
                 for (int kb = 0; kb < p.total_kblocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -179,11 +187,19 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
         }
     } else {
         // ===================== epilogue warps =====================
-        const int q = warp & 3;            // TMEM lane quarter this warp may access
-        const int row = q * 32 + lane;     // accumulator row == pixel index inside the tile
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;       // which half of the column chunks
+        const int row = q * 32 + lane;          // accumulator row == pixel index inside the tile
+        float* stg = epi_stage + (warp - 2) * kStageFloats;
+        long long* row_out = epi_rows + (warp - 2) * 64;
+        long long* row_res = row_out + 32;
+        const int nch = (p.block_n + 31) >> 5;
+        const int ch_begin = half ? (nch + 1) / 2 : 0;
+        const int ch_end = half ? nch : (nch + 1) / 2;
         int acc = 0;
         uint32_t acc_phase = 0;
         const int pix_per_img = p.TH * p.TW;
+        const float* __restrict__ resp = p.residual;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int n_tile = tile % p.num_n_tiles;
             int m_tile = tile / p.num_n_tiles;
@@ -198,109 +214,96 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             const int n = tn_i * p.TN + tn, h = th_i * p.TH + th, w = tw_i * p.TW + tw;
             const bool valid = (tn < p.TN) && (n < p.N) && (h < p.H) && (w < p.W);
             const int col0 = n_tile * p.block_n;
-            const long long pix = ((long long)n * p.H + h) * p.W + w;
-
-            const float* res0 = nullptr;
-            const float* res1 = nullptr;
-            const float* res2 = nullptr;
-            const float* res3 = nullptr;
-            if (valid && p.residual != nullptr) {
-                if (p.res_mode == NDB_RES_SAME) {
-                    res0 = p.residual + pix * p.cout;
-                } else if (p.res_mode == NDB_RES_UP2) {
-                    const int Hh = p.H >> 1, Wh = p.W >> 1;
-                    res0 = p.residual + (((long long)n * Hh + (h >> 1)) * Wh + (w >> 1)) * p.cout;
-                } else if (p.res_mode == NDB_RES_DOWN2) {
-                    const int H2 = p.H * 2, W2 = p.W * 2;
-                    res0 = p.residual + (((long long)n * H2 + 2 * h) * W2 + 2 * w) * p.cout;
-                    res1 = res0 + p.cout;
-                    res2 = res0 + (long long)W2 * p.cout;
-                    res3 = res2 + p.cout;
-                }
+            // element offsets of this row's pixel (valid rows only)
+            long long out_off = 0, res_off = 0;
+            if (valid) {
+                const long long pix = ((long long)n * p.H + h) * p.W + w;
+                out_off = (p.out_kind == NDB_OUT_F32_NCHW) ? ((long long)n * p.cout * p.H + h) * p.W + w : pix * p.cout;
+                if (p.res_mode == NDB_RES_SAME) res_off = pix * p.cout;
+                else if (p.res_mode == NDB_RES_UP2)
+                    res_off = (((long long)n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1)) * p.cout;
+                else if (p.res_mode == NDB_RES_DOWN2)
+                    res_off = (((long long)n * (2 * p.H) + 2 * h) * (2 * p.W) + 2 * w) * p.cout;
             }
+            const long long down_dx = p.cout, down_dy = (long long)(2 * p.W) * p.cout;
+            const unsigned valid_mask = __ballot_sync(0xffffffffu, valid);
+            // per-row element offsets, published to the warp through smem (invalid rows point at offset 0 and are
+            // masked) so the inner loops are free of shuffles and branches
+            __syncwarp();
+            row_out[lane] = out_off;
+            row_res[lane] = res_off;
+            __syncwarp();
 
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * p.block_n;
-            for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(t_row + c0, r);
-                tmem_ld_wait();
-                if (valid) {
-                    float v[16];
+            const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * p.acc_stride;
+            for (int ch = ch_begin; ch < ch_end; ++ch) {
+                const int cl = ch * 32 + lane;             // column inside the tile owned by this lane (transposed view)
+                const int col = col0 + cl;
+                const bool colok = (cl < p.block_n) && (col < p.cout);
+                const unsigned okmask = colok ? valid_mask : 0u;
+                // (1) residual, lanes along channels: 32 independent coalesced loads in flight
+                float res[32];
+                if (p.res_mode == NDB_RES_NONE) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-                    const int c = col0 + c0;
-                    if (c + 16 <= p.cout) {
-                        if (p.bias != nullptr) {
+                    for (int r = 0; r < 32; ++r) res[r] = 0.f;
+                } else if (p.res_mode != NDB_RES_DOWN2) {
+                    const float* base = resp + col;
 #pragma unroll
-                            for (int i = 0; i < 16; i += 4) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c + i));
-                                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-                            }
+                    for (int r = 0; r < 32; ++r) {
+                        float v = 0.f;
+                        if ((okmask >> r) & 1u) v = __ldg(base + row_res[r]);
+                        res[r] = v;
+                    }
+                } else {
+                    const float* base = resp + col;
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+                        if ((okmask >> r) & 1u) {
+                            const float* a = base + row_res[r];
+                            v0 = __ldg(a); v1 = __ldg(a + down_dx); v2 = __ldg(a + down_dy); v3 = __ldg(a + down_dy + down_dx);
                         }
-                        if (res0 != nullptr) {
-#pragma unroll
-                            for (int i = 0; i < 16; i += 4) {
-                                float4 a4 = __ldg(reinterpret_cast<const float4*>(res0 + c + i));
-                                if (res1 != nullptr) {
-                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(res1 + c + i));
-                                    const float4 c4 = __ldg(reinterpret_cast<const float4*>(res2 + c + i));
-                                    const float4 d4 = __ldg(reinterpret_cast<const float4*>(res3 + c + i));
-                                    // same association as F.avg_pool2d: sum of the 4 taps, then * 0.25
-                                    a4.x = (a4.x + b4.x + c4.x + d4.x) * 0.25f;
-                                    a4.y = (a4.y + b4.y + c4.y + d4.y) * 0.25f;
-                                    a4.z = (a4.z + b4.z + c4.z + d4.z) * 0.25f;
-                                    a4.w = (a4.w + b4.w + c4.w + d4.w) * 0.25f;
-                                }
-                                v[i] += a4.x; v[i + 1] += a4.y; v[i + 2] += a4.z; v[i + 3] += a4.w;
-                            }
-                        }
-                        if (p.out_kind == NDB_OUT_F32_NHWC) {
-                            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.cout + c);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                        } else if (p.out_kind == NDB_OUT_F16_NHWC) {
-                            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + pix * p.cout + c);
-                            uint32_t w[8];
-                            if (p.fmt == 0) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) w[i] = pack2<0>(v[2 * i], v[2 * i + 1]);
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) w[i] = pack2<1>(v[2 * i], v[2 * i + 1]);
-                            }
-                            o[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                            o[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                        } else {  // NCHW fp32
-                            float* o = reinterpret_cast<float*>(p.out);
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                o[(((long long)n * p.cout + c + i) * p.H + h) * p.W + w] = v[i];
-                        }
-                    } else {
-                        // ragged channel tail (e.g. the 6-channel head in a 16-wide tile): scalar path
-                        for (int i = 0; i < 16; ++i) {
-                            const int cc = c + i;
-                            if (cc >= p.cout) break;
-                            float val = v[i];
-                            if (p.bias != nullptr) val += __ldg(p.bias + cc);
-                            if (res0 != nullptr) {
-                                float rr = __ldg(res0 + cc);
-                                if (res1 != nullptr) rr = (rr + __ldg(res1 + cc) + __ldg(res2 + cc) + __ldg(res3 + cc)) * 0.25f;
-                                val += rr;
-                            }
-                            if (p.out_kind == NDB_OUT_F32_NHWC) {
-                                reinterpret_cast<float*>(p.out)[pix * p.cout + cc] = val;
-                            } else if (p.out_kind == NDB_OUT_F16_NHWC) {
-                                if (p.fmt == 0) reinterpret_cast<__half*>(p.out)[pix * p.cout + cc] = __float2half_rn(val);
-                                else reinterpret_cast<__nv_bfloat16*>(p.out)[pix * p.cout + cc] = __float2bfloat16_rn(val);
-                            } else {
-                                reinterpret_cast<float*>(p.out)[(((long long)n * p.cout + cc) * p.H + h) * p.W + w] = val;
-                            }
-                        }
+                        // same association as F.avg_pool2d: sum of the four taps, then * 0.25
+                        res[r] = (v0 + v1 + v2 + v3) * 0.25f;
                     }
                 }
+                // (2) accumulator chunk out of TMEM (thread = row)
+                uint32_t racc[32];
+                tmem_ld32(t_row + ch * 32, racc);
+                tmem_ld_wait();
+                // (3) transpose through the padded per-warp tile
+#pragma unroll
+                for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __uint_as_float(racc[i]);
+                __syncwarp();
+                const float bias_v = (colok && p.bias != nullptr) ? __ldg(p.bias + col) : 0.f;
+                // (4) bias + residual + store, lanes along channels
+                if (p.out_kind == NDB_OUT_F32_NHWC) {
+                    float* ob = reinterpret_cast<float*>(p.out) + col;
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        const float v = stg[r * 33 + lane] + bias_v + res[r];
+                        if ((okmask >> r) & 1u) ob[row_out[r]] = v;
+                    }
+                } else if (p.out_kind == NDB_OUT_F16_NHWC) {
+                    uint16_t* ob = reinterpret_cast<uint16_t*>(p.out) + col;
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        const float v = stg[r * 33 + lane] + bias_v + res[r];
+                        uint16_t bits;
+                        if (p.fmt == 0) { __half hv = __float2half_rn(v); bits = *reinterpret_cast<uint16_t*>(&hv); }
+                        else { __nv_bfloat16 hv = __float2bfloat16_rn(v); bits = *reinterpret_cast<uint16_t*>(&hv); }
+                        if ((okmask >> r) & 1u) ob[row_out[r]] = bits;
+                    }
+                } else {
+                    float* ob = reinterpret_cast<float*>(p.out) + (long long)col * p.H * p.W;
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        const float v = stg[r * 33 + lane] + bias_v + res[r];
+                        if ((okmask >> r) & 1u) ob[row_out[r]] = v;
+                    }
+                }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
@@ -347,6 +350,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, uint16_t* __rest
 }
 
 static int pick_block_n(int cout_pad) {
+    // 192 first: it divides every ImageNet-64 width (192..2304) and leaves room for a 4-stage smem ring
+    if (cout_pad % 192 == 0) return 192;
     for (int bn = 256; bn >= 16; bn -= 16)
         if (cout_pad % bn == 0) return bn;
     return 0;
@@ -378,7 +383,6 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     NDB_CHECK_ARG(prm->out != nullptr);
     NDB_CHECK_ARG(prm->operand_format == 0 || prm->operand_format == 1);
     if (prm->gn_stats != nullptr) return NDB_ERR_UNSUPPORTED;
-    if (prm->out_kind != NDB_OUT_F32_NCHW) NDB_CHECK_ARG(prm->cout % 4 == 0 || prm->cout < 16);
     if (prm->residual_mode == NDB_RES_UP2) NDB_CHECK_ARG(prm->H % 2 == 0 && prm->W % 2 == 0);
 
     ConvArgs a{};
@@ -403,7 +407,8 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     a.cout = prm->cout;
     a.num_seg = prm->num_segments;
     a.a_box_bytes = (uint32_t)(a.TN * a.TH * a.TW * 128);
-    a.tmem_cols = a.block_n <= 16 ? 32 : a.block_n <= 32 ? 64 : a.block_n <= 64 ? 128 : a.block_n <= 128 ? 256 : 512;
+    a.acc_stride = (a.block_n + 31) / 32 * 32;
+    a.tmem_cols = a.acc_stride <= 32 ? 64 : a.acc_stride <= 64 ? 128 : a.acc_stride <= 128 ? 256 : 512;
     a.idesc = make_idesc_f16(kBlockM, a.block_n, prm->operand_format, 0, 0);
     a.bias = prm->bias;
     a.residual = prm->residual;
@@ -441,13 +446,14 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     }
 
     const int stage_bytes = kATileBytes + a.block_n * 128;
-    const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
+    const int epi_bytes = kEpiWarps * (kStageFloats * (int)sizeof(float) + 64 * (int)sizeof(long long));
+    const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - epi_bytes;
     int stages = smem_budget / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages > a.total_kblocks) stages = a.total_kblocks < 2 ? 2 : a.total_kblocks;
     NDB_CHECK_ARG(stages >= 2);
     a.stages = stages;
-    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 256;
+    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 256 + epi_bytes;
 
     static bool attr_set = false;
     if (!attr_set) {

@@ -100,7 +100,7 @@ gn_stats_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ 
 // ------------------------------------------------------------------------------------------------------
 // apply
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float silu_f(float v) { return v / (1.f + expf(-v)); }
+__device__ __forceinline__ float silu_f(float v) { return v * __frcp_rn(1.f + __expf(-v)); }
 
 template <int FMT>
 __device__ __forceinline__ uint32_t pack2h(float a, float b) {
@@ -124,103 +124,126 @@ struct GnApplyArgs {
     int silu, resample;
     uint16_t* out; uint16_t* raw16;
     float eps;
-    int items_per_block;
+    int pix_per_block, threads_per_row, rows_per_block;
 };
 
-template <int FMT>
+// Thread (r, v): fixed 8-channel vector v, output pixels p = p_begin + r, + rows_per_block, ...  The per-channel
+// affine (a, b) = (rstd*gamma*(1+scale), (beta - mean*rstd*gamma + a'*pre)*(1+scale) + shift) lives in registers.
+template <int FMT, int RESAMPLE, bool SILU>
 __global__ void __launch_bounds__(kGnThreads)
 gn_apply_kernel(const GnApplyArgs p) {
-    extern __shared__ float sm[];  // a[C], b[C], pre[C]
     const int C = p.C0 + p.C1;
+    const int V8 = C >> 3;
     const int n = blockIdx.y;
-    float* sa = sm;
-    float* sb = sm + C;
-    float* sp = sm + 2 * C;
+    const int r = threadIdx.x / p.threads_per_row;
+    const int tv = threadIdx.x - r * p.threads_per_row;
+    if (r >= p.rows_per_block) return;
     const int cpg = C / kGroups;
     const double inv_cnt = 1.0 / ((double)cpg * p.H * p.W);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int g = c / cpg;
-        const double s = p.stats[((size_t)n * kGroups + g) * 2 + 0];
-        const double ss = p.stats[((size_t)n * kGroups + g) * 2 + 1];
-        const double mean = s * inv_cnt;
-        double var = ss * inv_cnt - mean * mean;
-        if (var < 0.0) var = 0.0;
-        const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
-        const float ga = p.gamma[c], be = p.beta[c];
-        float a = rstd * ga;
-        float b = be - (float)mean * a;
-        const float pre = p.pre_add ? p.pre_add[(size_t)n * p.ld_pre + c] : 0.f;
-        b += a * pre;
-        if (p.scale != nullptr) {
-            const float sc = 1.f + p.scale[(size_t)n * p.ld_ss + c];
-            const float sh = p.shift[(size_t)n * p.ld_ss + c];
-            a *= sc;
-            b = b * sc + sh;
-        }
-        sa[c] = a;
-        sb[c] = b;
-        sp[c] = pre;
-    }
-    __syncthreads();
+    const int npix = p.Ho * p.Wo;
+    const int p_begin = blockIdx.x * p.pix_per_block;
+    int p_end = p_begin + p.pix_per_block;
+    if (p_end > npix) p_end = npix;
 
-    const int V8 = C >> 3;
-    const long long items = (long long)p.Ho * p.Wo * V8;
-    long long i0 = (long long)blockIdx.x * p.items_per_block;
-    long long i1 = i0 + p.items_per_block;
-    if (i1 > items) i1 = items;
-    for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-        const int v = (int)(i % V8);
-        const long long po = i / V8;
-        const int wo = (int)(po % p.Wo);
-        const int ho = (int)(po / p.Wo);
+    for (int v = tv; v < V8; v += p.threads_per_row) {
         const int c = v << 3;
+        float a[8], b[8], pre[8];
+        int g_prev = -1;
+        float mean_f = 0.f, rstd = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int g = (c + k) / cpg;
+            if (g != g_prev) {
+                const double s = p.stats[((size_t)n * kGroups + g) * 2 + 0];
+                const double ss = p.stats[((size_t)n * kGroups + g) * 2 + 1];
+                const double mean = s * inv_cnt;
+                double var = ss * inv_cnt - mean * mean;
+                if (var < 0.0) var = 0.0;
+                rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+                mean_f = (float)mean;
+                g_prev = g;
+            }
+            float ak = rstd * __ldg(p.gamma + c + k);
+            float bk = __ldg(p.beta + c + k) - mean_f * ak;
+            const float pr = p.pre_add ? __ldg(p.pre_add + (size_t)n * p.ld_pre + c + k) : 0.f;
+            bk += ak * pr;
+            if (p.scale != nullptr) {
+                const float sc = 1.f + __ldg(p.scale + (size_t)n * p.ld_ss + c + k);
+                ak *= sc;
+                bk = bk * sc + __ldg(p.shift + (size_t)n * p.ld_ss + c + k);
+            }
+            a[k] = ak; b[k] = bk; pre[k] = pr;
+        }
         const float* src;
         int ldc, cc;
         if (c < p.C0) { src = p.x0; ldc = p.C0; cc = c; } else { src = p.x1; ldc = p.C1; cc = c - p.C0; }
-        float y[8], raw[8];
-        if (p.resample == NDB_RESAMPLE_DOWN2) {
+        src += (size_t)n * p.H * p.W * ldc + cc;
+        uint16_t* outp = p.out + (size_t)n * npix * C + c;
+        uint16_t* rawp = p.raw16 ? p.raw16 + (size_t)n * npix * C + c : nullptr;
+
+#pragma unroll 2
+        for (int po = p_begin + r; po < p_end; po += p.rows_per_block) {
+            float y[8], raw[8];
+            if (RESAMPLE == NDB_RESAMPLE_DOWN2) {
+                const int ho = po / p.Wo, wo = po - ho * p.Wo;
+                const float* px = src + ((size_t)(2 * ho) * p.W + 2 * wo) * ldc;
+                const float4 l0 = __ldg(reinterpret_cast<const float4*>(px)), h0 = __ldg(reinterpret_cast<const float4*>(px + 4));
+                const float4 l1 = __ldg(reinterpret_cast<const float4*>(px + ldc)), h1 = __ldg(reinterpret_cast<const float4*>(px + ldc + 4));
+                const float* py = px + (size_t)p.W * ldc;
+                const float4 l2 = __ldg(reinterpret_cast<const float4*>(py)), h2 = __ldg(reinterpret_cast<const float4*>(py + 4));
+                const float4 l3 = __ldg(reinterpret_cast<const float4*>(py + ldc)), h3 = __ldg(reinterpret_cast<const float4*>(py + ldc + 4));
+                const float xv[4][8] = {{l0.x, l0.y, l0.z, l0.w, h0.x, h0.y, h0.z, h0.w},
+                                        {l1.x, l1.y, l1.z, l1.w, h1.x, h1.y, h1.z, h1.w},
+                                        {l2.x, l2.y, l2.z, l2.w, h2.x, h2.y, h2.z, h2.w},
+                                        {l3.x, l3.y, l3.z, l3.w, h3.x, h3.y, h3.z, h3.w}};
 #pragma unroll
-            for (int k = 0; k < 8; ++k) y[k] = raw[k] = 0.f;
+                for (int k = 0; k < 8; ++k) {
+                    float acc = 0.f, racc = 0.f;
 #pragma unroll
-            for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 2; ++dx) {
-                    const float* px = src + (((size_t)n * p.H + (2 * ho + dy)) * p.W + (2 * wo + dx)) * ldc + cc;
-                    const float4 lo = __ldg(reinterpret_cast<const float4*>(px));
-                    const float4 hi = __ldg(reinterpret_cast<const float4*>(px + 4));
-                    const float xv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        float t = sa[c + k] * xv[k] + sb[c + k];
-                        if (p.silu) t = silu_f(t);
-                        y[k] += t;
-                        raw[k] += xv[k] + sp[c + k];
+                    for (int q = 0; q < 4; ++q) {
+                        float t = a[k] * xv[q][k] + b[k];
+                        if (SILU) t = silu_f(t);
+                        acc += t;
+                        racc += xv[q][k] + pre[k];
                     }
+                    y[k] = acc * 0.25f;
+                    raw[k] = racc * 0.25f;
                 }
+            } else {
+                int pi = po;
+                if (RESAMPLE == NDB_RESAMPLE_UP2) {
+                    const int ho = po / p.Wo, wo = po - ho * p.Wo;
+                    pi = (ho >> 1) * p.W + (wo >> 1);
+                }
+                const float* px = src + (size_t)pi * ldc;
+                const float4 lo = __ldg(reinterpret_cast<const float4*>(px));
+                const float4 hi = __ldg(reinterpret_cast<const float4*>(px + 4));
+                const float xv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { y[k] *= 0.25f; raw[k] *= 0.25f; }
-        } else {
-            const int hi_ = (p.resample == NDB_RESAMPLE_UP2) ? (ho >> 1) : ho;
-            const int wi_ = (p.resample == NDB_RESAMPLE_UP2) ? (wo >> 1) : wo;
-            const float* px = src + (((size_t)n * p.H + hi_) * p.W + wi_) * ldc + cc;
-            const float4 lo = __ldg(reinterpret_cast<const float4*>(px));
-            const float4 hi = __ldg(reinterpret_cast<const float4*>(px + 4));
-            const float xv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                float t = sa[c + k] * xv[k] + sb[c + k];
-                if (p.silu) t = silu_f(t);
-                y[k] = t;
-                raw[k] = xv[k] + sp[c + k];
+                for (int k = 0; k < 8; ++k) {
+                    float t = a[k] * xv[k] + b[k];
+                    if (SILU) t = silu_f(t);
+                    y[k] = t;
+                    raw[k] = xv[k] + pre[k];
+                }
             }
+            const size_t o = (size_t)po * C;
+            *reinterpret_cast<uint4*>(outp + o) =
+                make_uint4(pack2h<FMT>(y[0], y[1]), pack2h<FMT>(y[2], y[3]), pack2h<FMT>(y[4], y[5]), pack2h<FMT>(y[6], y[7]));
+            if (rawp != nullptr)
+                *reinterpret_cast<uint4*>(rawp + o) = make_uint4(pack2h<FMT>(raw[0], raw[1]), pack2h<FMT>(raw[2], raw[3]),
+                                                                 pack2h<FMT>(raw[4], raw[5]), pack2h<FMT>(raw[6], raw[7]));
         }
-        const size_t o = (((size_t)n * p.Ho + ho) * p.Wo + wo) * C + c;
-        *reinterpret_cast<uint4*>(p.out + o) =
-            make_uint4(pack2h<FMT>(y[0], y[1]), pack2h<FMT>(y[2], y[3]), pack2h<FMT>(y[4], y[5]), pack2h<FMT>(y[6], y[7]));
-        if (p.raw16 != nullptr)
-            *reinterpret_cast<uint4*>(p.raw16 + o) = make_uint4(pack2h<FMT>(raw[0], raw[1]), pack2h<FMT>(raw[2], raw[3]),
-                                                                pack2h<FMT>(raw[4], raw[5]), pack2h<FMT>(raw[6], raw[7]));
     }
+}
+
+template <int FMT>
+static void launch_gn_apply(const GnApplyArgs& a, dim3 grid, cudaStream_t st) {
+#define NDB_GN_CASE(RS, SL) gn_apply_kernel<FMT, RS, SL><<<grid, kGnThreads, 0, st>>>(a)
+    if (a.resample == NDB_RESAMPLE_NONE) { if (a.silu) NDB_GN_CASE(NDB_RESAMPLE_NONE, true); else NDB_GN_CASE(NDB_RESAMPLE_NONE, false); }
+    else if (a.resample == NDB_RESAMPLE_UP2) { if (a.silu) NDB_GN_CASE(NDB_RESAMPLE_UP2, true); else NDB_GN_CASE(NDB_RESAMPLE_UP2, false); }
+    else { if (a.silu) NDB_GN_CASE(NDB_RESAMPLE_DOWN2, true); else NDB_GN_CASE(NDB_RESAMPLE_DOWN2, false); }
+#undef NDB_GN_CASE
 }
 
 }  // namespace ndb
@@ -294,18 +317,19 @@ extern "C" int ndb_gn_apply(const ndb_gn_apply_params* q, void* stream) {
     a.silu = q->silu; a.resample = q->resample;
     a.out = (uint16_t*)q->out; a.raw16 = (uint16_t*)q->raw16;
     a.eps = q->eps;
-    const long long items = (long long)a.Ho * a.Wo * (C / 8);
+    const int V8 = C / 8;
+    a.threads_per_row = V8 < kGnThreads ? V8 : kGnThreads;
+    a.rows_per_block = kGnThreads / a.threads_per_row;
+    const int npix = a.Ho * a.Wo;
     int blocks_per_sample = (8 * num_sms() + q->N - 1) / q->N;
-    long long ipb = (items + blocks_per_sample - 1) / blocks_per_sample;
-    const long long min_items = 4LL * kGnThreads;
-    if (ipb < min_items) ipb = min_items;
-    a.items_per_block = (int)ipb;
-    const int chunks = (int)((items + ipb - 1) / ipb);
-    dim3 grid(chunks, q->N);
-    const size_t smem = 3 * (size_t)C * sizeof(float);
+    int ppb = (npix + blocks_per_sample - 1) / blocks_per_sample;
+    const int min_pix = a.rows_per_block * 4;
+    if (ppb < min_pix) ppb = min_pix;
+    a.pix_per_block = ppb;
+    dim3 grid((npix + ppb - 1) / ppb, q->N);
     if (q->operand_format == 0)
-        gn_apply_kernel<0><<<grid, kGnThreads, smem, (cudaStream_t)stream>>>(a);
+        launch_gn_apply<0>(a, grid, (cudaStream_t)stream);
     else
-        gn_apply_kernel<1><<<grid, kGnThreads, smem, (cudaStream_t)stream>>>(a);
+        launch_gn_apply<1>(a, grid, (cudaStream_t)stream);
     return launch_status("ndb_gn_apply");
 }

@@ -22,52 +22,74 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// embedding front end: one CTA per sample
-//   te = [cos(t f) | sin(t f)]  ->  h1 = SiLU(W0 te + b0)  ->  emb = W2 h1 + b2 (+ class_emb[y])
+// embedding front end, two launches, one warp per output feature (weight row held in registers, looped over
+// the batch so every weight is read from HBM once per forward):
+//   L1: h1 = SiLU(W0 [cos(t f) | sin(t f)] + b0)      L2: emb = W2 h1 + b2 (+ class_emb[y]);  act = SiLU(emb)
 // ------------------------------------------------------------------------------------------------------
+constexpr int kEmbMaxMcPerLane = 16;   // model_channels <= 512
+constexpr int kEmbMaxEPerLane = 64;    // 4 * model_channels <= 2048
+
 __global__ void __launch_bounds__(256)
-embed_kernel(const float* __restrict__ t, const int64_t* __restrict__ y, const float* __restrict__ freqs, int mc,
-             const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w2,
-             const float* __restrict__ b2, const float* __restrict__ class_emb, float* __restrict__ emb_out,
-             uint16_t* __restrict__ act_out, int fmt) {
-    extern __shared__ float sm[];  // te[mc] h1[E]
+embed_l1_kernel(const float* __restrict__ t, const float* __restrict__ freqs, int B, int mc,
+                const float* __restrict__ w0, const float* __restrict__ b0, float* __restrict__ h1) {
     const int E = 4 * mc;
-    float* te = sm;
-    float* h1 = sm + mc;
-    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 8 + warp;
+    if (j >= E) return;
     const int half = mc / 2;
-    const float tb = t[b];
-    for (int i = threadIdx.x; i < mc; i += blockDim.x) {
-        float v = 0.f;  // zero pad for odd mc (model.py:521-522)
-        if (i < half) v = cosf(tb * freqs[i]);
-        else if (i < 2 * half) v = sinf(tb * freqs[i - half]);
-        te[i] = v;
+    float w[kEmbMaxMcPerLane], f[kEmbMaxMcPerLane];
+#pragma unroll
+    for (int i = 0; i < kEmbMaxMcPerLane; ++i) {
+        const int k = lane + 32 * i;
+        w[i] = (k < mc) ? __ldg(w0 + (size_t)j * mc + k) : 0.f;
+        f[i] = (k < 2 * half) ? __ldg(freqs + (k < half ? k : k - half)) : 0.f;
     }
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int j = warp; j < E; j += nwarps) {
-        const float* wr = w0 + (size_t)j * mc;
+    const float bj = b0[j];
+    for (int b = 0; b < B; ++b) {
+        const float tb = t[b];
         float acc = 0.f;
-        for (int k = lane; k < mc; k += 32) acc += __ldg(wr + k) * te[k];
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            const float v = acc + b0[j];
-            h1[j] = v / (1.f + expf(-v));
-        }
-    }
-    __syncthreads();
-    const float* ce = (y != nullptr && class_emb != nullptr) ? class_emb + (size_t)y[b] * E : nullptr;
-    for (int j = warp; j < E; j += nwarps) {
-        const float* wr = w2 + (size_t)j * E;
-        float acc = 0.f;
-        for (int k = lane * 4; k < E; k += 128) {
-            const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + k));
-            acc += w4.x * h1[k] + w4.y * h1[k + 1] + w4.z * h1[k + 2] + w4.w * h1[k + 3];
+#pragma unroll
+        for (int i = 0; i < kEmbMaxMcPerLane; ++i) {
+            const int k = lane + 32 * i;
+            if (k < 2 * half) {
+                const float ang = tb * f[i];
+                acc += w[i] * (k < half ? cosf(ang) : sinf(ang));   // zero pad for odd mc (model.py:521-522)
+            }
         }
         acc = warp_sum(acc);
         if (lane == 0) {
-            float v = acc + b2[j];
-            if (ce != nullptr) v += ce[j];
+            const float v = acc + bj;
+            h1[(size_t)b * E + j] = v / (1.f + expf(-v));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+embed_l2_kernel(const float* __restrict__ h1, const int64_t* __restrict__ y, int B, int E,
+                const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ class_emb,
+                float* __restrict__ emb_out, uint16_t* __restrict__ act_out, int fmt) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 8 + warp;
+    if (j >= E) return;
+    float w[kEmbMaxEPerLane];
+#pragma unroll
+    for (int i = 0; i < kEmbMaxEPerLane; ++i) {
+        const int k = lane + 32 * i;
+        w[i] = (k < E) ? __ldg(w2 + (size_t)j * E + k) : 0.f;
+    }
+    const float bj = b2[j];
+    for (int b = 0; b < B; ++b) {
+        const float* hb = h1 + (size_t)b * E;
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < kEmbMaxEPerLane; ++i) {
+            const int k = lane + 32 * i;
+            if (k < E) acc += w[i] * __ldg(hb + k);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            float v = acc + bj;
+            if (y != nullptr) v += __ldg(class_emb + (size_t)y[b] * E + j);
             if (emb_out != nullptr) emb_out[(size_t)b * E + j] = v;
             if (act_out != nullptr) act_out[(size_t)b * E + j] = to16(v / (1.f + expf(-v)), fmt);
         }
@@ -217,14 +239,16 @@ static inline int grid_for(long long work, int threads) {
 using namespace ndb;
 
 extern "C" int ndb_embed(const float* t, const int64_t* y, const float* freqs, int B, int mc, const float* w0,
-                         const float* b0, const float* w2, const float* b2, const float* class_emb, float* emb_out,
-                         void* act_out, int operand_format, void* stream) {
-    NDB_CHECK_ARG(t && freqs && w0 && b0 && w2 && b2 && B > 0 && mc > 0);
-    NDB_CHECK_ARG(mc % 4 == 0);
+                         const float* b0, const float* w2, const float* b2, const float* class_emb, float* h1_scratch,
+                         float* emb_out, void* act_out, int operand_format, void* stream) {
+    NDB_CHECK_ARG(t && freqs && w0 && b0 && w2 && b2 && h1_scratch && B > 0 && mc > 0);
+    NDB_CHECK_ARG(mc % 4 == 0 && mc <= 32 * kEmbMaxMcPerLane);
     NDB_CHECK_ARG((y == nullptr) == (class_emb == nullptr));
-    const size_t smem = (size_t)(mc + 4 * mc) * sizeof(float);
-    embed_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(t, y, freqs, mc, w0, b0, w2, b2, class_emb, emb_out,
-                                                        (uint16_t*)act_out, operand_format);
+    const int E = 4 * mc;
+    const int grid = (E + 7) / 8;
+    embed_l1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t, freqs, B, mc, w0, b0, h1_scratch);
+    embed_l2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h1_scratch, y, B, E, w2, b2, class_emb, emb_out,
+                                                           (uint16_t*)act_out, operand_format);
     return launch_status("ndb_embed");
 }
 

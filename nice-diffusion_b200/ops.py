@@ -23,19 +23,19 @@ def _begin():
         _pending.record()
 
 
-def _count(name='kernel', flops=0):
+def _count(name='kernel', flops=0, desc=''):
     global LAUNCHES
     LAUNCHES += 1
     if PROFILE is not None:
         end = torch.cuda.Event(enable_timing=True)
         end.record()
-        PROFILE.append((name, _pending, end, flops))
+        PROFILE.append((name, _pending, end, flops, desc))
 
 
 def profile_summary(records):
     """Aggregate PROFILE records (after a device synchronize) -> {name: {ms, launches, flops}, total_ms}."""
     out, total = {}, 0.0
-    for name, e0, e1, flops in records:
+    for name, e0, e1, flops, _desc in records:
         ms = e0.elapsed_time(e1)
         d = out.setdefault(name, {'ms': 0.0, 'launches': 0, 'flops': 0})
         d['ms'] += ms
@@ -110,7 +110,9 @@ def conv_gemm(segments, N, H, W, cout, bias=None, residual=None, residual_mode=L
     p.gn_stats = None
     _begin()
     L.check(L.load().ndb_conv_gemm(C.byref(p), L.stream_ptr()), 'ndb_conv_gemm')
-    _count('conv_gemm', 2 * N * H * W * cout * sum(a.shape[-1] * w.shape[0] for a, w in segments))
+    _count('conv_gemm', 2 * N * H * W * cout * sum(a.shape[-1] * w.shape[0] for a, w in segments),
+           'N{} {}x{} K{} cout{} out{} res{}'.format(N, H, W, sum(a.shape[-1] * w.shape[0] for a, w in segments), cout,
+                                                    out_kind, p.residual_mode))
     return out
 
 
@@ -134,7 +136,7 @@ def gn_stats(x0, x1=None, pre_add=None, stats=None, workspace=None):
     L.check(L.load().ndb_gn_stats(L.ptr(x0), x0.shape[-1], L.ptr(x1), x1.shape[-1] if x1 is not None else 0, N, HW,
                                   L.ptr(pre_add), pre_add.stride(0) if pre_add is not None else 0,
                                   L.ptr(stats), L.ptr(workspace), L.stream_ptr()), 'ndb_gn_stats')
-    _count('gn_stats')
+    _count('gn_stats', 0, 'N{} HW{} C{}'.format(N, HW, C))
     return stats
 
 
@@ -171,7 +173,7 @@ def gn_apply(x0, stats, gamma, beta, x1=None, scale=None, shift=None, pre_add=No
     p.eps = eps
     _begin()
     L.check(L.load().ndb_gn_apply(C.byref(p), L.stream_ptr()), 'ndb_gn_apply')
-    _count('gn_apply')
+    _count('gn_apply', 0, 'N{} {}x{} C{} rs{} raw{}'.format(N, H, W, C0 + C1, resample, int(raw16 is not None)))
     return (out, raw16) if (want_raw16 or raw16 is not None) else out
 
 
@@ -184,11 +186,11 @@ def attention(qkv16, B, T, heads, d, order=0, out=None, fmt=L.FMT_FP16):
     _begin()
     L.check(L.load().ndb_attention(L.ptr(qkv16), L.ptr(out), B, T, heads, d, order, fmt, L.stream_ptr()),
             'ndb_attention')
-    _count('attention', 4 * B * heads * T * T * d)
+    _count('attention', 4 * B * heads * T * T * d, 'B{} T{} h{} d{}'.format(B, T, heads, d))
     return out
 
 
-def embed(t, y, freqs, w0, b0, w2, b2, class_emb, emb_out=None, act_out=None, fmt=L.FMT_FP16):
+def embed(t, y, freqs, w0, b0, w2, b2, class_emb, emb_out=None, act_out=None, fmt=L.FMT_FP16, scratch=None):
     L.require_device(t, 'embed')
     B = t.shape[0]
     mc = w0.shape[1]
@@ -198,11 +200,15 @@ def embed(t, y, freqs, w0, b0, w2, b2, class_emb, emb_out=None, act_out=None, fm
         emb_out = torch.empty((B, E), dtype=torch.float32, device=t.device)
     if act_out is None:
         act_out = torch.empty((B, E), dtype=dtype16(fmt), device=t.device)
+    if scratch is None:
+        scratch = torch.empty((B, E), dtype=torch.float32, device=t.device)
     _begin()
     L.check(L.load().ndb_embed(L.ptr(t), L.ptr(y), L.ptr(freqs), B, mc, L.ptr(w0), L.ptr(b0), L.ptr(w2), L.ptr(b2),
-                               L.ptr(class_emb) if y is not None else None, L.ptr(emb_out), L.ptr(act_out), fmt,
+                               L.ptr(class_emb) if y is not None else None, L.ptr(scratch), L.ptr(emb_out), L.ptr(act_out), fmt,
                                L.stream_ptr()), 'ndb_embed')
     _count('embed')
+    global LAUNCHES
+    LAUNCHES += 1   # two kernels
     return emb_out, act_out
 
 
