@@ -76,11 +76,19 @@ typedef struct {
     void* out;
     int32_t operand_format;  /* 0 = fp16, 1 = bf16 (both: fp32 accumulation in TMEM) */
     int32_t block_n;         /* 0 = auto */
-    double* gn_stats;        /* optional [N][32][2] fp64 (sum, sum of squares) of `out` per GroupNorm group,
-                                accumulated by the epilogue (must be zeroed by the caller); NULL = off */
+    void* stat_parts;        /* optional float2 [N][stat_smax][cout]: GroupNorm statistics of `out`, produced by the
+                                epilogue: per image and channel, (sum, sum of squares) of the stored values, split
+                                over the (few) persistent CTAs that swept the image's tiles -- slot s of image n is
+                                written by the s-th such CTA, ndb_conv_stats_layout() says how many there are. The
+                                consumer (ndb_gn_apply) adds the slots in order: deterministic, no atomics, no fences,
+                                no extra pass over the tensor. NULL = off. */
+    int32_t stat_smax;       /* slots per image, must equal ndb_conv_stats_layout(...) */
 } ndb_conv_params;
 
 int ndb_conv_gemm(const ndb_conv_params* p, void* stream);
+/* Returns stat_smax for this geometry and fills counts[N] (HOST pointer) with the slots written per image. */
+int ndb_conv_stats_layout(int N, int H, int W, int cout_pad, int block_n, int32_t* counts);
+int ndb_conv_stats_supported(int N, int H, int W);   /* 1 if stat_parts is available for this geometry */
 
 /* OIHW fp32 (nn.Conv2d / Conv1d / Linear weight, kernel 1 or 3) -> [taps][cout_pad][cin] 16-bit, rows >= cout zero.
  * `cin_off`/`cin_len` select an input-channel range (used to split a weight over concat segments). */
@@ -90,11 +98,15 @@ int ndb_pack_conv_weight(const float* w_oihw, void* dst, int cout, int cin_total
 /* ---- GroupNorm(32) statistics + apply ------------------------------------------------------------------
  * Replaces nn.GroupNorm(32, C, eps=1e-5) + SiLU + AdaGN scale/shift + h_resample + torch.cat
  * (model.py:172,176,190-193,199-207,250,264,446-447).
- * Input is the (virtual) channel concat of up to two fp32 NHWC tensors [N,H,W,C0] ++ [N,H,W,C1].
- * `pre_add` ([N][ld_pre], optional) is added per (n, channel) before normalisation (the non-adaptive
- * `h += embedding` path, model.py:205). */
-int ndb_gn_stats(const float* x0, int C0, const float* x1, int C1, int N, int HW, const float* pre_add,
-                 int ld_pre, double* stats /* [N][32][2] (sum, sum of squares), overwritten */,
+ * Statistics travel as PER-CHANNEL partial sums: float2 parts[n][slot][c] = (sum, sum of squares) over a subset of
+ * the pixels of image n; the slots of an image add up to the whole image (counts[n] of the smax slots are in use).
+ * They are normally produced for free by the conv epilogue (ndb_conv_params.stat_parts); ndb_gn_stats is the
+ * standalone producer (one slot per image) for tensors that do not come out of a GEMM (the stem) or geometries the
+ * epilogue does not cover. The consumer (ndb_gn_apply) folds slots and channels into the 32 groups itself in fp64, so
+ * one tensor's statistics serve every norm that reads it -- also the norms over a channel concat [x0 ++ x1]
+ * (model.py:474), whose groups straddle the two tensors. */
+int ndb_gn_stats(const float* x0, int C0, const float* x1, int C1, int N, int HW,
+                 void* parts0 /* float2 [N][1][C0] */, void* parts1 /* float2 [N][1][C1] or NULL */,
                  void* workspace, void* stream);
 /* Scratch for the deterministic cross-block reduction (no floating-point atomics: results are bit-identical from
  * run to run). Must be zero-filled ONCE before first use; it is left clean by every call and may be shared by all
@@ -109,11 +121,14 @@ typedef struct {
     const float* x0; int32_t C0;
     const float* x1; int32_t C1;       /* optional second concat source */
     int32_t N, H, W;                   /* input spatial size */
-    const double* stats;               /* [N][32][2] from ndb_gn_stats / conv epilogue */
+    const void* parts0; const int32_t* counts0; int32_t smax0;   /* statistics of x0: float2 [N][smax0][C0], int [N] */
+    const void* parts1; const int32_t* counts1; int32_t smax1;   /* statistics of x1 (when x1 != NULL) */
     const float* gamma; const float* beta;   /* [C0+C1] */
     const float* scale; const float* shift;  /* optional AdaGN [N][ld_ss] rows: y = gn*(1+scale)+shift */
     int32_t ld_ss;
-    const float* pre_add; int32_t ld_pre;    /* optional */
+    const float* pre_add; int32_t ld_pre;    /* optional [N][ld_pre]: added per (n, channel) BEFORE the norm (the
+                                                non-adaptive `h += embedding` path, model.py:205); the statistics are
+                                                corrected analytically */
     int32_t silu;                      /* apply SiLU after the affine */
     int32_t resample;                  /* NDB_RESAMPLE_* applied after the activation */
     void* out;                         /* 16-bit NHWC [N,H',W',C0+C1] */

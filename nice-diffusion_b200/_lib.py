@@ -36,14 +36,15 @@ class ConvParams(C.Structure):
                 ('residual_mode', C.c_int32), ('out_kind', C.c_int32),
                 ('out', C.c_void_p),
                 ('operand_format', C.c_int32), ('block_n', C.c_int32),
-                ('gn_stats', C.c_void_p)]
+                ('stat_parts', C.c_void_p), ('stat_smax', C.c_int32)]
 
 
 class GnApplyParams(C.Structure):
     _fields_ = [('x0', C.c_void_p), ('C0', C.c_int32),
                 ('x1', C.c_void_p), ('C1', C.c_int32),
                 ('N', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
-                ('stats', C.c_void_p),
+                ('parts0', C.c_void_p), ('counts0', C.c_void_p), ('smax0', C.c_int32),
+                ('parts1', C.c_void_p), ('counts1', C.c_void_p), ('smax1', C.c_int32),
                 ('gamma', C.c_void_p), ('beta', C.c_void_p),
                 ('scale', C.c_void_p), ('shift', C.c_void_p), ('ld_ss', C.c_int32),
                 ('pre_add', C.c_void_p), ('ld_pre', C.c_int32),
@@ -71,8 +72,10 @@ SIGNATURES = {
     'ndb_device_supported': (_I, []),
     'ndb_last_error': (C.c_char_p, []),
     'ndb_conv_gemm': (_I, [C.POINTER(ConvParams), _P]),
+    'ndb_conv_stats_layout': (_I, [_I, _I, _I, _I, _I, _P]),
+    'ndb_conv_stats_supported': (_I, [_I, _I, _I]),
     'ndb_pack_conv_weight': (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
-    'ndb_gn_stats': (_I, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _P, _P]),
+    'ndb_gn_stats': (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P, _P]),
     'ndb_gn_stats_workspace_bytes': (_I64, [_I, _I, _I]),
     'ndb_gn_apply': (_I, [C.POINTER(GnApplyParams), _P]),
     'ndb_attention': (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),

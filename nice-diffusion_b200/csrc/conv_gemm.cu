@@ -10,7 +10,8 @@
 // tcgen05.mma (128 x BLOCK_N x 16, fp32 accumulate in TMEM); accumulators are double-buffered in TMEM so
 // the epilogue of tile i overlaps the main loop of tile i+1. Persistent CTAs, one per SM.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
+// Warp roles (352 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue,
+// warp 10 = GroupNorm-statistics reducer (only active when chan_stats is requested).
 // Epilogue: each warp owns 32 accumulator rows (its TMEM lane quarter) and half of the tile's column chunks. Per
 // 32-column chunk it (1) issues the residual loads with lanes along channels (32 independent, fully coalesced 128-byte
 // requests in flight per warp), (2) pulls the chunk out of TMEM (thread = row), (3) transposes it through a padded
@@ -26,7 +27,7 @@ constexpr int kMaxSeg = NDB_MAX_SEGMENTS;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                        // 64 x 16-bit = one 128-byte swizzle row
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
-constexpr int kThreads = 320;
+constexpr int kThreads = 352;                       // 11 warps: TMA, MMA, 8 epilogue, 1 statistics
 constexpr int kEpiWarps = 8;
 constexpr int kStageFloats = 32 * 33;               // padded 32x32 transpose tile per epilogue warp
 constexpr int kMaxStages = 8;
@@ -58,7 +59,22 @@ struct ConvArgs {
     int out_kind;
     void* out;
     int fmt;
+    // fused GroupNorm statistics: per (image, CTA slot, channel) partial (sum, sum of squares) of the stored output
+    float2* stat_parts;        // [N][stat_smax][cout] or nullptr
+    int stat_smax;             // partial slots per image
+    int tiles_per_group;       // tiles (m x n) covering one group of TN images
 };
+
+// Persistent CTAs own CONTIGUOUS tile ranges: CTA c processes tiles [tile_start(c), tile_start(c+1)). Tiles are ordered
+// (image group, row block, column block, n tile), so a CTA sweeps an image's tiles back to back and can keep that
+// image's per-channel sums on chip; an image is shared by few CTAs (its "slots").
+__host__ __device__ inline int tile_start(int c, int T, int G) { return (int)(((long long)c * T) / G); }
+__host__ __device__ inline int cta_of_tile(int t, int T, int G) {
+    int c = (int)((((long long)t + 1) * G - 1) / T);
+    while (c > 0 && tile_start(c, T, G) > t) --c;
+    while (c + 1 < G && tile_start(c + 1, T, G) <= t) ++c;
+    return c;
+}
 
 template <int FMT>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -71,6 +87,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     }
 }
 
+template <bool kStats>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -83,13 +100,19 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full_bar = empty_bar + kMaxStages;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* stat_full_bar = tmem_empty_bar + 2;
+    uint64_t* stat_empty_bar = stat_full_bar + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(stat_empty_bar + 2);
     float* epi_stage = reinterpret_cast<float*>(smem + p.stages * stage_bytes + 256);
     long long* epi_rows = reinterpret_cast<long long*>(epi_stage + kEpiWarps * kStageFloats);
+    float2* part_smem = reinterpret_cast<float2*>(epi_rows + kEpiWarps * 64);   // [2 buffers][4 quarters][block_n]
+    float2* stat_acc = part_smem + 2 * 4 * p.block_n;                           // [TN][cout] (statistics warp only)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int tile_begin = tile_start(blockIdx.x, num_tiles, gridDim.x);
+    const int tile_end = tile_start(blockIdx.x + 1, num_tiles, gridDim.x);
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.num_seg; ++s) {
@@ -103,6 +126,8 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full_bar[s], 1);
             mbar_init(&tmem_empty_bar[s], kEpiWarps);  // one arrive per epilogue warp
+            mbar_init(&stat_full_bar[s], kEpiWarps);
+            mbar_init(&stat_empty_bar[s], 1);
         }
         fence_barrier_init();
     }
@@ -120,7 +145,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile_begin; tile < tile_end; ++tile) {
                 const int n_tile = tile % p.num_n_tiles;
                 int m_tile = tile / p.num_n_tiles;
                 const int tw_i = m_tile % p.tiles_w;
@@ -157,7 +182,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile_begin; tile < tile_end; ++tile) {
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
@@ -185,7 +210,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                 }
             }
         }
-    } else {
+    } else if (warp < 2 + kEpiWarps) {
         // ===================== epilogue warps =====================
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;       // which half of the column chunks
@@ -198,9 +223,11 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
         const int ch_end = half ? nch : (nch + 1) / 2;
         int acc = 0;
         uint32_t acc_phase = 0;
+        int stat_buf = 0;
+        uint32_t stat_phase = 0;
         const int pix_per_img = p.TH * p.TW;
         const float* __restrict__ resp = p.residual;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
             const int n_tile = tile % p.num_n_tiles;
             int m_tile = tile / p.num_n_tiles;
             const int tw_i = m_tile % p.tiles_w;
@@ -236,6 +263,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
 
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
+            if (kStats) mbar_wait(&stat_empty_bar[stat_buf], stat_phase ^ 1);   // part_smem buffer free
             const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * p.acc_stride;
             for (int ch = ch_begin; ch < ch_end; ++ch) {
                 const int cl = ch * 32 + lane;             // column inside the tile owned by this lane (transposed view)
@@ -277,31 +305,39 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                 for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __uint_as_float(racc[i]);
                 __syncwarp();
                 const float bias_v = (colok && p.bias != nullptr) ? __ldg(p.bias + col) : 0.f;
-                // (4) bias + residual + store, lanes along channels
+                // (4) bias + residual, then store with lanes along channels
+#pragma unroll
+                for (int r = 0; r < 32; ++r) res[r] = stg[r * 33 + lane] + bias_v + res[r];
                 if (p.out_kind == NDB_OUT_F32_NHWC) {
                     float* ob = reinterpret_cast<float*>(p.out) + col;
 #pragma unroll
-                    for (int r = 0; r < 32; ++r) {
-                        const float v = stg[r * 33 + lane] + bias_v + res[r];
-                        if ((okmask >> r) & 1u) ob[row_out[r]] = v;
-                    }
+                    for (int r = 0; r < 32; ++r)
+                        if ((okmask >> r) & 1u) ob[row_out[r]] = res[r];
                 } else if (p.out_kind == NDB_OUT_F16_NHWC) {
                     uint16_t* ob = reinterpret_cast<uint16_t*>(p.out) + col;
 #pragma unroll
                     for (int r = 0; r < 32; ++r) {
-                        const float v = stg[r * 33 + lane] + bias_v + res[r];
                         uint16_t bits;
-                        if (p.fmt == 0) { __half hv = __float2half_rn(v); bits = *reinterpret_cast<uint16_t*>(&hv); }
-                        else { __nv_bfloat16 hv = __float2bfloat16_rn(v); bits = *reinterpret_cast<uint16_t*>(&hv); }
+                        if (p.fmt == 0) { __half hv = __float2half_rn(res[r]); bits = *reinterpret_cast<uint16_t*>(&hv); }
+                        else { __nv_bfloat16 hv = __float2bfloat16_rn(res[r]); bits = *reinterpret_cast<uint16_t*>(&hv); }
                         if ((okmask >> r) & 1u) ob[row_out[r]] = bits;
                     }
                 } else {
                     float* ob = reinterpret_cast<float*>(p.out) + (long long)col * p.H * p.W;
 #pragma unroll
+                    for (int r = 0; r < 32; ++r)
+                        if ((okmask >> r) & 1u) ob[row_out[r]] = res[r];
+                }
+                if (kStats) {
+                    // column sums over this warp's 32 rows come for free in the transposed view (fixed order)
+                    float cs = 0.f, css = 0.f;
+#pragma unroll
                     for (int r = 0; r < 32; ++r) {
-                        const float v = stg[r * 33 + lane] + bias_v + res[r];
-                        if ((okmask >> r) & 1u) ob[row_out[r]] = v;
+                        const float v = ((okmask >> r) & 1u) ? res[r] : 0.f;
+                        cs += v;
+                        css += v * v;
                     }
+                    if (cl < p.block_n) part_smem[(stat_buf * 4 + q) * p.block_n + cl] = make_float2(cs, css);
                 }
                 __syncwarp();
             }
@@ -312,7 +348,62 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                 acc = 0;
                 acc_phase ^= 1;
             }
+            if (kStats) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&stat_full_bar[stat_buf]);   // this warp's column sums are in part_smem
+                if ((stat_buf ^= 1) == 0) stat_phase ^= 1;
+            }
         }
+    } else if (kStats) {
+        // ===================== statistics warp =====================
+        // Folds the four row-quarters of every finished tile into per-(image, channel) running sums kept in shared
+        // memory while this CTA sweeps the tiles of one image group, and writes them out ONCE when it moves on to
+        // the next group: slot (this CTA - first CTA of the group) of stat_parts[image]. No atomics, no fences, no
+        // cross-CTA traffic inside the kernel; the consuming gn_apply adds the (few) slots of its image in slot order.
+        int stat_buf = 0;
+        uint32_t stat_phase = 0;
+        const int warps_per_slot = 4 / p.TN;                  // TN in {1, 2, 4} (host-checked)
+        int cur_group = -1;
+        auto flush = [&](int group) {
+            const int first_cta = cta_of_tile(group * p.tiles_per_group, num_tiles, gridDim.x);
+            const int slot_idx = blockIdx.x - first_cta;
+            for (int sl = 0; sl < p.TN; ++sl) {
+                const int img = group * p.TN + sl;
+                if (img >= p.N) break;
+                float2* dst = p.stat_parts + ((size_t)img * p.stat_smax + slot_idx) * p.cout;
+                for (int c = lane; c < p.cout; c += 32) dst[c] = stat_acc[sl * p.cout + c];
+            }
+        };
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
+            const int n_tile = tile % p.num_n_tiles;
+            const int group = tile / p.tiles_per_group;
+            const int col0 = n_tile * p.block_n;
+            if (group != cur_group) {
+                if (cur_group >= 0) flush(cur_group);
+                for (int i = lane; i < p.TN * p.cout; i += 32) stat_acc[i] = make_float2(0.f, 0.f);
+                cur_group = group;
+                __syncwarp();
+            }
+            mbar_wait(&stat_full_bar[stat_buf], stat_phase);
+            const float2* ps = part_smem + stat_buf * 4 * p.block_n;
+            for (int i = lane; i < p.TN * p.block_n; i += 32) {
+                const int sl = i / p.block_n, c = i - sl * p.block_n;
+                float sx = 0.f, sy = 0.f;
+                for (int qq = sl * warps_per_slot; qq < (sl + 1) * warps_per_slot; ++qq) {
+                    const float2 v = ps[qq * p.block_n + c];
+                    sx += v.x; sy += v.y;
+                }
+                if (col0 + c < p.cout) {
+                    float2 a = stat_acc[sl * p.cout + col0 + c];
+                    a.x += sx; a.y += sy;
+                    stat_acc[sl * p.cout + col0 + c] = a;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&stat_empty_bar[stat_buf]);
+            if ((stat_buf ^= 1) == 0) stat_phase ^= 1;
+        }
+        if (cur_group >= 0) flush(cur_group);
     }
 
     tc_fence_before();
@@ -349,6 +440,45 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, uint16_t* __rest
     }
 }
 
+// Number of partial slots an image needs (max over image groups of the CTAs sweeping its tiles) and, optionally, the
+// per-image slot counts.
+static int stats_slots(int groups, int tiles_per_group, int T, int G, int32_t* counts, int N, int TN) {
+    int smax = 1;
+    for (int g = 0; g < groups; ++g) {
+        const int c0 = cta_of_tile(g * tiles_per_group, T, G);
+        const int c1 = cta_of_tile((g + 1) * tiles_per_group - 1, T, G);
+        const int n = c1 - c0 + 1;
+        if (n > smax) smax = n;
+        if (counts != nullptr)
+            for (int sl = 0; sl < TN; ++sl)
+                if (g * TN + sl < N) counts[g * TN + sl] = n;
+    }
+    return smax;
+}
+
+struct ConvGeom {
+    int TW, TH, TN, tiles_w, tiles_h, tiles_n, num_m_tiles;
+};
+
+static ConvGeom conv_geom(int N, int H, int W) {
+    ConvGeom g;
+    g.TW = W < kBlockM ? W : kBlockM;
+    g.TH = kBlockM / g.TW;
+    if (g.TH > H) g.TH = H;
+    if (g.TH < 1) g.TH = 1;
+    g.TN = 1;
+    if (g.TH == H && g.TW == W) {
+        g.TN = kBlockM / (H * W);
+        if (g.TN < 1) g.TN = 1;
+        if (g.TN > N) g.TN = N;
+    }
+    g.tiles_w = (W + g.TW - 1) / g.TW;
+    g.tiles_h = (H + g.TH - 1) / g.TH;
+    g.tiles_n = (N + g.TN - 1) / g.TN;
+    g.num_m_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
+    return g;
+}
+
 static int pick_block_n(int cout_pad) {
     // 192 first: it divides every ImageNet-64 width (192..2304) and leaves room for a 4-stage smem ring
     if (cout_pad % 192 == 0) return 192;
@@ -382,7 +512,6 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     NDB_CHECK_ARG(prm->cout >= 1 && prm->cout_pad >= prm->cout && prm->cout_pad % 16 == 0);
     NDB_CHECK_ARG(prm->out != nullptr);
     NDB_CHECK_ARG(prm->operand_format == 0 || prm->operand_format == 1);
-    if (prm->gn_stats != nullptr) return NDB_ERR_UNSUPPORTED;
     if (prm->residual_mode == NDB_RES_UP2) NDB_CHECK_ARG(prm->H % 2 == 0 && prm->W % 2 == 0);
 
     ConvArgs a{};
@@ -417,6 +546,17 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     a.out_kind = prm->out_kind;
     a.out = prm->out;
     a.fmt = prm->operand_format;
+    a.stat_parts = reinterpret_cast<float2*>(prm->stat_parts);
+    a.tiles_per_group = a.tiles_w * a.tiles_h * a.num_n_tiles;
+    const int num_tiles_all = a.num_m_tiles * a.num_n_tiles;
+    const int grid_all = num_tiles_all < num_sms() ? num_tiles_all : num_sms();
+    if (prm->stat_parts != nullptr) {
+        NDB_CHECK_ARG(prm->out_kind != NDB_OUT_F32_NCHW);
+        // image slots inside a tile must be whole warps
+        NDB_CHECK_ARG(a.TN == 1 || ((a.TN == 2 || a.TN == 4) && (prm->H * prm->W) % 32 == 0 && a.TN * prm->H * prm->W == kBlockM));
+        a.stat_smax = stats_slots(a.tiles_n, a.tiles_per_group, num_tiles_all, grid_all, nullptr, 0, 0);
+        NDB_CHECK_ARG(prm->stat_smax == a.stat_smax);
+    }
 
     TmapPack maps;
     a.total_kblocks = 0;
@@ -446,7 +586,9 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     }
 
     const int stage_bytes = kATileBytes + a.block_n * 128;
-    const int epi_bytes = kEpiWarps * (kStageFloats * (int)sizeof(float) + 64 * (int)sizeof(long long));
+    const int epi_bytes = kEpiWarps * (kStageFloats * (int)sizeof(float) + 64 * (int)sizeof(long long)) +
+                          2 * 4 * a.block_n * (int)sizeof(float2) +
+                          (prm->stat_parts ? a.TN * prm->cout * (int)sizeof(float2) : 0);
     const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - epi_bytes;
     int stages = smem_budget / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
@@ -457,12 +599,37 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
 
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return launch_status("cudaFuncSetAttribute(conv_gemm_kernel)");
         attr_set = true;
     }
-    const int num_tiles = a.num_m_tiles * a.num_n_tiles;
-    int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    conv_gemm_kernel<<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(maps, a);
+    const int grid = grid_all;
+    if (a.stat_parts != nullptr)
+        conv_gemm_kernel<true><<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(maps, a);
+    else
+        conv_gemm_kernel<false><<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(maps, a);
     return launch_status("ndb_conv_gemm");
+}
+
+// Layout of the fused statistics output for a conv with this geometry: returns the number of partial slots per image
+// (stat_smax) and fills counts[N] (host memory) with the slots actually written for each image; <0 on error.
+// stat_parts must hold N * stat_smax * cout float2.
+extern "C" int ndb_conv_stats_layout(int N, int H, int W, int cout_pad, int block_n, int32_t* counts) {
+    if (N <= 0 || H <= 0 || W <= 0 || cout_pad <= 0) return NDB_ERR_INVALID;
+    const ConvGeom g = conv_geom(N, H, W);
+    const int bn = block_n > 0 ? block_n : pick_block_n(cout_pad);
+    if (bn <= 0 || cout_pad % bn != 0) return NDB_ERR_INVALID;
+    const int n_tiles = cout_pad / bn;
+    const int T = g.num_m_tiles * n_tiles;
+    const int G = T < num_sms() ? T : num_sms();
+    return stats_slots(g.tiles_n, g.tiles_w * g.tiles_h * n_tiles, T, G, counts, N, g.TN);
+}
+
+// 1 when the epilogue can produce per-image channel statistics for this geometry (else use ndb_gn_stats).
+extern "C" int ndb_conv_stats_supported(int N, int H, int W) {
+    const ConvGeom g = conv_geom(N, H, W);
+    if (g.TN == 1) return 1;
+    return ((g.TN == 2 || g.TN == 4) && (H * W) % 32 == 0 && g.TN * H * W == kBlockM) ? 1 : 0;
 }

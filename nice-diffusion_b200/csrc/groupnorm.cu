@@ -20,7 +20,7 @@ constexpr int kMaxVecPerThread = 4;  // supports C <= 4 * 4 * 256 = 4096
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kGnThreads)
 gn_stats_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, int HW,
-                const float* __restrict__ pre_add, int ld_pre, double* __restrict__ stats,
+                float* __restrict__ stats0, float* __restrict__ stats1,
                 double* __restrict__ partials, unsigned int* __restrict__ counters, int pix_per_block,
                 int threads_per_row, int rows_per_block) {
     // Deterministic two-level reduction (no floating-point atomics): per-thread partials -> fixed-order block
@@ -49,13 +49,10 @@ gn_stats_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ 
                 const float* src;
                 int ldc, cc;
                 if (c < C0) { src = x0; ldc = C0; cc = c; } else { src = x1; ldc = C1; cc = c - C0; }
-                float4 add = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (pre_add != nullptr) add = __ldg(reinterpret_cast<const float4*>(pre_add + (size_t)n * ld_pre + c));
                 const float* base = src + ((size_t)n * HW) * ldc + cc;
                 float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int p = p_begin + r; p < p_end; p += rows_per_block) {
-                    float4 a = __ldg(reinterpret_cast<const float4*>(base + (size_t)p * ldc));
-                    a.x += add.x; a.y += add.y; a.z += add.z; a.w += add.w;
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(base + (size_t)p * ldc));
                     s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
                     ss.x += a.x * a.x; ss.y += a.y * a.y; ss.z += a.z * a.z; ss.w += a.w * a.w;
                 }
@@ -65,18 +62,16 @@ gn_stats_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ 
         }
     }
     __syncthreads();
-    double* my_part = partials + ((size_t)n * chunks + blockIdx.x) * (2 * kGroups);
-    if (threadIdx.x < 2 * kGroups) {
-        const int g = threadIdx.x & (kGroups - 1);
-        const int which = threadIdx.x >> 5;
-        const int cpg = C / kGroups;
+    // per-channel block partial (fixed order over the row slots), fp64
+    double* my_part = partials + ((size_t)n * chunks + blockIdx.x) * (2 * (size_t)C);
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        const int which = i / C, c = i - which * C;
         const float* red = which ? red_ss : red_s;
         double acc = 0.0;
-        for (int k = 0; k < cpg; ++k)
-            for (int rr = 0; rr < rows_per_block; ++rr) acc += (double)red[rr * C + g * cpg + k];
-        my_part[which * kGroups + g] = acc;
-        __threadfence();
+        for (int rr = 0; rr < rows_per_block; ++rr) acc += (double)red[rr * C + c];
+        my_part[i] = acc;
     }
+    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int ticket = atomicAdd(&counters[n], 1u);
@@ -85,13 +80,13 @@ gn_stats_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ 
     __syncthreads();
     if (is_last) {
         __threadfence();
-        if (threadIdx.x < 2 * kGroups) {
-            const int g = threadIdx.x & (kGroups - 1);
-            const int which = threadIdx.x >> 5;
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+            const int which = i / C, c = i - which * C;
             double tot = 0.0;
-            for (int ch = 0; ch < chunks; ++ch)
-                tot += __ldcg(partials + ((size_t)n * chunks + ch) * (2 * kGroups) + which * kGroups + g);
-            stats[((size_t)n * kGroups + g) * 2 + which] = tot;
+            for (int ch = 0; ch < chunks; ++ch) tot += __ldcg(partials + ((size_t)n * chunks + ch) * (2 * (size_t)C) + i);
+            // split across the two sources so that each tensor owns its [N][C_src][2] statistics
+            if (c < C0) stats0[((size_t)n * C0 + c) * 2 + which] = (float)tot;
+            else stats1[((size_t)n * C1 + (c - C0)) * 2 + which] = (float)tot;
         }
         if (threadIdx.x == 0) counters[n] = 0u;  // self-resetting: the workspace needs zeroing only once
     }
@@ -117,7 +112,8 @@ struct GnApplyArgs {
     const float* x0; int C0;
     const float* x1; int C1;
     int N, H, W, Ho, Wo;
-    const double* stats;
+    const float2* parts0; const int* counts0; int smax0;
+    const float2* parts1; const int* counts1; int smax1;
     const float* gamma; const float* beta;
     const float* scale; const float* shift; int ld_ss;
     const float* pre_add; int ld_pre;
@@ -135,11 +131,59 @@ gn_apply_kernel(const GnApplyArgs p) {
     const int C = p.C0 + p.C1;
     const int V8 = C >> 3;
     const int n = blockIdx.y;
+    const int cpg = C / kGroups;
+    // block prologue: the 32 group (mean, rstd) of sample n from the per-channel sums of the source tensors.
+    // With `pre_add` e_c (non-adaptive ResBlock: h += emb before the norm) the sums of (x + e_c) follow
+    // analytically: S' = S + P e, SS' = SS + 2 e S + P e^2.
+    __shared__ float s_mean[kGroups], s_rstd[kGroups];
+    {
+        // 8 lanes per group: strided partial sums over the group's channels, then a 3-step shuffle tree (fixed order)
+        const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
+        const double P = (double)p.H * p.W;
+        double S = 0.0, SS = 0.0;
+        const int cnt0 = p.counts0[n];
+        const int cnt1 = p.parts1 ? p.counts1[n] : 0;
+        for (int k = sub; k < cpg; k += 8) {
+            const int c = g * cpg + k;
+            double s1 = 0.0, s2 = 0.0;
+            if (c < p.C0) {
+                const float2* src = p.parts0 + (size_t)n * p.smax0 * p.C0 + c;
+                for (int sl = 0; sl < cnt0; ++sl) {
+                    const float2 v = __ldg(src + (size_t)sl * p.C0);
+                    s1 += (double)v.x; s2 += (double)v.y;
+                }
+            } else {
+                const float2* src = p.parts1 + (size_t)n * p.smax1 * p.C1 + (c - p.C0);
+                for (int sl = 0; sl < cnt1; ++sl) {
+                    const float2 v = __ldg(src + (size_t)sl * p.C1);
+                    s1 += (double)v.x; s2 += (double)v.y;
+                }
+            }
+            if (p.pre_add != nullptr) {
+                const double e = (double)p.pre_add[(size_t)n * p.ld_pre + c];
+                s2 += 2.0 * e * s1 + P * e * e;
+                s1 += P * e;
+            }
+            S += s1; SS += s2;
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            S += __shfl_xor_sync(0xffffffffu, S, o);
+            SS += __shfl_xor_sync(0xffffffffu, SS, o);
+        }
+        if (sub == 0) {
+            const double inv_cnt = 1.0 / ((double)cpg * P);
+            const double mean = S * inv_cnt;
+            double var = SS * inv_cnt - mean * mean;
+            if (var < 0.0) var = 0.0;
+            s_mean[g] = (float)mean;
+            s_rstd[g] = rsqrtf((float)var + p.eps);
+        }
+    }
+    __syncthreads();
     const int r = threadIdx.x / p.threads_per_row;
     const int tv = threadIdx.x - r * p.threads_per_row;
     if (r >= p.rows_per_block) return;
-    const int cpg = C / kGroups;
-    const double inv_cnt = 1.0 / ((double)cpg * p.H * p.W);
     const int npix = p.Ho * p.Wo;
     const int p_begin = blockIdx.x * p.pix_per_block;
     int p_end = p_begin + p.pix_per_block;
@@ -148,23 +192,11 @@ gn_apply_kernel(const GnApplyArgs p) {
     for (int v = tv; v < V8; v += p.threads_per_row) {
         const int c = v << 3;
         float a[8], b[8], pre[8];
-        int g_prev = -1;
-        float mean_f = 0.f, rstd = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int g = (c + k) / cpg;
-            if (g != g_prev) {
-                const double s = p.stats[((size_t)n * kGroups + g) * 2 + 0];
-                const double ss = p.stats[((size_t)n * kGroups + g) * 2 + 1];
-                const double mean = s * inv_cnt;
-                double var = ss * inv_cnt - mean * mean;
-                if (var < 0.0) var = 0.0;
-                rstd = (float)(1.0 / sqrt(var + (double)p.eps));
-                mean_f = (float)mean;
-                g_prev = g;
-            }
-            float ak = rstd * __ldg(p.gamma + c + k);
-            float bk = __ldg(p.beta + c + k) - mean_f * ak;
+            float ak = s_rstd[g] * __ldg(p.gamma + c + k);
+            float bk = __ldg(p.beta + c + k) - s_mean[g] * ak;
             const float pr = p.pre_add ? __ldg(p.pre_add + (size_t)n * p.ld_pre + c + k) : 0.f;
             bk += ak * pr;
             if (p.scale != nullptr) {
@@ -274,15 +306,16 @@ static size_t gn_counter_bytes(int N) { return (((size_t)N * sizeof(unsigned int
 extern "C" int64_t ndb_gn_stats_workspace_bytes(int N, int HW, int C) {
     if (N <= 0 || HW <= 0 || C <= 0) return 0;
     const GnStatsGeom g = gn_stats_geom(N, HW, C);
-    return (int64_t)(gn_counter_bytes(N) + (size_t)N * g.chunks * 2 * kGroups * sizeof(double));
+    return (int64_t)(gn_counter_bytes(N) + (size_t)N * g.chunks * 2 * C * sizeof(double));
 }
 
-extern "C" int ndb_gn_stats(const float* x0, int C0, const float* x1, int C1, int N, int HW, const float* pre_add,
-                            int ld_pre, double* stats, void* workspace, void* stream) {
-    NDB_CHECK_ARG(x0 && stats && workspace && N > 0 && HW > 0);
+extern "C" int ndb_gn_stats(const float* x0, int C0, const float* x1, int C1, int N, int HW, void* stats0,
+                            void* stats1, void* workspace, void* stream) {
+    NDB_CHECK_ARG(x0 && stats0 && workspace && N > 0 && HW > 0);
     if (x1 == nullptr) C1 = 0;
+    NDB_CHECK_ARG(C1 == 0 || stats1 != nullptr);
     const int C = C0 + C1;
-    NDB_CHECK_ARG(C % kGroups == 0 && C0 % 4 == 0 && C1 % 4 == 0);
+    NDB_CHECK_ARG(C0 % 4 == 0 && C1 % 4 == 0);
     const int V = C / 4;
     NDB_CHECK_ARG(V <= kMaxVecPerThread * kGnThreads);
     const GnStatsGeom g = gn_stats_geom(N, HW, C);
@@ -291,13 +324,13 @@ extern "C" int ndb_gn_stats(const float* x0, int C0, const float* x1, int C1, in
     dim3 grid(g.chunks, N);
     const size_t smem = 2 * (size_t)g.rows_per_block * C * sizeof(float);
     gn_stats_kernel<<<grid, kGnThreads, smem, (cudaStream_t)stream>>>(
-        x0, C0, x1, C1, HW, pre_add, ld_pre, stats, partials, counters, g.pix_per_block, g.threads_per_row,
-        g.rows_per_block);
+        x0, C0, x1, C1, HW, (float*)stats0, (float*)stats1, partials, counters, g.pix_per_block, g.threads_per_row, g.rows_per_block);
     return launch_status("ndb_gn_stats");
 }
 
 extern "C" int ndb_gn_apply(const ndb_gn_apply_params* q, void* stream) {
-    NDB_CHECK_ARG(q && q->x0 && q->stats && q->gamma && q->beta && q->out);
+    NDB_CHECK_ARG(q && q->x0 && q->parts0 && q->counts0 && q->smax0 >= 1 && q->gamma && q->beta && q->out);
+    NDB_CHECK_ARG(q->x1 == nullptr || (q->parts1 != nullptr && q->counts1 != nullptr && q->smax1 >= 1));
     GnApplyArgs a{};
     a.x0 = q->x0; a.C0 = q->C0;
     a.x1 = q->x1; a.C1 = q->x1 ? q->C1 : 0;
@@ -311,7 +344,9 @@ extern "C" int ndb_gn_apply(const ndb_gn_apply_params* q, void* stream) {
         NDB_CHECK_ARG(q->H % 2 == 0 && q->W % 2 == 0);
         a.Ho = q->H / 2; a.Wo = q->W / 2;
     }
-    a.stats = q->stats; a.gamma = q->gamma; a.beta = q->beta;
+    a.parts0 = (const float2*)q->parts0; a.counts0 = q->counts0; a.smax0 = q->smax0;
+    a.parts1 = q->x1 ? (const float2*)q->parts1 : nullptr; a.counts1 = q->counts1; a.smax1 = q->smax1;
+    a.gamma = q->gamma; a.beta = q->beta;
     a.scale = q->scale; a.shift = q->shift; a.ld_ss = q->ld_ss;
     a.pre_add = q->pre_add; a.ld_pre = q->ld_pre;
     a.silu = q->silu; a.resample = q->resample;

@@ -4,14 +4,16 @@ whole forward captured in a CUDA graph.
 
 Dataflow per block (reference: model.py:188-211 ResidualBlock, :260-291 AttentionBlock):
 
-  ResBlock   gn_stats(x) -> gn_apply[SiLU, up/down, concat] -> conv3x3 GEMM (+bias) -> gn_stats
-             -> gn_apply[AdaGN scale/shift, SiLU] -> conv3x3 GEMM (+bias, + residual x | + 1x1 skip as an extra
-             K segment, x_resample folded into the epilogue)
-  Attention  gn_stats -> gn_apply -> qkv GEMM (fp16 out) -> fused attention -> proj GEMM (+bias +x)
+  ResBlock   gn_apply[in_norm, SiLU, up/down, concat] -> conv3x3 GEMM (+bias; epilogue emits GroupNorm statistics)
+             -> gn_apply[out_norm, AdaGN scale/shift, SiLU] -> conv3x3 GEMM (+bias, + residual x | + 1x1 skip as an
+             extra K segment, x_resample folded into the epilogue; epilogue emits statistics for the next norm)
+  Attention  gn_apply -> qkv GEMM (fp16 out) -> fused attention -> proj GEMM (+bias +x, statistics)
 
-The residual stream is fp32 NHWC; every tensor-core operand is written once in 16-bit NHWC by the producing
-GroupNorm kernel. `torch.cat` of the up path never materialises in fp32: the GroupNorm kernels read both
-sources (model.py:474). All step-embedding Linear layers run as ONE GEMM per forward.
+The residual stream is fp32 NHWC and every stream tensor travels with its per-channel (sum, sumsq) statistics, written
+by the epilogue of the GEMM that produced it -- there is no separate statistics pass except for the stem output.
+Every tensor-core operand is written once in 16-bit NHWC by the consuming norm's apply kernel. `torch.cat` of the up
+path never materialises in fp32: the apply kernel reads both sources (model.py:474). All step-embedding Linear
+layers run as ONE GEMM per forward.
 """
 import torch
 
@@ -41,6 +43,14 @@ class _Pool:
         self.free.setdefault((tuple(t.shape), t.dtype), []).append(t)
 
 
+class _Act:
+    """A residual-stream tensor (fp32 NHWC) and its GroupNorm statistics (parts [B, smax, C, 2] fp32, counts [B])."""
+    __slots__ = ('t', 'stats')
+
+    def __init__(self, t, stats):
+        self.t, self.stats = t, stats
+
+
 class UNetEngine:
     def __init__(self, model, batch, device):
         self.model = model
@@ -53,6 +63,8 @@ class UNetEngine:
         self.graph = None
         self.sig = None
         self.pool = _Pool(device)
+        self._layouts = {}
+        self._ones = torch.ones((batch,), dtype=torch.int32, device=device)
         with torch.no_grad():
             self._build()
 
@@ -65,11 +77,10 @@ class UNetEngine:
         return buf
 
     def _packed(self, p, cout_pad=None):
-        w = p
-        cout = w.shape[0]
-        k = w.shape[2] if w.dim() >= 3 else 1
+        cout = p.shape[0]
+        k = p.shape[2] if p.dim() >= 3 else 1
         cp = ops.pad16(cout) if cout_pad is None else cout_pad
-        buf = torch.empty((k * k, cp, w.shape[1]), dtype=self.dt16, device=self.device)
+        buf = torch.empty((k * k, cp, p.shape[1]), dtype=self.dt16, device=self.device)
         self.packers.append(lambda: ops.pack_conv_weight(p.detach().to(self.device), cout_pad=cp, fmt=self.fmt, out=buf))
         return buf
 
@@ -88,6 +99,53 @@ class UNetEngine:
                 for f in self.packers:
                     f()
             self.sig = sig
+
+    # ------------------------------------------------------------------------------------------
+    # emit helpers
+    # ------------------------------------------------------------------------------------------
+    def _stats_buf(self, C, smax=1, counts=None):
+        parts = self.pool.get((self.B, smax, C, 2), torch.float32)
+        if counts is None:
+            counts = self._ones
+        return (parts, counts)
+
+    def _release(self, act):
+        self.pool.put(act.t)
+        if act.stats is not None:
+            self.pool.put(act.stats[0])
+
+    def _emit_stats_kernel(self, t, stats):
+        self.steps.append(lambda: ops.gn_stats(t, stats0=stats, workspace=self.gn_ws))
+
+    def _conv_stats_layout(self, H, W, cout):
+        key = (H, W, cout)
+        if key not in self._layouts:
+            import ctypes
+            counts = (ctypes.c_int32 * self.B)()
+            smax = int(L.load().ndb_conv_stats_layout(self.B, H, W, ops.pad16(cout), 0, counts))
+            if smax < 1:
+                raise L.NdbError('ndb_conv_stats_layout failed')
+            self._layouts[key] = (smax, torch.tensor(list(counts), dtype=torch.int32, device=self.device))
+        return self._layouts[key]
+
+    def _conv(self, segs, H, W, cout, want_stats, out=None, **kw):
+        """Emit one implicit-GEMM launch. With want_stats the epilogue also produces the output's per-channel
+        statistics (or, for geometries it does not cover, a standalone statistics launch follows)."""
+        B, fmt = self.B, self.fmt
+        if out is None:
+            out = self.pool.get((B, H, W, cout), torch.float32)
+        stats = None
+        fused = want_stats and ops.conv_stats_supported(B, H, W)
+        if fused:
+            smax, counts = self._conv_stats_layout(H, W, cout)
+            stats = self._stats_buf(cout, smax, counts)
+            self.steps.append(lambda: ops.conv_gemm(segs, B, H, W, cout, out=out, fmt=fmt, stats=stats, **kw))
+        else:
+            self.steps.append(lambda: ops.conv_gemm(segs, B, H, W, cout, out=out, fmt=fmt, **kw))
+            if want_stats:
+                stats = self._stats_buf(cout)
+                self._emit_stats_kernel(out, stats)
+        return _Act(out, stats)
 
     # ------------------------------------------------------------------------------------------
     # plan construction
@@ -136,15 +194,11 @@ class UNetEngine:
         self.steps.append(lambda: ops.conv_gemm([(a_view, w_all)], 1, 1, B, total, bias=b_all,
                                                 out=self.emb_all, fmt=fmt, cout_pad=total))
 
-        # ---- GroupNorm statistics: one [B,32,2] fp64 slot per norm + one shared reduction workspace ----
-        n_gn = sum(1 for mod in m.modules() if isinstance(mod, torch.nn.GroupNorm))
-        self.stats_pool = torch.zeros((n_gn, B, 32, 2), dtype=torch.float64, device=dev)
-        self._stats_i = 0
+        # ---- workspace of the standalone statistics kernel (stem output, uncovered geometries) ----
         ws_bytes = 0
         res = R
         while res >= 1:
-            for c in (64, 4096):
-                ws_bytes = max(ws_bytes, int(L.load().ndb_gn_stats_workspace_bytes(B, res * res, c)))
+            ws_bytes = max(ws_bytes, int(L.load().ndb_gn_stats_workspace_bytes(B, res * res, 4096)))
             res //= 2
         self.gn_ws = torch.zeros((ws_bytes + 7) // 8, dtype=torch.int64, device=dev)
 
@@ -152,8 +206,9 @@ class UNetEngine:
         stem = m.downsampling[0][0]
         stem_w = self._copy_param(stem.weight); stem_b = self._copy_param(stem.bias)
         C0 = stem.weight.shape[0]
-        x = self.pool.get((B, R, R, C0), torch.float32)
-        self.steps.append(lambda x=x: ops.stem_conv(self.x_in, stem_w, stem_b, out=x))
+        x = _Act(self.pool.get((B, R, R, C0), torch.float32), self._stats_buf(C0))
+        self.steps.append(lambda: ops.stem_conv(self.x_in, stem_w, stem_b, out=x.t))
+        self._emit_stats_kernel(x.t, x.stats)
         xs = [x]
         cur = x
         for seq in list(m.downsampling)[1:]:
@@ -163,41 +218,32 @@ class UNetEngine:
         for seq in m.upsampling:
             skip = xs.pop()
             new = self._run_sequential(seq, cur, skip, input_saved=False)
-            self.pool.put(skip)
+            self._release(skip)
             cur = new
         # head: GroupNorm -> SiLU -> conv3x3 to out_channels (model.py:446-449), NCHW fp32 out
         gn, conv = m.out[0], m.out[2]
-        C = cur.shape[-1]
-        st = self._next_stats()
         g = self._copy_param(gn.weight); bt = self._copy_param(gn.bias)
-        a = self.pool.get(tuple(cur.shape), self.dt16)
+        a = self.pool.get(tuple(cur.t.shape), self.dt16)
         wp = self._packed(conv.weight); bp = self._copy_param(conv.bias)
-        H = cur.shape[1]
-        self.steps.append(lambda cur=cur, st=st: ops.gn_stats(cur, stats=st, workspace=self.gn_ws))
-        self.steps.append(lambda cur=cur, st=st, a=a: ops.gn_apply(cur, st, g, bt, silu=True, out=a, fmt=fmt, eps=gn.eps))
-        self.steps.append(lambda a=a: ops.conv_gemm([(a, wp)], B, H, H, m.out_channels, bias=bp,
-                                                    out_kind=L.OUT_F32_NCHW, out=self.out, fmt=fmt))
+        H = cur.t.shape[1]
+        self.steps.append(lambda: ops.gn_apply(cur.t, cur.stats, g, bt, silu=True, out=a, fmt=fmt, eps=gn.eps))
+        self.steps.append(lambda: ops.conv_gemm([(a, wp)], B, H, H, m.out_channels, bias=bp,
+                                                out_kind=L.OUT_F32_NCHW, out=self.out, fmt=fmt))
         self.num_kernels = len(self.steps) + 1   # the embedding front end is two launches
 
     def _all_channels(self):
-        m = self.model
         cs = set()
-        for mod in m.modules():
+        for mod in self.model.modules():
             if isinstance(mod, ResidualBlock):
                 cs.add(mod.in_channels); cs.add(mod.out_channels)
             elif isinstance(mod, AttentionBlock):
                 cs.add(mod.channels)
         return cs
 
-    def _next_stats(self):
-        s = self.stats_pool[self._stats_i]
-        self._stats_i += 1
-        return s
-
     def _run_sequential(self, seq, x, skip, input_saved):
         """Emit the launches of one UsesStepsSequential (model.py:40-48). `x` (+ optional concat partner `skip`
-        for the first layer, model.py:474) is the input; returns the output tensor. Buffers of consumed
-        intermediates go back to the pool; `input_saved` says the input is still referenced by the skip stack."""
+        for the first layer, model.py:474) is the input; returns the output. Buffers of consumed intermediates go
+        back to the pool; `input_saved` says the input is still referenced by the skip stack."""
         cur, cur_saved, first = x, input_saved, True
         for layer in seq:
             if isinstance(layer, ResidualBlock):
@@ -211,15 +257,15 @@ class UNetEngine:
             else:
                 raise L.NdbError('unexpected layer {}'.format(type(layer)))
             if not cur_saved:
-                self.pool.put(cur)
+                self._release(cur)
             cur, cur_saved, first = out, False, False
         return cur
 
     # ---- blocks ---------------------------------------------------------------------------
     def _resblock(self, rb, x, skip):
         B, fmt, pool = self.B, self.fmt, self.pool
-        _, H, W, C0 = x.shape
-        C1 = skip.shape[-1] if skip is not None else 0
+        _, H, W, C0 = x.t.shape
+        C1 = skip.t.shape[-1] if skip is not None else 0
         Cin, Cout = rb.in_channels, rb.out_channels
         assert C0 + C1 == Cin, (C0, C1, Cin)
         mode = {'same': L.RESAMPLE_NONE, 'up': L.RESAMPLE_UP2, 'down': L.RESAMPLE_DOWN2}[rb.mode]
@@ -246,57 +292,51 @@ class UNetEngine:
             scale = shift = None
             pre = self.emb_all[:, off:off + Cout]
 
-        st1, st2 = self._next_stats(), self._next_stats()
         a1 = pool.get((B, Ho, Wo, Cin), self.dt16)
         raw = pool.get((B, Ho, Wo, Cin), self.dt16) if conv_skip else None
-        h = pool.get((B, Ho, Wo, Cout), torch.float32)
         a2 = pool.get((B, Ho, Wo, Cout), self.dt16)
-        out = pool.get((B, Ho, Wo, Cout), torch.float32)
         eps1, eps2 = rb.in_norm.eps, rb.out_norm.eps
+        x1 = skip.t if skip is not None else None
+        s1 = skip.stats if skip is not None else None
 
-        self.steps.append(lambda: ops.gn_stats(x, skip, stats=st1, workspace=self.gn_ws))
-        self.steps.append(lambda: ops.gn_apply(x, st1, g1, b1, x1=skip, silu=True, resample=mode, out=a1, raw16=raw,
-                                               fmt=fmt, eps=eps1))
-        self.steps.append(lambda: ops.conv_gemm([(a1, w_in)], B, Ho, Wo, Cout, bias=bias_in, out=h, fmt=fmt))
-        self.steps.append(lambda: ops.gn_stats(h, pre_add=pre, stats=st2, workspace=self.gn_ws))
-        self.steps.append(lambda: ops.gn_apply(h, st2, g2, b2, scale=scale, shift=shift, pre_add=pre, silu=True,
+        self.steps.append(lambda: ops.gn_apply(x.t, x.stats, g1, b1, x1=x1, stats1=s1, silu=True, resample=mode,
+                                               out=a1, raw16=raw, fmt=fmt, eps=eps1))
+        h = self._conv([(a1, w_in)], Ho, Wo, Cout, want_stats=True, bias=bias_in)
+        self.steps.append(lambda: ops.gn_apply(h.t, h.stats, g2, b2, scale=scale, shift=shift, pre_add=pre, silu=True,
                                                out=a2, fmt=fmt, eps=eps2))
         if conv_skip:
-            segs = [(a2, w_out), (raw, w_skip)]  # 1x1 (or 3x3 when use_conv) skip conv as extra K range
-            self.steps.append(lambda: ops.conv_gemm(segs, B, Ho, Wo, Cout, bias=bias_out, out=out, fmt=fmt))
+            # 1x1 (or 3x3 when use_conv) skip conv as an extra K range of the same GEMM
+            out = self._conv([(a2, w_out), (raw, w_skip)], Ho, Wo, Cout, want_stats=True, bias=bias_out)
         else:
             rmode = {'same': L.RES_SAME, 'up': L.RES_UP2, 'down': L.RES_DOWN2}[rb.mode]
-            self.steps.append(lambda: ops.conv_gemm([(a2, w_out)], B, Ho, Wo, Cout, bias=bias_out, residual=x,
-                                                    residual_mode=rmode, out=out, fmt=fmt))
-        for t in (a1, raw, h, a2):
+            out = self._conv([(a2, w_out)], Ho, Wo, Cout, want_stats=True, bias=bias_out, residual=x.t,
+                             residual_mode=rmode)
+        for t in (a1, raw, a2):
             if t is not None:
                 pool.put(t)
+        self._release(h)
         return out
 
     def _attention(self, ab, x):
         B, fmt, pool = self.B, self.fmt, self.pool
-        _, H, W, C = x.shape
+        _, H, W, C = x.t.shape
         T = H * W
         heads = ab.num_heads
         d = C // heads
         g = self._copy_param(ab.norm.weight); bt = self._copy_param(ab.norm.bias)
         w_qkv = self._packed(ab.qkv_nin.weight); b_qkv = self._copy_param(ab.qkv_nin.bias)
         w_proj = self._packed(ab.proj_out.weight); b_proj = self._copy_param(ab.proj_out.bias)
-        st = self._next_stats()
         n16 = pool.get((B, H, W, C), self.dt16)
         qkv = pool.get((B, H, W, 3 * C), self.dt16)
         o16 = pool.get((B, H, W, C), self.dt16)
-        out = pool.get((B, H, W, C), torch.float32)
         order = 0 if ab.split_qkv_first else 1
         eps = ab.norm.eps
-        self.steps.append(lambda: ops.gn_stats(x, stats=st, workspace=self.gn_ws))
-        self.steps.append(lambda: ops.gn_apply(x, st, g, bt, silu=False, out=n16, fmt=fmt, eps=eps))
-        self.steps.append(lambda: ops.conv_gemm([(n16, w_qkv)], B, H, W, 3 * C, bias=b_qkv,
-                                                out_kind=L.OUT_F16_NHWC, out=qkv, fmt=fmt))
+        self.steps.append(lambda: ops.gn_apply(x.t, x.stats, g, bt, silu=False, out=n16, fmt=fmt, eps=eps))
+        self._conv([(n16, w_qkv)], H, W, 3 * C, want_stats=False, out=qkv, bias=b_qkv, out_kind=L.OUT_F16_NHWC)
         self.steps.append(lambda: ops.attention(qkv.view(B, T, 3 * C), B, T, heads, d, order=order,
                                                 out=o16.view(B, T, C), fmt=fmt))
-        self.steps.append(lambda: ops.conv_gemm([(o16, w_proj)], B, H, W, C, bias=b_proj, residual=x,
-                                                residual_mode=L.RES_SAME, out=out, fmt=fmt))
+        out = self._conv([(o16, w_proj)], H, W, C, want_stats=True, bias=b_proj, residual=x.t,
+                         residual_mode=L.RES_SAME)
         for t in (n16, qkv, o16):
             pool.put(t)
         return out
@@ -304,36 +344,38 @@ class UNetEngine:
     def _upsample(self, layer, x):
         """Standalone Upsample (resblock_updown=False): nearest x2 [+ conv3x3] (model.py:76-80)."""
         B, fmt, pool = self.B, self.fmt, self.pool
-        _, H, W, C = x.shape
+        _, H, W, C = x.t.shape
         up = pool.get((B, 2 * H, 2 * W, C), torch.float32)
-        self.steps.append(lambda: ops.resample_f32(x, L.RESAMPLE_UP2, out=up))
+        self.steps.append(lambda: ops.resample_f32(x.t, L.RESAMPLE_UP2, out=up))
         if not layer.with_conv:
-            return up
+            act = _Act(up, self._stats_buf(C))
+            self._emit_stats_kernel(up, act.stats)
+            return act
         Cout = layer.conv.weight.shape[0]
         a = pool.get((B, 2 * H, 2 * W, C), self.dt16)
-        out = pool.get((B, 2 * H, 2 * W, Cout), torch.float32)
         wp = self._packed(layer.conv.weight); bp = self._copy_param(layer.conv.bias)
         self.steps.append(lambda: ops.cast16(up, out=a, fmt=fmt))
-        self.steps.append(lambda: ops.conv_gemm([(a, wp)], B, 2 * H, 2 * W, Cout, bias=bp, out=out, fmt=fmt))
+        out = self._conv([(a, wp)], 2 * H, 2 * W, Cout, want_stats=True, bias=bp)
         pool.put(up); pool.put(a)
         return out
 
     def _downsample(self, layer, x):
         """Standalone Downsample: conv3x3 stride 2 (as nine 1x1 K-segments over a gathered operand) or avg-pool."""
         B, fmt, pool = self.B, self.fmt, self.pool
-        _, H, W, C = x.shape
+        _, H, W, C = x.t.shape
         if not layer.with_conv:
             out = pool.get((B, H // 2, W // 2, C), torch.float32)
-            self.steps.append(lambda: ops.resample_f32(x, L.RESAMPLE_DOWN2, out=out))
-            return out
+            self.steps.append(lambda: ops.resample_f32(x.t, L.RESAMPLE_DOWN2, out=out))
+            act = _Act(out, self._stats_buf(C))
+            self._emit_stats_kernel(out, act.stats)
+            return act
         Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
         Cout = layer.conv.weight.shape[0]
         cols = pool.get((9, B, Ho, Wo, C), self.dt16)
-        out = pool.get((B, Ho, Wo, Cout), torch.float32)
         wp = self._packed(layer.conv.weight); bp = self._copy_param(layer.conv.bias)
         segs = [(cols[tap], wp[tap:tap + 1]) for tap in range(9)]
-        self.steps.append(lambda: ops.im2col_s2(x, out=cols, fmt=fmt))
-        self.steps.append(lambda: ops.conv_gemm(segs, B, Ho, Wo, Cout, bias=bp, out=out, fmt=fmt))
+        self.steps.append(lambda: ops.im2col_s2(x.t, out=cols, fmt=fmt))
+        out = self._conv(segs, Ho, Wo, Cout, want_stats=True, bias=bp)
         pool.put(cols)
         return out
 

@@ -75,7 +75,8 @@ def pack_conv_weight(w, cout_pad=None, cin_off=0, cin_len=None, fmt=L.FMT_FP16, 
 
 
 def conv_gemm(segments, N, H, W, cout, bias=None, residual=None, residual_mode=L.RES_NONE,
-              out_kind=L.OUT_F32_NHWC, out=None, fmt=L.FMT_FP16, block_n=0, cout_pad=None):
+              out_kind=L.OUT_F32_NHWC, out=None, fmt=L.FMT_FP16, block_n=0, cout_pad=None,
+              stats=None):
     """segments: list of (act16 [N,H,W,C], packed_weight [taps,cout_pad,C]).  Returns `out`."""
     p = L.ConvParams()
     p.N, p.H, p.W = N, H, W
@@ -107,7 +108,11 @@ def conv_gemm(segments, N, H, W, cout, bias=None, residual=None, residual_mode=L
     p.out = out.data_ptr()
     p.operand_format = fmt
     p.block_n = block_n
-    p.gn_stats = None
+    if stats is not None:
+        parts = stats[0]   # float32 [N, smax, cout, 2]
+        assert parts.dtype == torch.float32 and parts.shape[0] == N and parts.shape[2] == cout and parts.shape[3] == 2
+        p.stat_parts = parts.data_ptr()
+        p.stat_smax = parts.shape[1]
     _begin()
     L.check(L.load().ndb_conv_gemm(C.byref(p), L.stream_ptr()), 'ndb_conv_gemm')
     _count('conv_gemm', 2 * N * H * W * cout * sum(a.shape[-1] * w.shape[0] for a, w in segments),
@@ -116,31 +121,66 @@ def conv_gemm(segments, N, H, W, cout, bias=None, residual=None, residual_mode=L
     return out
 
 
+def conv_stats_supported(N, H, W):
+    return bool(L.load().ndb_conv_stats_supported(N, H, W))
+
+
+def conv_stats_alloc(N, H, W, cout, device, cout_pad=None, block_n=0):
+    """Buffers for the statistics a conv epilogue writes for its output: (parts float32 [N, smax, cout, 2],
+    counts int32 [N]) -- see ndb_conv_stats_layout."""
+    import ctypes
+    cp = pad16(cout) if cout_pad is None else cout_pad
+    counts = (ctypes.c_int32 * N)()
+    smax = int(L.load().ndb_conv_stats_layout(N, H, W, cp, block_n, counts))
+    if smax < 1:
+        raise L.NdbError('ndb_conv_stats_layout failed ({})'.format(smax))
+    parts = torch.zeros((N, smax, cout, 2), dtype=torch.float32, device=device)
+    return parts, torch.tensor(list(counts), dtype=torch.int32, device=device)
+
+
 def gn_workspace(N, HW, C, device):
     """Zero-filled scratch for gn_stats (see ndb_gn_stats_workspace_bytes)."""
     nbytes = int(L.load().ndb_gn_stats_workspace_bytes(N, HW, C))
     return torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device=device)
 
 
-def gn_stats(x0, x1=None, pre_add=None, stats=None, workspace=None):
-    """x0 [N,H,W,C0] (+ x1 [N,H,W,C1]) fp32 -> fp64 [N,32,2] (sum, sumsq). Deterministic (no fp atomics)."""
+def gn_stats(x0, x1=None, stats0=None, stats1=None, workspace=None):
+    """Standalone statistics producer: per-channel (sum, sumsq) over the pixels of each image, one slot per image:
+    x0 [N,H,W,C0] fp32 -> (parts float32 [N,1,C0,2], counts int32 [N] of ones); same for an optional second tensor
+    in the same launch. Deterministic (no fp atomics)."""
     L.require_device(x0, 'gn_stats')
     N = x0.shape[0]
     HW = x0.shape[1] * x0.shape[2]
-    C = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
-    if stats is None:
-        stats = torch.empty((N, 32, 2), dtype=torch.float64, device=x0.device)
+    C0 = x0.shape[-1]
+    C1 = x1.shape[-1] if x1 is not None else 0
+
+    def fresh(C):
+        return (torch.empty((N, 1, C, 2), dtype=torch.float32, device=x0.device),
+                torch.ones((N,), dtype=torch.int32, device=x0.device))
+    if stats0 is None:
+        stats0 = fresh(C0)
+    if x1 is not None and stats1 is None:
+        stats1 = fresh(C1)
     if workspace is None:
-        workspace = gn_workspace(N, HW, C, x0.device)
+        workspace = gn_workspace(N, HW, C0 + C1, x0.device)
+    assert stats0[0].shape[1] == 1
     _begin()
-    L.check(L.load().ndb_gn_stats(L.ptr(x0), x0.shape[-1], L.ptr(x1), x1.shape[-1] if x1 is not None else 0, N, HW,
-                                  L.ptr(pre_add), pre_add.stride(0) if pre_add is not None else 0,
-                                  L.ptr(stats), L.ptr(workspace), L.stream_ptr()), 'ndb_gn_stats')
-    _count('gn_stats', 0, 'N{} HW{} C{}'.format(N, HW, C))
-    return stats
+    L.check(L.load().ndb_gn_stats(L.ptr(x0), C0, L.ptr(x1), C1, N, HW, L.ptr(stats0[0]),
+                                  L.ptr(stats1[0]) if x1 is not None else None,
+                                  L.ptr(workspace), L.stream_ptr()), 'ndb_gn_stats')
+    _count('gn_stats', 0, 'N{} HW{} C{}'.format(N, HW, C0 + C1))
+    return (stats0, stats1) if x1 is not None else stats0
 
 
-def gn_apply(x0, stats, gamma, beta, x1=None, scale=None, shift=None, pre_add=None, silu=True,
+def stats_totals(stats):
+    """(parts, counts) -> float64 [N, C, 2] totals (test helper; the kernels never materialise this)."""
+    parts, counts = stats
+    N, smax = parts.shape[0], parts.shape[1]
+    mask = (torch.arange(smax, device=parts.device)[None, :] < counts[:, None]).to(torch.float64)
+    return (parts.double() * mask[:, :, None, None]).sum(1)
+
+
+def gn_apply(x0, stats0, gamma, beta, x1=None, stats1=None, scale=None, shift=None, pre_add=None, silu=True,
              resample=L.RESAMPLE_NONE, out=None, raw16=None, want_raw16=False, fmt=L.FMT_FP16, eps=1e-5):
     L.require_device(x0, 'gn_apply')
     N, H, W, C0 = x0.shape
@@ -158,7 +198,11 @@ def gn_apply(x0, stats, gamma, beta, x1=None, scale=None, shift=None, pre_add=No
     p.x0, p.C0 = x0.data_ptr(), C0
     p.x1, p.C1 = (x1.data_ptr() if x1 is not None else None), C1
     p.N, p.H, p.W = N, H, W
-    p.stats = stats.data_ptr()
+    p.parts0, p.counts0, p.smax0 = stats0[0].data_ptr(), stats0[1].data_ptr(), stats0[0].shape[1]
+    assert stats0[0].shape[2] == C0
+    if x1 is not None:
+        assert stats1 is not None and stats1[0].shape[2] == C1
+        p.parts1, p.counts1, p.smax1 = stats1[0].data_ptr(), stats1[1].data_ptr(), stats1[0].shape[1]
     p.gamma, p.beta = gamma.data_ptr(), beta.data_ptr()
     if scale is not None:
         assert scale.stride(0) == shift.stride(0) and scale.stride(1) == 1

@@ -113,6 +113,37 @@ def test_conv_gemm_segments_fuse_concat_and_skip(cuda_dev):
     assert rel_err(out.permute(0, 3, 1, 2), ref) < 2e-5
 
 
+@pytest.mark.parametrize('N,H,W,Cin,Cout,res', [(3, 32, 32, 64, 192, 0), (4, 16, 16, 128, 384, 1), (5, 8, 8, 64, 576, 1),
+                                                (2, 64, 64, 64, 64, 0), (2, 28, 28, 64, 128, 1)])
+def test_conv_epilogue_fused_groupnorm_statistics(cuda_dev, N, H, W, Cin, Cout, res):
+    """chan_stats written by the GEMM epilogue == per-channel sums of the tensor it stored; bit-identical re-runs."""
+    ops, L = _ops()
+    assert ops.conv_stats_supported(N, H, W)
+    g = torch.Generator(device='cpu').manual_seed(N + H + Cout)
+    x = torch.randn(N, Cin, H, W, generator=g).to(cuda_dev)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)).to(cuda_dev)
+    b = (0.5 * torch.randn(Cout, generator=g)).to(cuda_dev)
+    r = nhwc(torch.randn(N, Cout, H, W, generator=g).to(cuda_dev)) if res else None
+    x16, wp = nhwc(x).half(), ops.pack_conv_weight(w)
+    st = ops.conv_stats_alloc(N, H, W, Cout, cuda_dev)
+    st[0].fill_(float('nan'))
+    out = ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, residual=r, residual_mode=L.RES_SAME, stats=st)
+    o = out.double().flatten(1, 2)                      # [N, HW, C]
+    tot = ops.stats_totals(st)
+    assert torch.allclose(tot[:, :, 0], o.sum(1), rtol=1e-5, atol=2e-3)
+    assert torch.allclose(tot[:, :, 1], (o * o).sum(1), rtol=1e-5, atol=2e-3)
+    st2 = ops.conv_stats_alloc(N, H, W, Cout, cuda_dev)
+    out2 = ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, residual=r, residual_mode=L.RES_SAME, stats=st2)
+    assert torch.equal(out, out2) and torch.equal(ops.stats_totals(st), ops.stats_totals(st2))
+    # a GroupNorm fed by the fused statistics == one fed by the standalone statistics kernel == torch
+    gamma = (1 + 0.1 * torch.randn(Cout, generator=g)).to(cuda_dev)
+    beta = (0.1 * torch.randn(Cout, generator=g)).to(cuda_dev)
+    a = ops.gn_apply(out, st, gamma, beta, silu=True)
+    bq = ops.gn_apply(out, ops.gn_stats(out), gamma, beta, silu=True)
+    ref = F.silu(F.group_norm(out.permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-5))
+    assert rel_err(a.permute(0, 3, 1, 2), ref) < 1.5e-3 and rel_err(bq.permute(0, 3, 1, 2), ref) < 1.5e-3
+
+
 def test_linear_as_gemm(cuda_dev):
     """The per-ResBlock step_embedding Linear layers run as one 1x1 'conv' over a [1,1,B,E] image."""
     ops, L = _ops()
@@ -143,9 +174,12 @@ def test_groupnorm_apply(cuda_dev, N, H, W, C0, C1, resample):
     ss = (0.3 * torch.randn(N, 2 * C, generator=g)).to(cuda_dev)
     scale, shift = ss[:, :C], ss[:, C:]
     xin = torch.cat([x0, x1], 1) if C1 else x0
-    stats = ops.gn_stats(nhwc(x0), nhwc(x1) if C1 else None)
-    out, raw = ops.gn_apply(nhwc(x0), stats, gamma, beta, x1=nhwc(x1) if C1 else None, scale=scale, shift=shift,
-                            silu=True, resample=resample, want_raw16=True)
+    if C1:
+        st0, st1 = ops.gn_stats(nhwc(x0), nhwc(x1))
+    else:
+        st0, st1 = ops.gn_stats(nhwc(x0)), None
+    out, raw = ops.gn_apply(nhwc(x0), st0, gamma, beta, x1=nhwc(x1) if C1 else None, stats1=st1, scale=scale,
+                            shift=shift, silu=True, resample=resample, want_raw16=True)
     ref = F.silu(F.group_norm(xin, 32, gamma, beta, eps=1e-5) * (1 + scale[:, :, None, None]) + shift[:, :, None, None])
     rraw = xin
     if resample == 1:
@@ -154,11 +188,13 @@ def test_groupnorm_apply(cuda_dev, N, H, W, C0, C1, resample):
         ref, rraw = F.avg_pool2d(ref, 2), F.avg_pool2d(xin, 2)
     assert rel_err(out.permute(0, 3, 1, 2), ref) < 1.5e-3   # fp16 output rounding
     assert rel_err(raw.permute(0, 3, 1, 2), rraw) < 1.5e-3
-    # statistics themselves: fp64 sums against torch
-    cpg = C // 32
-    xs = xin.double().reshape(N, 32, cpg * H * W)
-    assert torch.allclose(stats[:, :, 0], xs.sum(-1), rtol=1e-5, atol=1e-3)
-    assert torch.allclose(stats[:, :, 1], (xs * xs).sum(-1), rtol=1e-5, atol=1e-3)
+    # statistics themselves: per-channel fp64 sums against torch, and run-to-run bit-exactness
+    xs = x0.double().flatten(2)
+    tot = ops.stats_totals(st0)
+    assert torch.allclose(tot[:, :, 0], xs.sum(-1), rtol=1e-6, atol=1e-3)
+    assert torch.allclose(tot[:, :, 1], (xs * xs).sum(-1), rtol=1e-6, atol=1e-3)
+    again = ops.gn_stats(nhwc(x0), nhwc(x1))[0] if C1 else ops.gn_stats(nhwc(x0))
+    assert torch.equal(again[0], st0[0])
 
 
 def test_groupnorm_plain_preadd_nosilu(cuda_dev):
@@ -170,7 +206,7 @@ def test_groupnorm_plain_preadd_nosilu(cuda_dev):
     e = torch.randn(N, C, generator=g).to(cuda_dev)
     gamma = (1 + 0.1 * torch.randn(C, generator=g)).to(cuda_dev)
     beta = (0.1 * torch.randn(C, generator=g)).to(cuda_dev)
-    stats = ops.gn_stats(nhwc(x), pre_add=e)
+    stats = ops.gn_stats(nhwc(x))
     out = ops.gn_apply(nhwc(x), stats, gamma, beta, pre_add=e, silu=False)
     ref = F.group_norm(x + e[:, :, None, None], 32, gamma, beta, eps=1e-5)
     assert rel_err(out.permute(0, 3, 1, 2), ref) < 1.5e-3
