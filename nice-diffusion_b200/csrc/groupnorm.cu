@@ -123,21 +123,66 @@ struct GnApplyArgs {
     int pix_per_block, threads_per_row, rows_per_block;
 };
 
-// Thread (r, v): fixed 8-channel vector v, output pixels p = p_begin + r, + rows_per_block, ...  The per-channel
-// affine (a, b) = (rstd*gamma*(1+scale), (beta - mean*rstd*gamma + a'*pre)*(1+scale) + shift) lives in registers.
-template <int FMT, int RESAMPLE, bool SILU>
-__global__ void __launch_bounds__(kGnThreads)
+// Block = one sample n and a range of output pixels. Thread (r, v) owns the 8-channel vector v and pixels
+// p_begin + r, + rows_per_block, ...  Order of business, arranged so that the dependent-load chains overlap:
+//   0. request the first four pixels of this thread's data (independent of everything else);
+//   1. 8 lanes per group fold the statistics slots of the source tensor(s) into (mean, rstd) -> smem;
+//   2. all threads fold mean / rstd / gamma / beta / AdaGN (1+scale), shift / pre-add into one per-channel FMA
+//      (a_c, b_c) -> smem;
+//   3. stream: y = SiLU(a x + b) (+ resample) -> 16-bit operand, 16-byte stores, four pixels in flight per thread.
+template <int FMT, int RESAMPLE, bool SILU, bool RAW>
+__global__ void __launch_bounds__(kGnThreads, 3)
 gn_apply_kernel(const GnApplyArgs p) {
+    extern __shared__ float sm_ab[];   // a[C], b[C], pre[C]
+    __shared__ float s_mean[kGroups], s_rstd[kGroups];
     const int C = p.C0 + p.C1;
     const int V8 = C >> 3;
     const int n = blockIdx.y;
     const int cpg = C / kGroups;
-    // block prologue: the 32 group (mean, rstd) of sample n from the per-channel sums of the source tensors.
-    // With `pre_add` e_c (non-adaptive ResBlock: h += emb before the norm) the sums of (x + e_c) follow
-    // analytically: S' = S + P e, SS' = SS + 2 e S + P e^2.
-    __shared__ float s_mean[kGroups], s_rstd[kGroups];
+    float* sa = sm_ab;
+    float* sb = sm_ab + C;
+    float* sp = sm_ab + 2 * C;
+    const int r = threadIdx.x / p.threads_per_row;
+    const int tv = threadIdx.x - r * p.threads_per_row;
+    const bool worker = (r < p.rows_per_block) && (tv < V8);
+    const int npix = p.Ho * p.Wo;
+    const int p_begin = blockIdx.x * p.pix_per_block;
+    int p_end = p_begin + p.pix_per_block;
+    if (p_end > npix) p_end = npix;
+    constexpr int U = 4;
+
+    auto src_of = [&](int c, const float*& src, int& ldc) {
+        int cc;
+        if (c < p.C0) { src = p.x0; ldc = p.C0; cc = c; } else { src = p.x1; ldc = p.C1; cc = c - p.C0; }
+        src += (size_t)n * p.H * p.W * ldc + cc;
+    };
+    auto in_pixel = [&](int pu) {
+        if (RESAMPLE == NDB_RESAMPLE_UP2) {
+            const int ho = pu / p.Wo, wo = pu - ho * p.Wo;
+            return (ho >> 1) * p.W + (wo >> 1);
+        }
+        return pu;
+    };
+
+    // ---- 0. first trip's data ----
+    float4 lo[U], hi[U];
+    if (RESAMPLE != NDB_RESAMPLE_DOWN2 && worker) {
+        const float* src; int ldc;
+        src_of(tv << 3, src, ldc);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int pu = p_begin + r + u * p.rows_per_block;
+            if (pu < p_end) {
+                const float* px = src + (size_t)in_pixel(pu) * ldc;
+                lo[u] = __ldg(reinterpret_cast<const float4*>(px));
+                hi[u] = __ldg(reinterpret_cast<const float4*>(px + 4));
+            }
+        }
+    }
+
+    // ---- 1. group statistics. With `pre_add` e_c (non-adaptive ResBlock: h += emb before the norm) the sums of
+    //         (x + e_c) follow analytically: S' = S + P e, SS' = SS + 2 e S + P e^2. ----
     {
-        // 8 lanes per group: strided partial sums over the group's channels, then a 3-step shuffle tree (fixed order)
         const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
         const double P = (double)p.H * p.W;
         double S = 0.0, SS = 0.0;
@@ -181,44 +226,48 @@ gn_apply_kernel(const GnApplyArgs p) {
         }
     }
     __syncthreads();
-    const int r = threadIdx.x / p.threads_per_row;
-    const int tv = threadIdx.x - r * p.threads_per_row;
-    if (r >= p.rows_per_block) return;
-    const int npix = p.Ho * p.Wo;
-    const int p_begin = blockIdx.x * p.pix_per_block;
-    int p_end = p_begin + p.pix_per_block;
-    if (p_end > npix) p_end = npix;
+    // ---- 2. per-channel affine ----
+    for (int c = threadIdx.x; c < C; c += kGnThreads) {
+        const int g = c / cpg;
+        float ak = s_rstd[g] * __ldg(p.gamma + c);
+        float bk = __ldg(p.beta + c) - s_mean[g] * ak;
+        const float pr = p.pre_add ? __ldg(p.pre_add + (size_t)n * p.ld_pre + c) : 0.f;
+        bk += ak * pr;
+        if (p.scale != nullptr) {
+            const float s1 = 1.f + __ldg(p.scale + (size_t)n * p.ld_ss + c);
+            ak *= s1;
+            bk = bk * s1 + __ldg(p.shift + (size_t)n * p.ld_ss + c);
+        }
+        sa[c] = ak; sb[c] = bk;
+        if (RAW) sp[c] = pr;
+    }
+    __syncthreads();
+    if (!worker) return;
 
+    // ---- 3. stream ----
     for (int v = tv; v < V8; v += p.threads_per_row) {
         const int c = v << 3;
         float a[8], b[8], pre[8];
+        {
+            const float4 a0 = *reinterpret_cast<const float4*>(sa + c), a1 = *reinterpret_cast<const float4*>(sa + c + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(sb + c), b1 = *reinterpret_cast<const float4*>(sb + c + 4);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+            if (RAW) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int g = (c + k) / cpg;
-            float ak = s_rstd[g] * __ldg(p.gamma + c + k);
-            float bk = __ldg(p.beta + c + k) - s_mean[g] * ak;
-            const float pr = p.pre_add ? __ldg(p.pre_add + (size_t)n * p.ld_pre + c + k) : 0.f;
-            bk += ak * pr;
-            if (p.scale != nullptr) {
-                const float sc = 1.f + __ldg(p.scale + (size_t)n * p.ld_ss + c + k);
-                ak *= sc;
-                bk = bk * sc + __ldg(p.shift + (size_t)n * p.ld_ss + c + k);
+                for (int k = 0; k < 8; ++k) pre[k] = sp[c + k];
             }
-            a[k] = ak; b[k] = bk; pre[k] = pr;
         }
-        const float* src;
-        int ldc, cc;
-        if (c < p.C0) { src = p.x0; ldc = p.C0; cc = c; } else { src = p.x1; ldc = p.C1; cc = c - p.C0; }
-        src += (size_t)n * p.H * p.W * ldc + cc;
-        uint16_t* outp = p.out + (size_t)n * npix * C + c;
-        uint16_t* rawp = p.raw16 ? p.raw16 + (size_t)n * npix * C + c : nullptr;
-
-#pragma unroll 2
-        for (int po = p_begin + r; po < p_end; po += p.rows_per_block) {
-            float y[8], raw[8];
-            if (RESAMPLE == NDB_RESAMPLE_DOWN2) {
+        const float* src; int ldc;
+        src_of(c, src, ldc);
+        const float* __restrict__ srcp = src;
+        uint16_t* __restrict__ outq = p.out + (size_t)n * npix * C + c;
+        uint16_t* __restrict__ rawq = RAW ? p.raw16 + (size_t)n * npix * C + c : nullptr;
+        if (RESAMPLE == NDB_RESAMPLE_DOWN2) {
+            for (int po = p_begin + r; po < p_end; po += p.rows_per_block) {
+                float y[8], raw[8];
                 const int ho = po / p.Wo, wo = po - ho * p.Wo;
-                const float* px = src + ((size_t)(2 * ho) * p.W + 2 * wo) * ldc;
+                const float* px = srcp + ((size_t)(2 * ho) * p.W + 2 * wo) * ldc;
                 const float4 l0 = __ldg(reinterpret_cast<const float4*>(px)), h0 = __ldg(reinterpret_cast<const float4*>(px + 4));
                 const float4 l1 = __ldg(reinterpret_cast<const float4*>(px + ldc)), h1 = __ldg(reinterpret_cast<const float4*>(px + ldc + 4));
                 const float* py = px + (size_t)p.W * ldc;
@@ -236,46 +285,71 @@ gn_apply_kernel(const GnApplyArgs p) {
                         float t = a[k] * xv[q][k] + b[k];
                         if (SILU) t = silu_f(t);
                         acc += t;
-                        racc += xv[q][k] + pre[k];
+                        if (RAW) racc += xv[q][k] + pre[k];
                     }
                     y[k] = acc * 0.25f;
                     raw[k] = racc * 0.25f;
                 }
-            } else {
-                int pi = po;
-                if (RESAMPLE == NDB_RESAMPLE_UP2) {
-                    const int ho = po / p.Wo, wo = po - ho * p.Wo;
-                    pi = (ho >> 1) * p.W + (wo >> 1);
-                }
-                const float* px = src + (size_t)pi * ldc;
-                const float4 lo = __ldg(reinterpret_cast<const float4*>(px));
-                const float4 hi = __ldg(reinterpret_cast<const float4*>(px + 4));
-                const float xv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+                const size_t o = (size_t)po * C;
+                *reinterpret_cast<uint4*>(outq + o) =
+                    make_uint4(pack2h<FMT>(y[0], y[1]), pack2h<FMT>(y[2], y[3]), pack2h<FMT>(y[4], y[5]), pack2h<FMT>(y[6], y[7]));
+                if (RAW)
+                    *reinterpret_cast<uint4*>(rawq + o) = make_uint4(pack2h<FMT>(raw[0], raw[1]), pack2h<FMT>(raw[2], raw[3]),
+                                                                     pack2h<FMT>(raw[4], raw[5]), pack2h<FMT>(raw[6], raw[7]));
+            }
+        } else {
+            for (int po = p_begin + r; po < p_end; po += U * p.rows_per_block) {
+                if (!(v == tv && po == p_begin + r)) {   // the very first trip was requested before the prologue
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    float t = a[k] * xv[k] + b[k];
-                    if (SILU) t = silu_f(t);
-                    y[k] = t;
-                    raw[k] = xv[k] + pre[k];
+                    for (int u = 0; u < U; ++u) {
+                        const int pu = po + u * p.rows_per_block;
+                        if (pu < p_end) {
+                            const float* px = srcp + (size_t)in_pixel(pu) * ldc;
+                            lo[u] = __ldg(reinterpret_cast<const float4*>(px));
+                            hi[u] = __ldg(reinterpret_cast<const float4*>(px + 4));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int pu = po + u * p.rows_per_block;
+                    if (pu < p_end) {
+                        const float xv[8] = {lo[u].x, lo[u].y, lo[u].z, lo[u].w, hi[u].x, hi[u].y, hi[u].z, hi[u].w};
+                        float y[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            float t = a[k] * xv[k] + b[k];
+                            if (SILU) t = silu_f(t);
+                            y[k] = t;
+                        }
+                        const size_t o = (size_t)pu * C;
+                        *reinterpret_cast<uint4*>(outq + o) = make_uint4(pack2h<FMT>(y[0], y[1]), pack2h<FMT>(y[2], y[3]),
+                                                                         pack2h<FMT>(y[4], y[5]), pack2h<FMT>(y[6], y[7]));
+                        if (RAW)
+                            *reinterpret_cast<uint4*>(rawq + o) =
+                                make_uint4(pack2h<FMT>(xv[0] + pre[0], xv[1] + pre[1]), pack2h<FMT>(xv[2] + pre[2], xv[3] + pre[3]),
+                                           pack2h<FMT>(xv[4] + pre[4], xv[5] + pre[5]), pack2h<FMT>(xv[6] + pre[6], xv[7] + pre[7]));
+                    }
                 }
             }
-            const size_t o = (size_t)po * C;
-            *reinterpret_cast<uint4*>(outp + o) =
-                make_uint4(pack2h<FMT>(y[0], y[1]), pack2h<FMT>(y[2], y[3]), pack2h<FMT>(y[4], y[5]), pack2h<FMT>(y[6], y[7]));
-            if (rawp != nullptr)
-                *reinterpret_cast<uint4*>(rawp + o) = make_uint4(pack2h<FMT>(raw[0], raw[1]), pack2h<FMT>(raw[2], raw[3]),
-                                                                 pack2h<FMT>(raw[4], raw[5]), pack2h<FMT>(raw[6], raw[7]));
         }
     }
 }
 
-template <int FMT>
-static void launch_gn_apply(const GnApplyArgs& a, dim3 grid, cudaStream_t st) {
-#define NDB_GN_CASE(RS, SL) gn_apply_kernel<FMT, RS, SL><<<grid, kGnThreads, 0, st>>>(a)
+template <int FMT, bool RAW>
+static void launch_gn_apply2(const GnApplyArgs& a, dim3 grid, cudaStream_t st) {
+    const size_t smem = 3 * (size_t)(a.C0 + a.C1) * sizeof(float);
+#define NDB_GN_CASE(RS, SL) gn_apply_kernel<FMT, RS, SL, RAW><<<grid, kGnThreads, smem, st>>>(a)
     if (a.resample == NDB_RESAMPLE_NONE) { if (a.silu) NDB_GN_CASE(NDB_RESAMPLE_NONE, true); else NDB_GN_CASE(NDB_RESAMPLE_NONE, false); }
     else if (a.resample == NDB_RESAMPLE_UP2) { if (a.silu) NDB_GN_CASE(NDB_RESAMPLE_UP2, true); else NDB_GN_CASE(NDB_RESAMPLE_UP2, false); }
     else { if (a.silu) NDB_GN_CASE(NDB_RESAMPLE_DOWN2, true); else NDB_GN_CASE(NDB_RESAMPLE_DOWN2, false); }
 #undef NDB_GN_CASE
+}
+
+template <int FMT>
+static void launch_gn_apply(const GnApplyArgs& a, dim3 grid, cudaStream_t st) {
+    if (a.raw16 != nullptr) launch_gn_apply2<FMT, true>(a, grid, st);
+    else launch_gn_apply2<FMT, false>(a, grid, st);
 }
 
 }  // namespace ndb
@@ -356,7 +430,9 @@ extern "C" int ndb_gn_apply(const ndb_gn_apply_params* q, void* stream) {
     a.threads_per_row = V8 < kGnThreads ? V8 : kGnThreads;
     a.rows_per_block = kGnThreads / a.threads_per_row;
     const int npix = a.Ho * a.Wo;
-    int blocks_per_sample = (8 * num_sms() + q->N - 1) / q->N;
+    // one full wave at the kernel's occupancy (3 blocks per SM): no tail wave, prologue amortised over more pixels
+    int blocks_per_sample = (3 * num_sms()) / q->N;
+    if (blocks_per_sample < 1) blocks_per_sample = 1;
     int ppb = (npix + blocks_per_sample - 1) / blocks_per_sample;
     const int min_pix = a.rows_per_block * 4;
     if (ppb < min_pix) ppb = min_pix;
