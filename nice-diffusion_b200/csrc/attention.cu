@@ -32,6 +32,12 @@ struct AttnArgs {
     int C;
 };
 
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int FMT>
 __device__ __forceinline__ uint32_t pack2a(float a, float b) {
     if (FMT == 0) {
@@ -164,19 +170,26 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
             mbar_wait(s_full, j & 1);
             tc_fence_after();
             const int kv_valid = p.T - j * kAttnBN;  // keys >= kv_valid in this block are padding
-            // pass 1: row max
-            float m_blk = -INFINITY;
+            const bool full = kv_valid >= kAttnBN;
+            // pass 1: row max (four independent chains)
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
             for (int c0 = 0; c0 < kAttnBN; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_S + lane_addr + c0, r);
                 tmem_ld_wait();
+                if (full) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c0 + i < kv_valid) m_blk = fmaxf(m_blk, __uint_as_float(r[i]));
+                    for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c0 + i < kv_valid) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[i]));
+                }
             }
+            const float m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
             const float m_new = fmaxf(m_run, m_blk);
-            const float alpha = exp2f((m_run - m_new) * p.scale_log2e);  // 0 when m_run = -inf
+            const float alpha = ex2_fast((m_run - m_new) * p.scale_log2e);  // 0 when m_run = -inf
             const bool need_fix = (j > 0) && (m_new > m_run);
             // previous block's P V must have retired before P (smem) and O (TMEM) are touched
             if (j > 0) {
@@ -199,19 +212,29 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
             m_run = m_new;
             // pass 2: p = exp2((s - m) * scale*log2e) -> fp16 P tile in the K-major SWIZZLE_128B layout
             const float mb = m_new * p.scale_log2e;
-            float l_blk = 0.f;
+            float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
             for (int c0 = 0; c0 < kAttnBN; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_S + lane_addr + c0, r);
                 tmem_ld_wait();
                 uint32_t pk[16];
+                if (full) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float p0 = (c0 + i < kv_valid) ? exp2f(__uint_as_float(r[i]) * p.scale_log2e - mb) : 0.f;
-                    float p1 = (c0 + i + 1 < kv_valid) ? exp2f(__uint_as_float(r[i + 1]) * p.scale_log2e - mb) : 0.f;
-                    l_blk += p0 + p1;
-                    pk[i >> 1] = pack2a<FMT>(p0, p1);
+                    for (int i = 0; i < 32; i += 2) {
+                        const float p0 = ex2_fast(fmaf(__uint_as_float(r[i]), p.scale_log2e, -mb));
+                        const float p1 = ex2_fast(fmaf(__uint_as_float(r[i + 1]), p.scale_log2e, -mb));
+                        ls[(i >> 1) & 3] += p0 + p1;
+                        pk[i >> 1] = pack2a<FMT>(p0, p1);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float p0 = (c0 + i < kv_valid) ? ex2_fast(fmaf(__uint_as_float(r[i]), p.scale_log2e, -mb)) : 0.f;
+                        const float p1 = (c0 + i + 1 < kv_valid) ? ex2_fast(fmaf(__uint_as_float(r[i + 1]), p.scale_log2e, -mb)) : 0.f;
+                        ls[(i >> 1) & 3] += p0 + p1;
+                        pk[i >> 1] = pack2a<FMT>(p0, p1);
+                    }
                 }
                 // 32 keys = 64 bytes = four 16-byte chunks of this row's 128-byte line in K-chunk (c0 / 64)
                 uint8_t* line = sP + (c0 >> 6) * kChunkBytes + row * 128;
@@ -222,6 +245,7 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
                     *reinterpret_cast<uint4*>(line + phys * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 }
             }
+            const float l_blk = (ls[0] + ls[1]) + (ls[2] + ls[3]);
             l_run += l_blk;
             fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
             tc_fence_before();
