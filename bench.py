@@ -235,10 +235,15 @@ def main():
     clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = ops.LAUNCHES
+    if os.environ.get('NDB_CUDA_PROFILER'):
+        torch.cuda.profiler.start()       # ncu --profile-from-start off: capture exactly the timed steps
     ev0.record()
     for _ in range(args.steps):
         runner.step()
     ev1.record()
+    if os.environ.get('NDB_CUDA_PROFILER'):
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
     barrier()
     launches = ops.LAUNCHES - launches0
     clk = clocks.stop()

@@ -1,14 +1,16 @@
 #!/bin/bash
-# ncu evidence for profiles/: (1) launch list with device time per kernel for one denoising step, (2) --set full capture
-# of the dominant kernel. usage: scripts/gpu_profile.sh <tag> [kernel-regex]
+# ncu evidence for profiles/: (1) launch list with device time per kernel for ONE denoising step (the timed step of an
+# eager bench run, bracketed by cudaProfilerStart/Stop), (2) --set full capture of the dominant kernel.
+# usage: scripts/gpu_profile.sh <tag> [kernel-regex]
 TAG=${1:-r01}
 KRE=${2:-conv_gemm_kernel}
 mkdir -p gpurun_out
 CMD="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --eager"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -20 gpurun_out/plain_$TAG.log; exit 1; }
-# the eager bench launches (3 warm-up + 1 timed + 2 profile passes) x ~607 kernels; skip to the timed step
-ncu --metrics gpu__time_duration.sum --clock-control none -s 1830 -c 620 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu1_$TAG.log 2>&1
+NDB_CUDA_PROFILER=1 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu1_$TAG.log 2>&1
 echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:$KRE -s 120 -c 3 -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu2_$TAG.log 2>&1
+NDB_CUDA_PROFILER=1 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:$KRE -s 4 -c 3 \
+    -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu2_$TAG.log 2>&1
 echo "full capture rc=$?"
-ls -la gpurun_out | tail
+ls -la gpurun_out | grep $TAG
