@@ -105,12 +105,17 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
     else { cq = 3 * h; ck = 3 * h + 1; cv = 3 * h + 2; }
 
     if (warp == 4) {
-        if (lane == 0) {
+        // The whole warp runs this warp-uniform loop and one elected lane issues the TMA / MMA instructions, so their
+        // descriptor operands stay in uniform registers (no per-instruction R2UR waterfall).
+        {
             const uint32_t tile_bytes = (uint32_t)dpc * kChunkBytes;
             auto load_tile = [&](uint8_t* dst, uint64_t* bar, int colblk, int row0) {
-                mbar_arrive_expect_tx(bar, tile_bytes);
-                for (int c = 0; c < dpc; ++c)
-                    tma_load_4d(dst + c * kChunkBytes, &qkv_map, bar, c * 64, colblk, row0, b);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(bar, tile_bytes);
+                    for (int c = 0; c < dpc; ++c)
+                        tma_load_4d(dst + c * kChunkBytes, &qkv_map, bar, c * 64, colblk, row0, b);
+                }
+                __syncwarp();
             };
             load_tile(sQ, q_full, cq, q0);
             load_tile(sK, &k_full[0], ck, 0);
@@ -124,11 +129,14 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
                 tc_fence_after();
                 {
                     const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + st * dpc * kChunkBytes);
-                    for (int i = 0; i < Dp / 16; ++i) {
-                        const uint32_t off = (i >> 2) * kChunkBytes + (i & 3) * 32;
-                        umma_f16(tmem_S, make_desc_k_sw128(qa + off), make_desc_k_sw128(ka + off), p.idesc_qk, i ? 1u : 0u);
+                    if (elect_one()) {
+                        for (int i = 0; i < Dp / 16; ++i) {
+                            const uint32_t off = (i >> 2) * kChunkBytes + (i & 3) * 32;
+                            umma_f16(tmem_S, make_desc_k_sw128(qa + off), make_desc_k_sw128(ka + off), p.idesc_qk, i ? 1u : 0u);
+                        }
+                        umma_commit(s_full);
                     }
-                    umma_commit(s_full);
+                    __syncwarp();
                 }
                 // ---- prefetch K/V for block j+1 ----
                 if (j + 1 < nkv) {
@@ -145,13 +153,16 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
                 tc_fence_after();
                 {
                     const uint32_t pa = smem_u32(sP), va = smem_u32(sV + st * dpc * kChunkBytes);
-                    for (int i = 0; i < kAttnBN / 16; ++i) {
-                        const uint64_t adesc = make_desc_k_sw128(pa + (i >> 2) * kChunkBytes + (i & 3) * 32);
-                        // V tile: rows = keys (K dim), 64 d-elements contiguous per row (MN-major), 16 keys = 2048 B
-                        const uint64_t bdesc = make_desc_mn_sw128(va + i * 2048, kChunkBytes);
-                        umma_f16(tmem_O, adesc, bdesc, p.idesc_pv, (j | i) ? 1u : 0u);
+                    if (elect_one()) {
+                        for (int i = 0; i < kAttnBN / 16; ++i) {
+                            const uint64_t adesc = make_desc_k_sw128(pa + (i >> 2) * kChunkBytes + (i & 3) * 32);
+                            // V tile: rows = keys (K dim), 64 d-elements contiguous per row (MN-major), 16 keys = 2048 B
+                            const uint64_t bdesc = make_desc_mn_sw128(va + i * 2048, kChunkBytes);
+                            umma_f16(tmem_O, adesc, bdesc, p.idesc_pv, (j | i) ? 1u : 0u);
+                        }
+                        umma_commit(pv_done);
                     }
-                    umma_commit(pv_done);
+                    __syncwarp();
                 }
                 if (j + 1 < nkv && p.kv_stages == 1) {
                     // single-buffered K/V (large head dims): reload only after both MMAs of block j retired

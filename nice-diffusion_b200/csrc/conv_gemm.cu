@@ -20,6 +20,7 @@
 #include "ptx.cuh"
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace ndb {
 
@@ -63,6 +64,8 @@ struct ConvArgs {
     float2* stat_parts;        // [N][stat_smax][cout] or nullptr
     int stat_smax;             // partial slots per image
     int tiles_per_group;       // tiles (m x n) covering one group of TN images
+    int b_rows;                // weight rows per CTA per stage (block_n, or block_n / 2 in CTA-pair mode)
+    int dbg;                   // bring-up switches (env NDB_DBG): 1 = no TMA traffic, 2 = no MMAs (results are garbage)
 };
 
 // Persistent CTAs own CONTIGUOUS tile ranges: CTA c processes tiles [tile_start(c), tile_start(c+1)). Tiles are ordered
@@ -87,14 +90,18 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     }
 }
 
-template <bool kStats>
+// k2 = CTA-pair mode (cta_group::2): two CTAs of a cluster compute adjacent 128-row M tiles of the same N tile with ONE
+// 256 x BLOCK_N tcgen05.mma issued by the leader; each CTA stages its own A tile and only HALF of the weight tile, which
+// halves the B traffic per SM (L2 -> smem writes and smem -> tensor-core reads) -- the single-CTA kernel is shared-memory
+// bandwidth bound at ~55 % tensor utilisation.
+template <bool kStats, bool k2>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment for SWIZZLE_128B tiles
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-    const int b_tile_bytes = p.block_n * 128;
+    const int b_tile_bytes = p.b_rows * 128;
     const int stage_bytes = kATileBytes + b_tile_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
     uint64_t* empty_bar = full_bar + kMaxStages;
@@ -110,9 +117,14 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-    const int tile_begin = tile_start(blockIdx.x, num_tiles, gridDim.x);
-    const int tile_end = tile_start(blockIdx.x + 1, num_tiles, gridDim.x);
+    // work items: (m tile, n tile) per CTA, or (pair of adjacent m tiles, n tile) per CTA pair
+    const uint32_t rank = k2 ? cluster_ctarank() : 0u;
+    const int worker = k2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_workers = k2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int num_tiles = (k2 ? ((p.num_m_tiles + 1) >> 1) : p.num_m_tiles) * p.num_n_tiles;
+    const int tile_begin = tile_start(worker, num_tiles, n_workers);
+    const int tile_end = tile_start(worker + 1, num_tiles, n_workers);
+    auto m_tile_of = [&](int item) { return k2 ? 2 * (item / p.num_n_tiles) + (int)rank : item / p.num_n_tiles; };
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.num_seg; ++s) {
@@ -120,39 +132,44 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             prefetch_tmap(&maps.b[s]);
         }
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], k2 ? 2 : 1);   // pair mode: both CTAs' producers arrive on the leader's barrier
             mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full_bar[s], 1);
-            mbar_init(&tmem_empty_bar[s], kEpiWarps);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty_bar[s], k2 ? 2 * kEpiWarps : kEpiWarps);  // one arrive per epilogue warp (of both CTAs)
             mbar_init(&stat_full_bar[s], kEpiWarps);
             mbar_init(&stat_empty_bar[s], 1);
         }
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_ptr_smem, p.tmem_cols);
-        tmem_relinquish();
+        if (k2) { tmem_alloc_2sm(tmem_ptr_smem, p.tmem_cols); tmem_relinquish_2sm(); }
+        else { tmem_alloc(tmem_ptr_smem, p.tmem_cols); tmem_relinquish(); }
     }
     tc_fence_before();
     __syncthreads();
+    if (k2) cluster_sync_all();    // the peer's barriers must be initialised before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // The WHOLE warp runs the (warp-uniform) loop and one elected lane issues: with the loop inside `if (lane == 0)`
+        // ptxas cannot prove the descriptor / coordinate operands uniform and wraps every UTMALDG / UTCHMMA in an
+        // ELECT + R2UR "waterfall" loop (~150 cycles per instruction, measured).
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = tile_begin; tile < tile_end; ++tile) {
                 const int n_tile = tile % p.num_n_tiles;
-                int m_tile = tile / p.num_n_tiles;
+                int m_tile = m_tile_of(tile);
                 const int tw_i = m_tile % p.tiles_w;
                 m_tile /= p.tiles_w;
                 const int th_i = m_tile % p.tiles_h;
                 const int tn_i = m_tile / p.tiles_h;
-                const int w0 = tw_i * p.TW, h0 = th_i * p.TH, n0 = tn_i * p.TN;
+                const int w0 = tw_i * p.TW, h0 = th_i * p.TH, n0 = tn_i * p.TN;   // n0 >= N for the odd leftover tile: all zero
+                const int b_row0 = n_tile * p.block_n + (int)rank * p.b_rows;
                 for (int s = 0; s < p.num_seg; ++s) {
                     const int taps = p.seg_taps[s];
                     const int chunks = p.seg_chunks[s];
@@ -163,9 +180,22 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                             mbar_wait(&empty_bar[stage], phase ^ 1);
                             uint8_t* sa = smem + stage * stage_bytes;
                             uint8_t* sb = sa + kATileBytes;
-                            mbar_arrive_expect_tx(&full_bar[stage], p.a_box_bytes + (uint32_t)b_tile_bytes);
-                            tma_load_4d(sa, &maps.a[s], &full_bar[stage], ch * kBlockK, w0 + dx, h0 + dy, n0);
-                            tma_load_3d(sb, &maps.b[s], &full_bar[stage], ch * kBlockK, n_tile * p.block_n, tap);
+                            if (elect_one()) {
+                                if (p.dbg & 1) {
+                                    if (k2) mbar_arrive_cluster(mapa_u32(smem_u32(&full_bar[stage]), 0));
+                                    else mbar_arrive(&full_bar[stage]);
+                                } else if (k2) {
+                                    const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);   // leader's barrier
+                                    mbar_arrive_expect_tx_cluster(fb, p.a_box_bytes + (uint32_t)b_tile_bytes);
+                                    tma_load_4d_2sm(sa, &maps.a[s], fb, ch * kBlockK, w0 + dx, h0 + dy, n0);
+                                    tma_load_3d_2sm(sb, &maps.b[s], fb, ch * kBlockK, b_row0, tap);
+                                } else {
+                                    mbar_arrive_expect_tx(&full_bar[stage], p.a_box_bytes + (uint32_t)b_tile_bytes);
+                                    tma_load_4d(sa, &maps.a[s], &full_bar[stage], ch * kBlockK, w0 + dx, h0 + dy, n0);
+                                    tma_load_3d(sb, &maps.b[s], &full_bar[stage], ch * kBlockK, b_row0, tap);
+                                }
+                            }
+                            __syncwarp();
                             if (++stage == p.stages) {
                                 stage = 0;
                                 phase ^= 1;
@@ -176,8 +206,8 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (pair mode: the leader CTA only) =====================
+        if (rank == 0) {
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -192,18 +222,29 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                     const uint32_t sa = smem_u32(smem + stage * stage_bytes);
                     const uint64_t adesc = make_desc_k_sw128(sa);
                     const uint64_t bdesc = make_desc_k_sw128(sa + kATileBytes);
+                    if (elect_one()) {
+                        if (!(p.dbg & 2)) {
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
-                        umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
+                            for (int k = 0; k < kBlockK / 16; ++k) {
+                                // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
+                                if (k2) umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
+                                else umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
+                            }
+                        }
+                        // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+                        if (k2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
                     }
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    __syncwarp();
                     if (++stage == p.stages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+                // accumulator complete -> epilogue (of both CTAs)
+                if (elect_one()) {
+                    if (k2) umma_commit_2sm(&tmem_full_bar[acc]); else umma_commit(&tmem_full_bar[acc]);
+                }
+                __syncwarp();
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1;
@@ -229,7 +270,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
         const float* __restrict__ resp = p.residual;
         for (int tile = tile_begin; tile < tile_end; ++tile) {
             const int n_tile = tile % p.num_n_tiles;
-            int m_tile = tile / p.num_n_tiles;
+            int m_tile = m_tile_of(tile);
             const int tw_i = m_tile % p.tiles_w;
             m_tile /= p.tiles_w;
             const int th_i = m_tile % p.tiles_h;
@@ -297,18 +338,21 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                     }
                 }
                 // (2) accumulator chunk out of TMEM (thread = row)
+                if (!(p.dbg & 32)) {
                 uint32_t racc[32];
                 tmem_ld32(t_row + ch * 32, racc);
                 tmem_ld_wait();
                 // (3) transpose through the padded per-warp tile
 #pragma unroll
                 for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __uint_as_float(racc[i]);
+                }
                 __syncwarp();
                 const float bias_v = (colok && p.bias != nullptr) ? __ldg(p.bias + col) : 0.f;
                 // (4) bias + residual, then store with lanes along channels
 #pragma unroll
                 for (int r = 0; r < 32; ++r) res[r] = stg[r * 33 + lane] + bias_v + res[r];
-                if (p.out_kind == NDB_OUT_F32_NHWC) {
+                if (p.dbg & 4) {
+                } else if (p.out_kind == NDB_OUT_F32_NHWC) {
                     float* ob = reinterpret_cast<float*>(p.out) + col;
 #pragma unroll
                     for (int r = 0; r < 32; ++r)
@@ -328,7 +372,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                     for (int r = 0; r < 32; ++r)
                         if ((okmask >> r) & 1u) ob[row_out[r]] = res[r];
                 }
-                if (kStats) {
+                if (kStats && !(p.dbg & 16)) {
                     // column sums over this warp's 32 rows come for free in the transposed view (fixed order)
                     float cs = 0.f, css = 0.f;
 #pragma unroll
@@ -343,7 +387,10 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) {
+                if (k2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));   // the leader's MMA thread waits
+                else mbar_arrive(&tmem_empty_bar[acc]);
+            }
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;
@@ -364,9 +411,18 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
         uint32_t stat_phase = 0;
         const int warps_per_slot = 4 / p.TN;                  // TN in {1, 2, 4} (host-checked)
         int cur_group = -1;
+        // group of images a work item belongs to, and the slot this CTA writes for that group (see stats_slots())
+        auto group_of = [&](int item) {
+            if (!k2) return item / p.tiles_per_group;
+            if (p.TN == 1) return item / (p.tiles_per_group >> 1);      // both CTAs of a pair sweep the same images
+            return m_tile_of(item);                                      // one tile == one group of TN images
+        };
         auto flush = [&](int group) {
-            const int first_cta = cta_of_tile(group * p.tiles_per_group, num_tiles, gridDim.x);
-            const int slot_idx = blockIdx.x - first_cta;
+            int slot_idx;
+            if (!k2) slot_idx = worker - cta_of_tile(group * p.tiles_per_group, num_tiles, n_workers);
+            else if (p.TN == 1)
+                slot_idx = 2 * (worker - cta_of_tile(group * (p.tiles_per_group >> 1), num_tiles, n_workers)) + (int)rank;
+            else slot_idx = worker - cta_of_tile((group >> 1) * p.num_n_tiles, num_tiles, n_workers);
             for (int sl = 0; sl < p.TN; ++sl) {
                 const int img = group * p.TN + sl;
                 if (img >= p.N) break;
@@ -376,7 +432,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
         };
         for (int tile = tile_begin; tile < tile_end; ++tile) {
             const int n_tile = tile % p.num_n_tiles;
-            const int group = tile / p.tiles_per_group;
+            const int group = group_of(tile);
             const int col0 = n_tile * p.block_n;
             if (group != cur_group) {
                 if (cur_group >= 0) flush(cur_group);
@@ -408,9 +464,10 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
 
     tc_fence_before();
     __syncthreads();
+    if (k2) cluster_sync_all();    // the peer may still be reading this CTA's half of the weights / signalling its barriers
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, p.tmem_cols);
+        if (k2) tmem_dealloc_2sm(tmem_base, p.tmem_cols); else tmem_dealloc(tmem_base, p.tmem_cols);
     }
 }
 
@@ -441,13 +498,19 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, uint16_t* __rest
 }
 
 // Number of partial slots an image needs (max over image groups of the CTAs sweeping its tiles) and, optionally, the
-// per-image slot counts.
-static int stats_slots(int groups, int tiles_per_group, int T, int G, int32_t* counts, int N, int TN) {
+// per-image slot counts. Mirrors the device-side group_of()/flush() logic of the statistics warp.
+//   single CTA : work item = tile; a group of TN images spans `tiles_per_group` items; one slot per CTA
+//   pair, TN==1: work item = pair of m tiles x n tile; a group spans tiles_per_group/2 items; two slots per pair
+//   pair, TN>1 : each tile is its own group; the pair's items (all n tiles) give one slot per pair for each of its tiles
+static int stats_slots(int groups, int tiles_per_group, int num_n_tiles, int TN, bool pair, int T, int G, int32_t* counts,
+                       int N) {
     int smax = 1;
     for (int g = 0; g < groups; ++g) {
-        const int c0 = cta_of_tile(g * tiles_per_group, T, G);
-        const int c1 = cta_of_tile((g + 1) * tiles_per_group - 1, T, G);
-        const int n = c1 - c0 + 1;
+        int first_item, last_item, mult;
+        if (!pair) { first_item = g * tiles_per_group; last_item = (g + 1) * tiles_per_group - 1; mult = 1; }
+        else if (TN == 1) { first_item = g * (tiles_per_group / 2); last_item = (g + 1) * (tiles_per_group / 2) - 1; mult = 2; }
+        else { first_item = (g / 2) * num_n_tiles; last_item = (g / 2 + 1) * num_n_tiles - 1; mult = 1; }
+        const int n = mult * (cta_of_tile(last_item, T, G) - cta_of_tile(first_item, T, G) + 1);
         if (n > smax) smax = n;
         if (counts != nullptr)
             for (int sl = 0; sl < TN; ++sl)
@@ -485,6 +548,38 @@ static int pick_block_n(int cout_pad) {
     for (int bn = 256; bn >= 16; bn -= 16)
         if (cout_pad % bn == 0) return bn;
     return 0;
+}
+
+// CTA-pair mode is used whenever two M tiles exist and, when statistics are requested, both CTAs of a pair always sweep
+// the same images (even number of m tiles per image) or each tile holds whole images.
+static bool use_pair_mode(const ConvGeom& g, int block_n, bool want_stats) {
+    static int disabled = -1;
+    if (disabled < 0) disabled = std::getenv("NDB_DISABLE_2CTA") != nullptr ? 1 : 0;
+    if (disabled) return false;
+    if (g.num_m_tiles < 2 || (block_n / 2) % 8 != 0) return false;
+    if (want_stats && g.TN == 1 && ((g.tiles_w * g.tiles_h) % 2 != 0)) return false;
+    return true;
+}
+
+struct WorkGeom {
+    bool pair;
+    int items, workers, grid;
+};
+
+static WorkGeom work_geom(const ConvGeom& g, int num_n_tiles, int block_n, bool want_stats) {
+    WorkGeom w;
+    w.pair = use_pair_mode(g, block_n, want_stats);
+    if (w.pair) {
+        w.items = ((g.num_m_tiles + 1) / 2) * num_n_tiles;
+        const int max_workers = num_sms() / 2;
+        w.workers = w.items < max_workers ? w.items : max_workers;
+        w.grid = 2 * w.workers;
+    } else {
+        w.items = g.num_m_tiles * num_n_tiles;
+        w.workers = w.items < num_sms() ? w.items : num_sms();
+        w.grid = w.workers;
+    }
+    return w;
 }
 
 }  // namespace ndb
@@ -548,13 +643,20 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     a.fmt = prm->operand_format;
     a.stat_parts = reinterpret_cast<float2*>(prm->stat_parts);
     a.tiles_per_group = a.tiles_w * a.tiles_h * a.num_n_tiles;
-    const int num_tiles_all = a.num_m_tiles * a.num_n_tiles;
-    const int grid_all = num_tiles_all < num_sms() ? num_tiles_all : num_sms();
+    const ConvGeom cg = conv_geom(prm->N, prm->H, prm->W);
+    const WorkGeom wg = work_geom(cg, a.num_n_tiles, a.block_n, prm->stat_parts != nullptr);
+    a.b_rows = wg.pair ? a.block_n / 2 : a.block_n;
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = std::getenv("NDB_DBG"); dbg = e ? std::atoi(e) : 0; }
+        a.dbg = dbg;
+    }
+    if (wg.pair) a.idesc = make_idesc_f16(2 * kBlockM, a.block_n, prm->operand_format, 0, 0);
     if (prm->stat_parts != nullptr) {
         NDB_CHECK_ARG(prm->out_kind != NDB_OUT_F32_NCHW);
         // image slots inside a tile must be whole warps
         NDB_CHECK_ARG(a.TN == 1 || ((a.TN == 2 || a.TN == 4) && (prm->H * prm->W) % 32 == 0 && a.TN * prm->H * prm->W == kBlockM));
-        a.stat_smax = stats_slots(a.tiles_n, a.tiles_per_group, num_tiles_all, grid_all, nullptr, 0, 0);
+        a.stat_smax = stats_slots(a.tiles_n, a.tiles_per_group, a.num_n_tiles, a.TN, wg.pair, wg.items, wg.workers, nullptr, 0);
         NDB_CHECK_ARG(prm->stat_smax == a.stat_smax);
     }
 
@@ -579,13 +681,13 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
         {
             uint64_t dims[3] = {(uint64_t)sg.C, (uint64_t)prm->cout_pad, (uint64_t)sg.taps};
             uint64_t strides[2] = {(uint64_t)sg.C * 2, (uint64_t)prm->cout_pad * sg.C * 2};
-            uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)a.block_n, 1u};
+            uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)a.b_rows, 1u};
             int rc = encode_tmap_16bit(&maps.b[s], sg.weight, 3, dims, strides, box);
             if (rc != NDB_OK) return rc;
         }
     }
 
-    const int stage_bytes = kATileBytes + a.block_n * 128;
+    const int stage_bytes = kATileBytes + a.b_rows * 128;
     const int epi_bytes = kEpiWarps * (kStageFloats * (int)sizeof(float) + 64 * (int)sizeof(long long)) +
                           2 * 4 * a.block_n * (int)sizeof(float2) +
                           (prm->stat_parts ? a.TN * prm->cout * (int)sizeof(float2) : 0);
@@ -599,17 +701,35 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
 
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return launch_status("cudaFuncSetAttribute(conv_gemm_kernel)");
         attr_set = true;
     }
-    const int grid = grid_all;
-    if (a.stat_parts != nullptr)
-        conv_gemm_kernel<true><<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(maps, a);
-    else
-        conv_gemm_kernel<false><<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(maps, a);
+    const bool stats = a.stat_parts != nullptr;
+    if (!wg.pair) {
+        if (stats) conv_gemm_kernel<true, false><<<wg.grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(maps, a);
+        else conv_gemm_kernel<false, false><<<wg.grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(maps, a);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(wg.grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = stats ? cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, true>, maps, a)
+                              : cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false, true>, maps, a);
+        if (e != cudaSuccess) {
+            std::fprintf(stderr, "[ndb200] cluster launch of conv_gemm_kernel failed: %s\n", cudaGetErrorString(e));
+            return NDB_ERR_CUDA;
+        }
+    }
     return launch_status("ndb_conv_gemm");
 }
 
@@ -622,9 +742,8 @@ extern "C" int ndb_conv_stats_layout(int N, int H, int W, int cout_pad, int bloc
     const int bn = block_n > 0 ? block_n : pick_block_n(cout_pad);
     if (bn <= 0 || cout_pad % bn != 0) return NDB_ERR_INVALID;
     const int n_tiles = cout_pad / bn;
-    const int T = g.num_m_tiles * n_tiles;
-    const int G = T < num_sms() ? T : num_sms();
-    return stats_slots(g.tiles_n, g.tiles_w * g.tiles_h * n_tiles, T, G, counts, N, g.TN);
+    const WorkGeom w = work_geom(g, n_tiles, bn, true);
+    return stats_slots(g.tiles_n, g.tiles_w * g.tiles_h * n_tiles, n_tiles, g.TN, w.pair, w.items, w.workers, counts, N);
 }
 
 // 1 when the epilogue can produce per-image channel statistics for this geometry (else use ndb_gn_stats).
