@@ -133,6 +133,9 @@ typedef struct {
     int32_t resample;                  /* NDB_RESAMPLE_* applied after the activation */
     void* out;                         /* 16-bit NHWC [N,H',W',C0+C1] */
     void* raw16;                       /* optional 16-bit copy of the un-normalised (resampled) input, same shape */
+    float* pool32;                     /* optional, DOWN2 only: fp32 2x2 mean of the raw input [N,H/2,W/2,C] -- the
+                                          x_resample operand of a down ResBlock (model.py:193), read back by the conv
+                                          epilogue as a plain residual */
     int32_t operand_format;
     float eps;
 } ndb_gn_apply_params;

@@ -119,6 +119,7 @@ struct GnApplyArgs {
     const float* pre_add; int ld_pre;
     int silu, resample;
     uint16_t* out; uint16_t* raw16;
+    float* pool32;   // DOWN2 only: fp32 2x2 mean of the raw input (the x_resample operand of a down ResBlock)
     float eps;
     int pix_per_block, threads_per_row, rows_per_block;
 };
@@ -296,6 +297,15 @@ gn_apply_kernel(const GnApplyArgs p) {
                 if (RAW)
                     *reinterpret_cast<uint4*>(rawq + o) = make_uint4(pack2h<FMT>(raw[0], raw[1]), pack2h<FMT>(raw[2], raw[3]),
                                                                      pack2h<FMT>(raw[4], raw[5]), pack2h<FMT>(raw[6], raw[7]));
+                if (p.pool32 != nullptr) {
+                    // same association as F.avg_pool2d: sum of the four taps, then * 0.25 (pre_add is not part of x)
+                    float pl[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) pl[k] = (xv[0][k] + xv[1][k] + xv[2][k] + xv[3][k]) * 0.25f;
+                    float* pp = p.pool32 + ((size_t)n * npix + po) * C + c;
+                    *reinterpret_cast<float4*>(pp) = make_float4(pl[0], pl[1], pl[2], pl[3]);
+                    *reinterpret_cast<float4*>(pp + 4) = make_float4(pl[4], pl[5], pl[6], pl[7]);
+                }
             }
         } else {
             for (int po = p_begin + r; po < p_end; po += U * p.rows_per_block) {
@@ -425,6 +435,8 @@ extern "C" int ndb_gn_apply(const ndb_gn_apply_params* q, void* stream) {
     a.pre_add = q->pre_add; a.ld_pre = q->ld_pre;
     a.silu = q->silu; a.resample = q->resample;
     a.out = (uint16_t*)q->out; a.raw16 = (uint16_t*)q->raw16;
+    a.pool32 = q->pool32;
+    NDB_CHECK_ARG(q->pool32 == nullptr || q->resample == NDB_RESAMPLE_DOWN2);
     a.eps = q->eps;
     const int V8 = C / 8;
     a.threads_per_row = V8 < kGnThreads ? V8 : kGnThreads;

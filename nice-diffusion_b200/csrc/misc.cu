@@ -28,6 +28,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ------------------------------------------------------------------------------------------------------
 constexpr int kEmbMaxMcPerLane = 16;   // model_channels <= 512
 constexpr int kEmbMaxEPerLane = 64;    // 4 * model_channels <= 2048
+constexpr int kEmbBatchPerBlock = 4;   // samples per CTA (grid.y covers the batch)
 
 __global__ void __launch_bounds__(256)
 embed_l1_kernel(const float* __restrict__ t, const float* __restrict__ freqs, int B, int mc,
@@ -45,7 +46,8 @@ embed_l1_kernel(const float* __restrict__ t, const float* __restrict__ freqs, in
         f[i] = (k < 2 * half) ? __ldg(freqs + (k < half ? k : k - half)) : 0.f;
     }
     const float bj = b0[j];
-    for (int b = 0; b < B; ++b) {
+    const int b_lo = blockIdx.y * kEmbBatchPerBlock, b_hi = min(B, b_lo + kEmbBatchPerBlock);
+    for (int b = b_lo; b < b_hi; ++b) {
         const float tb = t[b];
         float acc = 0.f;
 #pragma unroll
@@ -78,7 +80,8 @@ embed_l2_kernel(const float* __restrict__ h1, const int64_t* __restrict__ y, int
         w[i] = (k < E) ? __ldg(w2 + (size_t)j * E + k) : 0.f;
     }
     const float bj = b2[j];
-    for (int b = 0; b < B; ++b) {
+    const int b_lo = blockIdx.y * kEmbBatchPerBlock, b_hi = min(B, b_lo + kEmbBatchPerBlock);
+    for (int b = b_lo; b < b_hi; ++b) {
         const float* hb = h1 + (size_t)b * E;
         float acc = 0.f;
 #pragma unroll
@@ -99,46 +102,78 @@ embed_l2_kernel(const float* __restrict__ h1, const int64_t* __restrict__ y, int
 // ------------------------------------------------------------------------------------------------------
 // stem conv 3x3 pad 1, NCHW fp32 in (Cin <= 4) -> NHWC fp32 out
 // ------------------------------------------------------------------------------------------------------
+// Block = 64 consecutive pixels x 4 channel groups. A thread owns one pixel and CPT = Cout/4 consecutive output channels:
+// it reads its Cin*9 input taps once (L1-resident, shared with its neighbours), keeps the CPT accumulators in registers
+// and streams the weights [tap][cout] from shared memory as warp-wide broadcasts (one LDS.128 feeds four FMAs per lane).
+template <int CIN, int CPT>
 __global__ void __launch_bounds__(256)
 stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                 float* __restrict__ out, int N, int Cin, int H, int W, int Cout) {
-    extern __shared__ float sw[];  // [Cin*9][Cout] transposed weights, then bias[Cout]
-    const int K = Cin * 9;
-    for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
-        const int co = i % Cout, k = i / Cout;
+                 float* __restrict__ out, int N, int H, int W) {
+    constexpr int K = CIN * 9;
+    constexpr int COUT = 4 * CPT;
+    __shared__ __align__(16) float sw[K * COUT];
+    for (int i = threadIdx.x; i < K * COUT; i += blockDim.x) {
+        const int co = i % COUT, k = i / COUT;
         sw[i] = w[(size_t)co * K + k];  // OIHW: k = ci*9 + ky*3 + kx
     }
-    float* sb = sw + K * Cout;
-    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
     __syncthreads();
-    const int Q = Cout >> 2;
-    const long long total = (long long)N * H * W * Q;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int q = (int)(i % Q);
-        long long pix = i / Q;
-        const int wx = (int)(pix % W);
-        const int hy = (int)((pix / W) % H);
-        const int n = (int)(pix / ((long long)W * H));
-        float4 acc = *reinterpret_cast<const float4*>(sb + 4 * q);
-        for (int ci = 0; ci < Cin; ++ci) {
-            const float* xp = x + ((size_t)n * Cin + ci) * H * W;
+    const int HW = H * W;
+    const int total = N * HW;
+    const int cg = threadIdx.x >> 6;           // channel group 0..3 (warp-uniform)
+    const int pl = threadIdx.x & 63;
+    for (int pix0 = blockIdx.x * 64; pix0 < total; pix0 += gridDim.x * 64) {
+        const int pix = pix0 + pl;
+        if (pix >= total) continue;
+        const int n = pix / HW;
+        const int rem = pix - n * HW;
+        const int hy = rem / W, wx = rem - hy * W;
+        float v[K];
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+            const float* xp = x + ((size_t)n * CIN + ci) * HW;
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
                 const int yy = hy + ky - 1;
-                if (yy < 0 || yy >= H) continue;
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
                     const int xx = wx + kx - 1;
-                    if (xx < 0 || xx >= W) continue;
-                    const float v = __ldg(xp + (size_t)yy * W + xx);
-                    const float4 w4 = *reinterpret_cast<const float4*>(sw + (ci * 9 + ky * 3 + kx) * Cout + 4 * q);
-                    acc.x += v * w4.x; acc.y += v * w4.y; acc.z += v * w4.z; acc.w += v * w4.w;
+                    v[ci * 9 + ky * 3 + kx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xp + yy * W + xx) : 0.f;
                 }
             }
         }
-        *reinterpret_cast<float4*>(out + pix * Cout + 4 * q) = acc;
+        float acc[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) acc[j] = bias ? __ldg(bias + cg * CPT + j) : 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float4* wrow = reinterpret_cast<const float4*>(sw + k * COUT + cg * CPT);
+#pragma unroll
+            for (int j = 0; j < CPT / 4; ++j) {
+                const float4 w4 = wrow[j];
+                acc[4 * j] += v[k] * w4.x; acc[4 * j + 1] += v[k] * w4.y;
+                acc[4 * j + 2] += v[k] * w4.z; acc[4 * j + 3] += v[k] * w4.w;
+            }
+        }
+        float4* o = reinterpret_cast<float4*>(out + (size_t)pix * COUT + cg * CPT);
+#pragma unroll
+        for (int j = 0; j < CPT / 4; ++j) o[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
     }
+}
+
+template <int CIN>
+static int launch_stem(const float* x, const float* w, const float* bias, float* out, int N, int H, int W, int Cout,
+                       cudaStream_t st) {
+    long long blocks = ((long long)N * H * W + 63) / 64;
+    const long long cap = (long long)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    switch (Cout) {
+        case 64: stem_conv_kernel<CIN, 16><<<(int)blocks, 256, 0, st>>>(x, w, bias, out, N, H, W); break;
+        case 128: stem_conv_kernel<CIN, 32><<<(int)blocks, 256, 0, st>>>(x, w, bias, out, N, H, W); break;
+        case 192: stem_conv_kernel<CIN, 48><<<(int)blocks, 256, 0, st>>>(x, w, bias, out, N, H, W); break;
+        case 256: stem_conv_kernel<CIN, 64><<<(int)blocks, 256, 0, st>>>(x, w, bias, out, N, H, W); break;
+        default: return NDB_ERR_UNSUPPORTED;
+    }
+    return NDB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -245,7 +280,7 @@ extern "C" int ndb_embed(const float* t, const int64_t* y, const float* freqs, i
     NDB_CHECK_ARG(mc % 4 == 0 && mc <= 32 * kEmbMaxMcPerLane);
     NDB_CHECK_ARG((y == nullptr) == (class_emb == nullptr));
     const int E = 4 * mc;
-    const int grid = (E + 7) / 8;
+    const dim3 grid((E + 7) / 8, (B + kEmbBatchPerBlock - 1) / kEmbBatchPerBlock);
     embed_l1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t, freqs, B, mc, w0, b0, h1_scratch);
     embed_l2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h1_scratch, y, B, E, w2, b2, class_emb, emb_out,
                                                            (uint16_t*)act_out, operand_format);
@@ -255,17 +290,19 @@ extern "C" int ndb_embed(const float* t, const int64_t* y, const float* freqs, i
 extern "C" int ndb_stem_conv(const float* x_nchw, const float* w_oihw, const float* bias, float* out_nhwc, int N,
                              int Cin, int H, int W, int Cout, void* stream) {
     NDB_CHECK_ARG(x_nchw && w_oihw && out_nhwc);
-    NDB_CHECK_ARG(Cin >= 1 && Cin <= 16 && Cout % 4 == 0);
-    const size_t smem = ((size_t)Cin * 9 * Cout + Cout) * sizeof(float);
-    NDB_CHECK_ARG(smem <= 200 * 1024);
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr = true;
+    NDB_CHECK_ARG(Cin >= 1 && Cin <= 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    switch (Cin) {
+        case 1: rc = launch_stem<1>(x_nchw, w_oihw, bias, out_nhwc, N, H, W, Cout, st); break;
+        case 2: rc = launch_stem<2>(x_nchw, w_oihw, bias, out_nhwc, N, H, W, Cout, st); break;
+        case 3: rc = launch_stem<3>(x_nchw, w_oihw, bias, out_nhwc, N, H, W, Cout, st); break;
+        default: rc = launch_stem<4>(x_nchw, w_oihw, bias, out_nhwc, N, H, W, Cout, st); break;
     }
-    const long long work = (long long)N * H * W * (Cout / 4);
-    int grid = grid_for(work, 256);
-    stem_conv_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x_nchw, w_oihw, bias, out_nhwc, N, Cin, H, W, Cout);
+    if (rc != NDB_OK) {
+        std::fprintf(stderr, "[ndb200] ndb_stem_conv: unsupported width %d (model_channels must be 64, 128, 192 or 256)\n", Cout);
+        return rc;
+    }
     return launch_status("ndb_stem_conv");
 }
 

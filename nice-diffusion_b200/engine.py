@@ -299,8 +299,11 @@ class UNetEngine:
         x1 = skip.t if skip is not None else None
         s1 = skip.stats if skip is not None else None
 
+        # down blocks with an identity skip: the apply kernel (which reads x anyway) also leaves avg_pool2d(x) in fp32,
+        # so the out_conv epilogue adds it as a plain residual instead of gathering four taps per element
+        pooled = pool.get((B, Ho, Wo, Cin), torch.float32) if (rb.mode == 'down' and not conv_skip) else None
         self.steps.append(lambda: ops.gn_apply(x.t, x.stats, g1, b1, x1=x1, stats1=s1, silu=True, resample=mode,
-                                               out=a1, raw16=raw, fmt=fmt, eps=eps1))
+                                               out=a1, raw16=raw, fmt=fmt, eps=eps1, pool32=pooled))
         h = self._conv([(a1, w_in)], Ho, Wo, Cout, want_stats=True, bias=bias_in)
         self.steps.append(lambda: ops.gn_apply(h.t, h.stats, g2, b2, scale=scale, shift=shift, pre_add=pre, silu=True,
                                                out=a2, fmt=fmt, eps=eps2))
@@ -308,10 +311,10 @@ class UNetEngine:
             # 1x1 (or 3x3 when use_conv) skip conv as an extra K range of the same GEMM
             out = self._conv([(a2, w_out), (raw, w_skip)], Ho, Wo, Cout, want_stats=True, bias=bias_out)
         else:
-            rmode = {'same': L.RES_SAME, 'up': L.RES_UP2, 'down': L.RES_DOWN2}[rb.mode]
-            out = self._conv([(a2, w_out)], Ho, Wo, Cout, want_stats=True, bias=bias_out, residual=x.t,
-                             residual_mode=rmode)
-        for t in (a1, raw, a2):
+            rmode = {'same': L.RES_SAME, 'up': L.RES_UP2, 'down': L.RES_SAME}[rb.mode]
+            out = self._conv([(a2, w_out)], Ho, Wo, Cout, want_stats=True, bias=bias_out,
+                             residual=pooled if pooled is not None else x.t, residual_mode=rmode)
+        for t in (a1, raw, a2, pooled):
             if t is not None:
                 pool.put(t)
         self._release(h)

@@ -178,8 +178,9 @@ def test_groupnorm_apply(cuda_dev, N, H, W, C0, C1, resample):
         st0, st1 = ops.gn_stats(nhwc(x0), nhwc(x1))
     else:
         st0, st1 = ops.gn_stats(nhwc(x0)), None
+    pool32 = torch.empty((N, H // 2, W // 2, C), device=cuda_dev) if resample == 2 else None
     out, raw = ops.gn_apply(nhwc(x0), st0, gamma, beta, x1=nhwc(x1) if C1 else None, stats1=st1, scale=scale,
-                            shift=shift, silu=True, resample=resample, want_raw16=True)
+                            shift=shift, silu=True, resample=resample, want_raw16=True, pool32=pool32)
     ref = F.silu(F.group_norm(xin, 32, gamma, beta, eps=1e-5) * (1 + scale[:, :, None, None]) + shift[:, :, None, None])
     rraw = xin
     if resample == 1:
@@ -188,6 +189,8 @@ def test_groupnorm_apply(cuda_dev, N, H, W, C0, C1, resample):
         ref, rraw = F.avg_pool2d(ref, 2), F.avg_pool2d(xin, 2)
     assert rel_err(out.permute(0, 3, 1, 2), ref) < 1.5e-3   # fp16 output rounding
     assert rel_err(raw.permute(0, 3, 1, 2), rraw) < 1.5e-3
+    if pool32 is not None:
+        assert rel_err(pool32.permute(0, 3, 1, 2), F.avg_pool2d(xin, 2)) < 1e-6
     # statistics themselves: per-channel fp64 sums against torch, and run-to-run bit-exactness
     xs = x0.double().flatten(2)
     tot = ops.stats_totals(st0)
