@@ -133,6 +133,8 @@ typedef struct {
     int32_t resample;                  /* NDB_RESAMPLE_* applied after the activation */
     void* out;                         /* 16-bit NHWC [N,H',W',C0+C1] */
     void* raw16;                       /* optional 16-bit copy of the un-normalised (resampled) input, same shape */
+    int32_t x0_is16;                   /* x0 is a 16-bit tensor (operand_format) instead of fp32: the `h` between the two
+                                          convs of a ResBlock; single source, no resampling, no raw copy */
     float* pool32;                     /* optional, DOWN2 only: fp32 2x2 mean of the raw input [N,H/2,W/2,C] -- the
                                           x_resample operand of a down ResBlock (model.py:193), read back by the conv
                                           epilogue as a plain residual */

@@ -306,7 +306,48 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             tc_fence_after();
             if (kStats) mbar_wait(&stat_empty_bar[stat_buf], stat_phase ^ 1);   // part_smem buffer free
             const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * p.acc_stride;
-            for (int ch = ch_begin; ch < ch_end; ++ch) {
+            // ---- fast path (no statistics, no residual, NHWC output: qkv / step-embedding GEMMs): the thread that owns
+            //      accumulator row r writes its 32 channels straight out as 16-byte vectors -- no transposition ----
+            const bool direct = !kStats && p.res_mode == NDB_RES_NONE && p.out_kind != NDB_OUT_F32_NCHW && (p.cout & 7) == 0;
+            for (int ch = ch_begin; direct && ch < ch_end; ++ch) {
+                uint32_t racc[32];
+                tmem_ld32(t_row + ch * 32, racc);
+                tmem_ld_wait();
+                const int c0 = col0 + ch * 32;
+                if (!valid || c0 >= p.cout || ch * 32 >= p.block_n) continue;
+                const int ncols = min(32, min(p.cout - c0, p.block_n - ch * 32));     // multiple of 8
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.bias != nullptr && i < ncols) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i));
+                    v[i] = __uint_as_float(racc[i]) + b4.x; v[i + 1] = __uint_as_float(racc[i + 1]) + b4.y;
+                    v[i + 2] = __uint_as_float(racc[i + 2]) + b4.z; v[i + 3] = __uint_as_float(racc[i + 3]) + b4.w;
+                }
+                if (p.out_kind == NDB_OUT_F32_NHWC) {
+                    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + c0);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (4 * i < ncols) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                } else {
+                    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + out_off + c0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (8 * i < ncols) {
+                            uint4 w4;
+                            if (p.fmt == 0) {
+                                w4 = make_uint4(pack2<0>(v[8 * i], v[8 * i + 1]), pack2<0>(v[8 * i + 2], v[8 * i + 3]),
+                                                pack2<0>(v[8 * i + 4], v[8 * i + 5]), pack2<0>(v[8 * i + 6], v[8 * i + 7]));
+                            } else {
+                                w4 = make_uint4(pack2<1>(v[8 * i], v[8 * i + 1]), pack2<1>(v[8 * i + 2], v[8 * i + 3]),
+                                                pack2<1>(v[8 * i + 4], v[8 * i + 5]), pack2<1>(v[8 * i + 6], v[8 * i + 7]));
+                            }
+                            o[i] = w4;
+                        }
+                    }
+                }
+            }
+            for (int ch = ch_begin; !direct && ch < ch_end; ++ch) {
                 const int cl = ch * 32 + lane;             // column inside the tile owned by this lane (transposed view)
                 const int col = col0 + cl;
                 const bool colok = (cl < p.block_n) && (col < p.cout);

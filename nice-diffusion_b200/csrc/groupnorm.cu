@@ -119,6 +119,7 @@ struct GnApplyArgs {
     const float* pre_add; int ld_pre;
     int silu, resample;
     uint16_t* out; uint16_t* raw16;
+    int x0_is16;     // x0 holds 16-bit values (operand_format) instead of fp32
     float* pool32;   // DOWN2 only: fp32 2x2 mean of the raw input (the x_resample operand of a down ResBlock)
     float eps;
     int pix_per_block, threads_per_row, rows_per_block;
@@ -131,7 +132,8 @@ struct GnApplyArgs {
 //   2. all threads fold mean / rstd / gamma / beta / AdaGN (1+scale), shift / pre-add into one per-channel FMA
 //      (a_c, b_c) -> smem;
 //   3. stream: y = SiLU(a x + b) (+ resample) -> 16-bit operand, 16-byte stores, four pixels in flight per thread.
-template <int FMT, int RESAMPLE, bool SILU, bool RAW>
+// IN16: x0 is a 16-bit tensor (the fp16 `h` between the two convs of a ResBlock) instead of fp32.
+template <int FMT, int RESAMPLE, bool SILU, bool RAW, bool IN16>
 __global__ void __launch_bounds__(kGnThreads, 3)
 gn_apply_kernel(const GnApplyArgs p) {
     extern __shared__ float sm_ab[];   // a[C], b[C], pre[C]
@@ -152,10 +154,37 @@ gn_apply_kernel(const GnApplyArgs p) {
     if (p_end > npix) p_end = npix;
     constexpr int U = 4;
 
+    // element pointer of channel c of sample n (in units of the source element: 4 bytes, or 2 when IN16)
     auto src_of = [&](int c, const float*& src, int& ldc) {
         int cc;
         if (c < p.C0) { src = p.x0; ldc = p.C0; cc = c; } else { src = p.x1; ldc = p.C1; cc = c - p.C0; }
-        src += (size_t)n * p.H * p.W * ldc + cc;
+        if (IN16) src = reinterpret_cast<const float*>(reinterpret_cast<const uint16_t*>(src) + (size_t)n * p.H * p.W * ldc + cc);
+        else src += (size_t)n * p.H * p.W * ldc + cc;
+    };
+    // eight consecutive channels of pixel `pix` -> two 16-byte registers (fp32) or one (16-bit)
+    auto load8 = [&](const float* src, int ldc, int pix, uint4& a, uint4& b) {
+        if (IN16) {
+            a = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(src) + (size_t)pix * ldc));
+        } else {
+            const float* px = src + (size_t)pix * ldc;
+            a = __ldg(reinterpret_cast<const uint4*>(px));
+            b = __ldg(reinterpret_cast<const uint4*>(px + 4));
+        }
+    };
+    auto unpack8 = [&](const uint4& a, const uint4& b, float* xv) {
+        if (IN16) {
+            const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float2 f;
+                if (FMT == 0) f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+                else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+                xv[2 * i] = f.x; xv[2 * i + 1] = f.y;
+            }
+        } else {
+            xv[0] = __uint_as_float(a.x); xv[1] = __uint_as_float(a.y); xv[2] = __uint_as_float(a.z); xv[3] = __uint_as_float(a.w);
+            xv[4] = __uint_as_float(b.x); xv[5] = __uint_as_float(b.y); xv[6] = __uint_as_float(b.z); xv[7] = __uint_as_float(b.w);
+        }
     };
     auto in_pixel = [&](int pu) {
         if (RESAMPLE == NDB_RESAMPLE_UP2) {
@@ -166,18 +195,14 @@ gn_apply_kernel(const GnApplyArgs p) {
     };
 
     // ---- 0. first trip's data ----
-    float4 lo[U], hi[U];
+    uint4 lo[U], hi[U];
     if (RESAMPLE != NDB_RESAMPLE_DOWN2 && worker) {
         const float* src; int ldc;
         src_of(tv << 3, src, ldc);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int pu = p_begin + r + u * p.rows_per_block;
-            if (pu < p_end) {
-                const float* px = src + (size_t)in_pixel(pu) * ldc;
-                lo[u] = __ldg(reinterpret_cast<const float4*>(px));
-                hi[u] = __ldg(reinterpret_cast<const float4*>(px + 4));
-            }
+            if (pu < p_end) load8(src, ldc, in_pixel(pu), lo[u], hi[u]);
         }
     }
 
@@ -313,18 +338,15 @@ gn_apply_kernel(const GnApplyArgs p) {
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         const int pu = po + u * p.rows_per_block;
-                        if (pu < p_end) {
-                            const float* px = srcp + (size_t)in_pixel(pu) * ldc;
-                            lo[u] = __ldg(reinterpret_cast<const float4*>(px));
-                            hi[u] = __ldg(reinterpret_cast<const float4*>(px + 4));
-                        }
+                        if (pu < p_end) load8(srcp, ldc, in_pixel(pu), lo[u], hi[u]);
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int pu = po + u * p.rows_per_block;
                     if (pu < p_end) {
-                        const float xv[8] = {lo[u].x, lo[u].y, lo[u].z, lo[u].w, hi[u].x, hi[u].y, hi[u].z, hi[u].w};
+                        float xv[8];
+                        unpack8(lo[u], hi[u], xv);
                         float y[8];
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
@@ -349,7 +371,7 @@ gn_apply_kernel(const GnApplyArgs p) {
 template <int FMT, bool RAW>
 static void launch_gn_apply2(const GnApplyArgs& a, dim3 grid, cudaStream_t st) {
     const size_t smem = 3 * (size_t)(a.C0 + a.C1) * sizeof(float);
-#define NDB_GN_CASE(RS, SL) gn_apply_kernel<FMT, RS, SL, RAW><<<grid, kGnThreads, smem, st>>>(a)
+#define NDB_GN_CASE(RS, SL) gn_apply_kernel<FMT, RS, SL, RAW, false><<<grid, kGnThreads, smem, st>>>(a)
     if (a.resample == NDB_RESAMPLE_NONE) { if (a.silu) NDB_GN_CASE(NDB_RESAMPLE_NONE, true); else NDB_GN_CASE(NDB_RESAMPLE_NONE, false); }
     else if (a.resample == NDB_RESAMPLE_UP2) { if (a.silu) NDB_GN_CASE(NDB_RESAMPLE_UP2, true); else NDB_GN_CASE(NDB_RESAMPLE_UP2, false); }
     else { if (a.silu) NDB_GN_CASE(NDB_RESAMPLE_DOWN2, true); else NDB_GN_CASE(NDB_RESAMPLE_DOWN2, false); }
@@ -358,7 +380,12 @@ static void launch_gn_apply2(const GnApplyArgs& a, dim3 grid, cudaStream_t st) {
 
 template <int FMT>
 static void launch_gn_apply(const GnApplyArgs& a, dim3 grid, cudaStream_t st) {
-    if (a.raw16 != nullptr) launch_gn_apply2<FMT, true>(a, grid, st);
+    if (a.x0_is16) {
+        // 16-bit source: the out_norm of a ResBlock (single source, no resampling, no raw copy)
+        const size_t smem = 3 * (size_t)(a.C0 + a.C1) * sizeof(float);
+        if (a.silu) gn_apply_kernel<FMT, NDB_RESAMPLE_NONE, true, false, true><<<grid, kGnThreads, smem, st>>>(a);
+        else gn_apply_kernel<FMT, NDB_RESAMPLE_NONE, false, false, true><<<grid, kGnThreads, smem, st>>>(a);
+    } else if (a.raw16 != nullptr) launch_gn_apply2<FMT, true>(a, grid, st);
     else launch_gn_apply2<FMT, false>(a, grid, st);
 }
 
@@ -436,6 +463,8 @@ extern "C" int ndb_gn_apply(const ndb_gn_apply_params* q, void* stream) {
     a.silu = q->silu; a.resample = q->resample;
     a.out = (uint16_t*)q->out; a.raw16 = (uint16_t*)q->raw16;
     a.pool32 = q->pool32;
+    a.x0_is16 = q->x0_is16;
+    if (q->x0_is16) NDB_CHECK_ARG(q->x1 == nullptr && q->resample == NDB_RESAMPLE_NONE && q->raw16 == nullptr);
     NDB_CHECK_ARG(q->pool32 == nullptr || q->resample == NDB_RESAMPLE_DOWN2);
     a.eps = q->eps;
     const int V8 = C / 8;

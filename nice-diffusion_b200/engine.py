@@ -304,7 +304,13 @@ class UNetEngine:
         pooled = pool.get((B, Ho, Wo, Cin), torch.float32) if (rb.mode == 'down' and not conv_skip) else None
         self.steps.append(lambda: ops.gn_apply(x.t, x.stats, g1, b1, x1=x1, stats1=s1, silu=True, resample=mode,
                                                out=a1, raw16=raw, fmt=fmt, eps=eps1, pool32=pooled))
-        h = self._conv([(a1, w_in)], Ho, Wo, Cout, want_stats=True, bias=bias_in)
+        if self.model.h_fp16 and ops.conv_stats_supported(B, Ho, Wo):
+            # `h` only feeds the out_norm: 16-bit storage halves its write + read (statistics still come from the fp32
+            # accumulators in the epilogue)
+            h = self._conv([(a1, w_in)], Ho, Wo, Cout, want_stats=True, bias=bias_in, out_kind=L.OUT_F16_NHWC,
+                           out=pool.get((B, Ho, Wo, Cout), self.dt16))
+        else:
+            h = self._conv([(a1, w_in)], Ho, Wo, Cout, want_stats=True, bias=bias_in)
         self.steps.append(lambda: ops.gn_apply(h.t, h.stats, g2, b2, scale=scale, shift=shift, pre_add=pre, silu=True,
                                                out=a2, fmt=fmt, eps=eps2))
         if conv_skip:

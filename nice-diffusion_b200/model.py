@@ -185,6 +185,10 @@ class DiffusionModel(nn.Module):
         # engine state (not part of the state dict)
         self.operand_format = L.FMT_FP16
         self.use_cuda_graph = True
+        # store the ResBlock-internal tensor h (in_conv output) in 16 bits: supported, but measured no faster on B200
+        # (the apply kernel is latency- not bandwidth-bound and 2-byte epilogue stores are slower) and it costs ~20 %
+        # of the error budget, so it is off
+        self.h_fp16 = False
         self._engines = {}
 
     # ------------------------------------------------------------------------------------------

@@ -196,6 +196,8 @@ def gn_apply(x0, stats0, gamma, beta, x1=None, stats1=None, scale=None, shift=No
         raw16 = torch.empty_like(out)
     p = L.GnApplyParams()
     p.x0, p.C0 = x0.data_ptr(), C0
+    p.x0_is16 = 1 if x0.dtype != torch.float32 else 0
+    assert x0.dtype in (torch.float32, dtype16(fmt))
     p.x1, p.C1 = (x1.data_ptr() if x1 is not None else None), C1
     p.N, p.H, p.W = N, H, W
     p.parts0, p.counts0, p.smax0 = stats0[0].data_ptr(), stats0[1].data_ptr(), stats0[0].shape[1]

@@ -1,31 +1,32 @@
-"""Time single conv shapes (CUDA events, 20 reps) under the env switches NDB_DISABLE_2CTA / NDB_DBG."""
+"""Time single conv shapes (CUDA graph of 20 launches, CUDA events) under the env switches NDB_DISABLE_2CTA / NDB_DBG."""
 import math, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from nice_diffusion_b200 import ops, _lib as L
 dev = torch.device('cuda:0')
-shapes = [(2, 8, 8, 64, 64, 1, 0), (32, 8, 8, 768, 768, 1, 1), (32, 64, 64, 384, 192, 3, 0), (32, 64, 64, 192, 192, 3, 1), (32, 32, 32, 384, 1152, 1, 0), (32, 16, 16, 576, 576, 3, 0),
-          (32, 8, 8, 768, 768, 3, 0)]
-for (N, H, W, Cin, Cout, k, res) in shapes:
+# N, H, W, Cin, Cout, k, residual, stats, fp16 out
+shapes = [(32, 32, 32, 384, 1152, 1, 0, 0, 1), (32, 32, 32, 384, 384, 1, 1, 1, 0), (32, 8, 8, 768, 768, 3, 1, 1, 0),
+          (32, 64, 64, 192, 192, 3, 1, 1, 0), (32, 64, 64, 384, 192, 3, 0, 1, 0)]
+if len(sys.argv) > 1:
+    shapes = [shapes[int(a)] for a in sys.argv[1:]]
+for (N, H, W, Cin, Cout, k, res, stats, o16) in shapes:
     x16 = torch.randn(N, H, W, Cin, device=dev).half()
     w = torch.randn(Cout, Cin, k, k, device=dev) / math.sqrt(Cin * k * k)
     wp = ops.pack_conv_weight(w)
     b = torch.randn(Cout, device=dev)
     r = torch.randn(N, H, W, Cout, device=dev) if res else None
-    out = torch.empty(N, H, W, Cout, device=dev)
-    st = ops.conv_stats_alloc(N, H, W, Cout, dev) if ops.conv_stats_supported(N, H, W) else None
-    f = lambda: ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, residual=r, residual_mode=L.RES_SAME, out=out, stats=st)
+    out = torch.empty(N, H, W, Cout, device=dev, dtype=torch.float16 if o16 else torch.float32)
+    st = ops.conv_stats_alloc(N, H, W, Cout, dev) if stats else None
+    f = lambda: ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, residual=r, residual_mode=L.RES_SAME, out=out, stats=st,
+                              out_kind=L.OUT_F16_NHWC if o16 else L.OUT_F32_NHWC)
     for _ in range(3): f()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         for _ in range(20): f()
     g.replay(); torch.cuda.synchronize()
-    e0.record()
-    g.replay()
-    e1.record(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / 20 * 1e3
     fl = 2.0 * N * H * W * Cout * Cin * k * k
-    print('N%d %dx%d %d->%d k%d res%d: %8.1f us  %7.1f TFLOP/s' % (N, H, W, Cin, Cout, k, res, us, fl / us / 1e6))
+    print('N%d %dx%d %d->%d k%d res%d st%d o16=%d: %8.1f us  %7.1f TFLOP/s' % (N, H, W, Cin, Cout, k, res, stats, o16, us, fl / us / 1e6))

@@ -200,6 +200,21 @@ def test_groupnorm_apply(cuda_dev, N, H, W, C0, C1, resample):
     assert torch.equal(again[0], st0[0])
 
 
+def test_groupnorm_apply_16bit_input(cuda_dev):
+    """out_norm over the fp16 `h` of a ResBlock with statistics taken from the fp32 values."""
+    ops, L = _ops()
+    g = torch.Generator(device='cpu').manual_seed(4)
+    N, H, W, C = 3, 16, 16, 192
+    x = (torch.randn(N, C, H, W, generator=g) * 1.5 + 0.3).to(cuda_dev)
+    gamma = (1 + 0.1 * torch.randn(C, generator=g)).to(cuda_dev)
+    beta = (0.1 * torch.randn(C, generator=g)).to(cuda_dev)
+    ss = (0.3 * torch.randn(N, 2 * C, generator=g)).to(cuda_dev)
+    stats = ops.gn_stats(nhwc(x))
+    out = ops.gn_apply(nhwc(x).half(), stats, gamma, beta, scale=ss[:, :C], shift=ss[:, C:], silu=True)
+    ref = F.silu(F.group_norm(x, 32, gamma, beta, eps=1e-5) * (1 + ss[:, :C, None, None]) + ss[:, C:, None, None])
+    assert rel_err(out.permute(0, 3, 1, 2), ref) < 2.5e-3
+
+
 def test_groupnorm_plain_preadd_nosilu(cuda_dev):
     """non-adaptive path: h += emb; GroupNorm(h) (model.py:204-206) and the attention norm (no SiLU)."""
     ops, L = _ops()
