@@ -96,6 +96,8 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t tmem_S = tmem_base;
     const uint32_t tmem_O = tmem_base + kAttnBN;
 
@@ -345,8 +347,8 @@ extern "C" int ndb_attention(const void* qkv, void* out, int B, int T, int heads
     }
     dim3 grid((T + kAttnBM - 1) / kAttnBM, heads, B);
     if (operand_format == 0)
-        attention_kernel<0><<<grid, 160, smem, (cudaStream_t)stream>>>(map, a);
+        launch_kernel(attention_kernel<0>, grid, dim3(160), smem, (cudaStream_t)stream, 1, map, a);
     else
-        attention_kernel<1><<<grid, 160, smem, (cudaStream_t)stream>>>(map, a);
+        launch_kernel(attention_kernel<1>, grid, dim3(160), smem, (cudaStream_t)stream, 1, map, a);
     return launch_status("ndb_attention");
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -53,26 +54,72 @@ inline PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-// 16-bit element tensor map, 128-byte swizzle, zero fill out of bounds. dims/box innermost first;
-// strides_bytes has rank-1 entries (dimension 0 is dense).
-inline int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                             const uint64_t* strides_bytes, const uint32_t* box) {
+// Tiled tensor map, zero fill out of bounds. dims/box innermost first; strides_bytes has rank-1 entries (dimension 0 is
+// dense). elem_bytes 2 (uint16 payload) or 4 (float32); swizzle_bytes 128 or 64.
+inline int encode_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle_bytes, int rank, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box) {
     PFN_encodeTiled fn = get_encode_fn();
     if (!fn) {
         std::fprintf(stderr, "[ndb200] cuTensorMapEncodeTiled unavailable\n");
         return NDB_ERR_CUDA;
     }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, (cuuint32_t)rank, const_cast<void*>(base),
-                    reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
-                    reinterpret_cast<const cuuint32_t*>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                    const_cast<void*>(base), reinterpret_cast<const cuuint64_t*>(dims),
+                    reinterpret_cast<const cuuint64_t*>(strides_bytes), reinterpret_cast<const cuuint32_t*>(box), estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         std::fprintf(stderr, "[ndb200] cuTensorMapEncodeTiled failed: %d (rank %d dims %llu %llu box %u %u)\n", (int)r,
                      rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
         return NDB_ERR_CUDA;
     }
     return NDB_OK;
+}
+
+// 16-bit elements, 128-byte swizzle: the tensor-core operand tiles
+inline int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                             const uint64_t* strides_bytes, const uint32_t* box) {
+    return encode_tmap(out, base, 2, 128, rank, dims, strides_bytes, box);
+}
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------
+// Every kernel of this library is launched with programmaticStreamSerialization: its CTAs may start while the previous
+// kernel of the stream is still draining and run their prologue (barrier init, TMEM allocation, tensor-map prefetch,
+// index math); `pdl_wait()` then blocks until the previous grid has completed and its writes are visible. It must precede
+// the first global-memory access. `pdl_launch_dependents()` lets the NEXT kernel start early in the same way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) on = std::getenv("NDB_DISABLE_PDL") ? 0 : 1;
+    return on != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 int cluster_x, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (cluster_x > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 }  // namespace ndb

@@ -12,10 +12,14 @@
 //
 // Warp roles (352 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue,
 // warp 10 = GroupNorm-statistics reducer (only active when chan_stats is requested).
-// Epilogue: each warp owns 32 accumulator rows (its TMEM lane quarter) and half of the tile's column chunks. Per
-// 32-column chunk it (1) issues the residual loads with lanes along channels (32 independent, fully coalesced 128-byte
-// requests in flight per warp), (2) pulls the chunk out of TMEM (thread = row), (3) transposes it through a padded
-// per-warp smem tile so that (4) bias + residual + the global store also run with lanes along channels.
+// Epilogue: each warp owns 32 accumulator rows (its TMEM lane quarter) and half of the tile's 32-column chunks.
+//   bulk path (NHWC outputs whose 32 rows form a {w, h} box -- every power-of-two image size): the chunk is pulled out of
+//   TMEM (thread = row) into a per-warp 4 KB SWIZZLE_128B staging tile with conflict-free 16-byte stores; when a residual
+//   or GroupNorm statistics are wanted the warp then walks the tile with lanes along channels (conflict-free again), adds
+//   bias + residual in place and takes the column sums; ONE TMA store writes the box back. Residual values are fetched
+//   with lanes along channels (32 coalesced 128-byte requests in flight per warp) one chunk AHEAD of the chunk being
+//   processed, across tile boundaries, so their latency hides behind the previous chunk.
+//   legacy path (NCHW head, 2x up/down-sampled residuals, odd image sizes): padded transpose tile + per-row stores.
 #include "common.cuh"
 #include "ptx.cuh"
 #include <cuda_fp16.h>
@@ -36,6 +40,7 @@ constexpr int kMaxStages = 8;
 struct TmapPack {
     CUtensorMap a[kMaxSeg];
     CUtensorMap b[kMaxSeg];
+    CUtensorMap out;    // bulk epilogue: {32 channels, box_w, box_h, 1} boxes of the NHWC output
 };
 
 struct ConvArgs {
@@ -65,7 +70,7 @@ struct ConvArgs {
     int stat_smax;             // partial slots per image
     int tiles_per_group;       // tiles (m x n) covering one group of TN images
     int b_rows;                // weight rows per CTA per stage (block_n, or block_n / 2 in CTA-pair mode)
-    int dbg;                   // bring-up switches (env NDB_DBG): 1 = no TMA traffic, 2 = no MMAs (results are garbage)
+    int epi_bulk;              // 1: staged TMA-store epilogue
 };
 
 // Persistent CTAs own CONTIGUOUS tile ranges: CTA c processes tiles [tile_start(c), tile_start(c+1)). Tiles are ordered
@@ -103,16 +108,16 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
 
     const int b_tile_bytes = p.b_rows * 128;
     const int stage_bytes = kATileBytes + b_tile_bytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+    uint8_t* epi_base = smem + p.stages * stage_bytes;   // 1024-aligned: per-warp staging tiles (bulk 4 KB / legacy 33x32 floats)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_base + kEpiWarps * kStageFloats * sizeof(float));
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full_bar = empty_bar + kMaxStages;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
     uint64_t* stat_full_bar = tmem_empty_bar + 2;
     uint64_t* stat_empty_bar = stat_full_bar + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(stat_empty_bar + 2);
-    float* epi_stage = reinterpret_cast<float*>(smem + p.stages * stage_bytes + 256);
-    long long* epi_rows = reinterpret_cast<long long*>(epi_stage + kEpiWarps * kStageFloats);
-    float2* part_smem = reinterpret_cast<float2*>(epi_rows + kEpiWarps * 64);   // [2 buffers][4 quarters][block_n]
+    long long* epi_rows = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
+    float2* part_smem = reinterpret_cast<float2*>(epi_rows + kEpiWarps * 128);  // [2 buffers][4 quarters][block_n]
     float2* stat_acc = part_smem + 2 * 4 * p.block_n;                           // [TN][cout] (statistics warp only)
 
     const int warp = threadIdx.x >> 5;
@@ -131,6 +136,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             prefetch_tmap(&maps.a[s]);
             prefetch_tmap(&maps.b[s]);
         }
+        if (p.epi_bulk) prefetch_tmap(&maps.out);
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], k2 ? 2 : 1);   // pair mode: both CTAs' producers arrive on the leader's barrier
             mbar_init(&empty_bar[s], 1);
@@ -152,6 +158,8 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
     if (k2) cluster_sync_all();    // the peer's barriers must be initialised before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_launch_dependents();   // the next kernel may begin its prologue as SM resources free up
+    pdl_wait();                // everything above overlapped the previous kernel's tail; its outputs are visible from here
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -181,10 +189,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                             uint8_t* sa = smem + stage * stage_bytes;
                             uint8_t* sb = sa + kATileBytes;
                             if (elect_one()) {
-                                if (p.dbg & 1) {
-                                    if (k2) mbar_arrive_cluster(mapa_u32(smem_u32(&full_bar[stage]), 0));
-                                    else mbar_arrive(&full_bar[stage]);
-                                } else if (k2) {
+                                if (k2) {
                                     const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);   // leader's barrier
                                     mbar_arrive_expect_tx_cluster(fb, p.a_box_bytes + (uint32_t)b_tile_bytes);
                                     tma_load_4d_2sm(sa, &maps.a[s], fb, ch * kBlockK, w0 + dx, h0 + dy, n0);
@@ -223,13 +228,11 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                     const uint64_t adesc = make_desc_k_sw128(sa);
                     const uint64_t bdesc = make_desc_k_sw128(sa + kATileBytes);
                     if (elect_one()) {
-                        if (!(p.dbg & 2)) {
 #pragma unroll
-                            for (int k = 0; k < kBlockK / 16; ++k) {
-                                // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
-                                if (k2) umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
-                                else umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
-                            }
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
+                            if (k2) umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
+                            else umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
                         }
                         // frees the smem slot (in both CTAs of a pair) once these MMAs retire
                         if (k2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
@@ -256,9 +259,6 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;       // which half of the column chunks
         const int row = q * 32 + lane;          // accumulator row == pixel index inside the tile
-        float* stg = epi_stage + (warp - 2) * kStageFloats;
-        long long* row_out = epi_rows + (warp - 2) * 64;
-        long long* row_res = row_out + 32;
         const int nch = (p.block_n + 31) >> 5;
         const int ch_begin = half ? (nch + 1) / 2 : 0;
         const int ch_end = half ? nch : (nch + 1) / 2;
@@ -268,6 +268,190 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
         uint32_t stat_phase = 0;
         const int pix_per_img = p.TH * p.TW;
         const float* __restrict__ resp = p.residual;
+        // position of this thread's row inside a tile
+        const int tn = row / pix_per_img;
+        const int rem = row - tn * pix_per_img;
+        const int th = rem / p.TW;
+        const int tw = rem - th * p.TW;
+        if (p.epi_bulk) {
+            // ------------------------------------------------------------------------------------------------
+            // bulk path
+            // ------------------------------------------------------------------------------------------------
+            uint8_t* sbuf = epi_base + (warp - 2) * 4096;
+            float* sf = reinterpret_cast<float*>(sbuf);
+            long long* row_tab = epi_rows + (warp - 2) * 128;     // [2 tile parities][32 rows]: residual element offsets
+            const bool has_res = p.res_mode == NDB_RES_SAME;
+            const bool transposed = kStats || has_res;
+            // the box covered by this warp's 32 rows
+            const int r0 = q * 32;
+            const int btn = r0 / pix_per_img;
+            const int brem = r0 - btn * pix_per_img;
+            const int bth = brem / p.TW;
+            const int btw = brem - bth * p.TW;
+            const bool box_on = btn < p.TN;
+
+            auto setup_tile = [&](int tile, int buf) -> unsigned {
+                int m_tile = m_tile_of(tile);
+                const int tw_i = m_tile % p.tiles_w;
+                m_tile /= p.tiles_w;
+                const int th_i = m_tile % p.tiles_h;
+                const int tn_i = m_tile / p.tiles_h;
+                const int n = tn_i * p.TN + tn, h = th_i * p.TH + th, w = tw_i * p.TW + tw;
+                const bool valid = (tn < p.TN) && (n < p.N) && (h < p.H) && (w < p.W);
+                row_tab[buf * 32 + lane] = valid ? (((long long)n * p.H + h) * p.W + w) * p.cout : 0;
+                const unsigned m = __ballot_sync(0xffffffffu, valid);
+                __syncwarp();
+                return m;
+            };
+            auto issue_res = [&](float (&dst)[32], int buf, unsigned vmask, int col) {
+                const unsigned okmask = (col < p.cout) ? vmask : 0u;
+                const float* base = resp + col;
+                const long long* rt = row_tab + buf * 32;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    float v = 0.f;
+                    if ((okmask >> r) & 1u) v = __ldg(base + rt[r]);
+                    dst[r] = v;
+                }
+            };
+
+            float resn[32];
+#pragma unroll
+            for (int r = 0; r < 32; ++r) resn[r] = 0.f;
+            unsigned vmask_next = 0;
+            if (tile_begin < tile_end && ch_begin < ch_end) {
+                vmask_next = setup_tile(tile_begin, 0);
+                if (has_res) issue_res(resn, 0, vmask_next, (tile_begin % p.num_n_tiles) * p.block_n + ch_begin * 32 + lane);
+            }
+            for (int tile = tile_begin; tile < tile_end; ++tile) {
+                const int buf = (tile - tile_begin) & 1;
+                const unsigned vmask = vmask_next;
+                const int col0 = (tile % p.num_n_tiles) * p.block_n;
+                int m_tile = m_tile_of(tile);
+                const int tw_i = m_tile % p.tiles_w;
+                m_tile /= p.tiles_w;
+                const int th_i = m_tile % p.tiles_h;
+                const int tn_i = m_tile / p.tiles_h;
+                const int bn = tn_i * p.TN + btn, bh = th_i * p.TH + bth, bw = tw_i * p.TW + btw;
+
+                mbar_wait(&tmem_full_bar[acc], acc_phase);
+                tc_fence_after();
+                if (kStats) mbar_wait(&stat_empty_bar[stat_buf], stat_phase ^ 1);   // part_smem buffer free
+                const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * p.acc_stride;
+                for (int ch = ch_begin; ch < ch_end; ++ch) {
+                    float res[32];
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) res[r] = resn[r];
+                    // next chunk's residual (possibly the next tile's first chunk) goes out before this chunk is touched
+                    if (ch + 1 < ch_end) {
+                        if (has_res) issue_res(resn, buf, vmask, col0 + (ch + 1) * 32 + lane);
+                    } else if (tile + 1 < tile_end) {
+                        vmask_next = setup_tile(tile + 1, buf ^ 1);
+                        if (has_res)
+                            issue_res(resn, buf ^ 1, vmask_next, ((tile + 1) % p.num_n_tiles) * p.block_n + ch_begin * 32 + lane);
+                    }
+                    uint32_t racc[32];
+                    tmem_ld32(t_row + ch * 32, racc);
+                    tmem_ld_wait();
+                    // the previous TMA store must have drained the staging tile
+                    if (elect_one()) bulk_wait_read_all();
+                    __syncwarp();
+                    const int c0 = col0 + ch * 32;
+                    if (!transposed) {
+                        // bias in thread = row form, straight into the staging tile
+                        if (p.out_kind == NDB_OUT_F32_NHWC) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (p.bias != nullptr && c0 + 4 * j < p.cout) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * j));
+                                *reinterpret_cast<float4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                                    make_float4(__uint_as_float(racc[4 * j]) + b4.x, __uint_as_float(racc[4 * j + 1]) + b4.y,
+                                                __uint_as_float(racc[4 * j + 2]) + b4.z, __uint_as_float(racc[4 * j + 3]) + b4.w);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                                if (p.bias != nullptr && c0 + 8 * j < p.cout) {
+                                    b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 8 * j));
+                                    b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 8 * j + 4));
+                                }
+                                const float v0 = __uint_as_float(racc[8 * j]) + b0.x, v1 = __uint_as_float(racc[8 * j + 1]) + b0.y;
+                                const float v2 = __uint_as_float(racc[8 * j + 2]) + b0.z, v3 = __uint_as_float(racc[8 * j + 3]) + b0.w;
+                                const float v4 = __uint_as_float(racc[8 * j + 4]) + b1.x, v5 = __uint_as_float(racc[8 * j + 5]) + b1.y;
+                                const float v6 = __uint_as_float(racc[8 * j + 6]) + b1.z, v7 = __uint_as_float(racc[8 * j + 7]) + b1.w;
+                                uint4 w4;
+                                if (p.fmt == 0) w4 = make_uint4(pack2<0>(v0, v1), pack2<0>(v2, v3), pack2<0>(v4, v5), pack2<0>(v6, v7));
+                                else w4 = make_uint4(pack2<1>(v0, v1), pack2<1>(v2, v3), pack2<1>(v4, v5), pack2<1>(v6, v7));
+                                // 64-byte rows, SWIZZLE_64B: 16-byte chunk index ^ bits [1,2] of the row
+                                *reinterpret_cast<uint4*>(sbuf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = w4;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                                make_uint4(racc[4 * j], racc[4 * j + 1], racc[4 * j + 2], racc[4 * j + 3]);
+                        __syncwarp();
+                        // lanes along channels: bias + residual in place, column sums on the way
+                        const int col = c0 + lane;
+                        const bool colok = col < p.cout;
+                        const float bias_v = (colok && p.bias != nullptr) ? __ldg(p.bias + col) : 0.f;
+                        const int lswz = lane >> 2, lw = lane & 3;
+#pragma unroll
+                        for (int r = 0; r < 32; ++r) {
+                            const int idx = r * 32 + (((lswz ^ (r & 7)) << 2) | lw);
+                            const float v = sf[idx] + bias_v + res[r];
+                            sf[idx] = v;
+                            res[r] = v;
+                        }
+                        if (kStats) {
+                            const unsigned okmask = colok ? vmask : 0u;
+                            float cs = 0.f, css = 0.f;
+#pragma unroll
+                            for (int r = 0; r < 32; ++r) {
+                                const float v = ((okmask >> r) & 1u) ? res[r] : 0.f;
+                                cs += v;
+                                css += v * v;
+                            }
+                            part_smem[(stat_buf * 4 + q) * p.block_n + ch * 32 + lane] = make_float2(cs, css);
+                        }
+                    }
+                    fence_proxy_async();      // generic-proxy writes -> visible to the TMA engine
+                    __syncwarp();
+                    if (box_on) {
+                        if (elect_one()) {
+                            tma_store_4d(&maps.out, sbuf, c0, bw, bh, bn);
+                            bulk_commit();
+                        }
+                    }
+                    __syncwarp();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (k2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));   // the leader's MMA thread waits
+                    else mbar_arrive(&tmem_empty_bar[acc]);
+                }
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+                if (kStats) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&stat_full_bar[stat_buf]);   // this warp's column sums are in part_smem
+                    if ((stat_buf ^= 1) == 0) stat_phase ^= 1;
+                }
+            }
+            if (elect_one()) bulk_wait_all();     // shared memory must outlive the last store's reads
+            __syncwarp();
+        } else {
+        // ----------------------------------------------------------------------------------------------------
+        // legacy path
+        // ----------------------------------------------------------------------------------------------------
+        float* stg = reinterpret_cast<float*>(epi_base) + (warp - 2) * kStageFloats;
+        long long* row_out = epi_rows + (warp - 2) * 128;
+        long long* row_res = row_out + 32;
         for (int tile = tile_begin; tile < tile_end; ++tile) {
             const int n_tile = tile % p.num_n_tiles;
             int m_tile = m_tile_of(tile);
@@ -275,10 +459,6 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             m_tile /= p.tiles_w;
             const int th_i = m_tile % p.tiles_h;
             const int tn_i = m_tile / p.tiles_h;
-            const int tn = row / pix_per_img;
-            const int rem = row - tn * pix_per_img;
-            const int th = rem / p.TW;
-            const int tw = rem - th * p.TW;
             const int n = tn_i * p.TN + tn, h = th_i * p.TH + th, w = tw_i * p.TW + tw;
             const bool valid = (tn < p.TN) && (n < p.N) && (h < p.H) && (w < p.W);
             const int col0 = n_tile * p.block_n;
@@ -306,48 +486,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             tc_fence_after();
             if (kStats) mbar_wait(&stat_empty_bar[stat_buf], stat_phase ^ 1);   // part_smem buffer free
             const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * p.acc_stride;
-            // ---- fast path (no statistics, no residual, NHWC output: qkv / step-embedding GEMMs): the thread that owns
-            //      accumulator row r writes its 32 channels straight out as 16-byte vectors -- no transposition ----
-            const bool direct = !kStats && p.res_mode == NDB_RES_NONE && p.out_kind != NDB_OUT_F32_NCHW && (p.cout & 7) == 0;
-            for (int ch = ch_begin; direct && ch < ch_end; ++ch) {
-                uint32_t racc[32];
-                tmem_ld32(t_row + ch * 32, racc);
-                tmem_ld_wait();
-                const int c0 = col0 + ch * 32;
-                if (!valid || c0 >= p.cout || ch * 32 >= p.block_n) continue;
-                const int ncols = min(32, min(p.cout - c0, p.block_n - ch * 32));     // multiple of 8
-                float v[32];
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (p.bias != nullptr && i < ncols) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i));
-                    v[i] = __uint_as_float(racc[i]) + b4.x; v[i + 1] = __uint_as_float(racc[i + 1]) + b4.y;
-                    v[i + 2] = __uint_as_float(racc[i + 2]) + b4.z; v[i + 3] = __uint_as_float(racc[i + 3]) + b4.w;
-                }
-                if (p.out_kind == NDB_OUT_F32_NHWC) {
-                    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + c0);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (4 * i < ncols) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                } else {
-                    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + out_off + c0);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (8 * i < ncols) {
-                            uint4 w4;
-                            if (p.fmt == 0) {
-                                w4 = make_uint4(pack2<0>(v[8 * i], v[8 * i + 1]), pack2<0>(v[8 * i + 2], v[8 * i + 3]),
-                                                pack2<0>(v[8 * i + 4], v[8 * i + 5]), pack2<0>(v[8 * i + 6], v[8 * i + 7]));
-                            } else {
-                                w4 = make_uint4(pack2<1>(v[8 * i], v[8 * i + 1]), pack2<1>(v[8 * i + 2], v[8 * i + 3]),
-                                                pack2<1>(v[8 * i + 4], v[8 * i + 5]), pack2<1>(v[8 * i + 6], v[8 * i + 7]));
-                            }
-                            o[i] = w4;
-                        }
-                    }
-                }
-            }
-            for (int ch = ch_begin; !direct && ch < ch_end; ++ch) {
+            for (int ch = ch_begin; ch < ch_end; ++ch) {
                 const int cl = ch * 32 + lane;             // column inside the tile owned by this lane (transposed view)
                 const int col = col0 + cl;
                 const bool colok = (cl < p.block_n) && (col < p.cout);
@@ -379,21 +518,18 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                     }
                 }
                 // (2) accumulator chunk out of TMEM (thread = row)
-                if (!(p.dbg & 32)) {
                 uint32_t racc[32];
                 tmem_ld32(t_row + ch * 32, racc);
                 tmem_ld_wait();
                 // (3) transpose through the padded per-warp tile
 #pragma unroll
                 for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __uint_as_float(racc[i]);
-                }
                 __syncwarp();
                 const float bias_v = (colok && p.bias != nullptr) ? __ldg(p.bias + col) : 0.f;
                 // (4) bias + residual, then store with lanes along channels
 #pragma unroll
                 for (int r = 0; r < 32; ++r) res[r] = stg[r * 33 + lane] + bias_v + res[r];
-                if (p.dbg & 4) {
-                } else if (p.out_kind == NDB_OUT_F32_NHWC) {
+                if (p.out_kind == NDB_OUT_F32_NHWC) {
                     float* ob = reinterpret_cast<float*>(p.out) + col;
 #pragma unroll
                     for (int r = 0; r < 32; ++r)
@@ -413,7 +549,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                     for (int r = 0; r < 32; ++r)
                         if ((okmask >> r) & 1u) ob[row_out[r]] = res[r];
                 }
-                if (kStats && !(p.dbg & 16)) {
+                if (kStats) {
                     // column sums over this warp's 32 rows come for free in the transposed view (fixed order)
                     float cs = 0.f, css = 0.f;
 #pragma unroll
@@ -441,6 +577,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                 if (lane == 0) mbar_arrive(&stat_full_bar[stat_buf]);   // this warp's column sums are in part_smem
                 if ((stat_buf ^= 1) == 0) stat_phase ^= 1;
             }
+        }
         }
     } else if (kStats) {
         // ===================== statistics warp =====================
@@ -518,6 +655,8 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
 __global__ void pack_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ dst, int cout, int cin_total,
                                    int taps, int cout_pad, int cin_off, int cin_len, int fmt) {
     const long long total = (long long)taps * cout_pad * cin_len;
+    pdl_launch_dependents();
+    pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int ci = (int)(i % cin_len);
@@ -636,8 +775,8 @@ extern "C" int ndb_pack_conv_weight(const float* w_oihw, void* dst, int cout, in
     const long long total = (long long)taps * cout_pad * cin_len;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, (uint16_t*)dst, cout, cin_total, taps, cout_pad,
-                                                                  cin_off, cin_len, operand_format);
+    launch_kernel(pack_weight_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, 1, w_oihw, (uint16_t*)dst, cout,
+                  cin_total, taps, cout_pad, cin_off, cin_len, operand_format);
     return launch_status("ndb_pack_conv_weight");
 }
 
@@ -687,11 +826,6 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     const ConvGeom cg = conv_geom(prm->N, prm->H, prm->W);
     const WorkGeom wg = work_geom(cg, a.num_n_tiles, a.block_n, prm->stat_parts != nullptr);
     a.b_rows = wg.pair ? a.block_n / 2 : a.block_n;
-    {
-        static int dbg = -1;
-        if (dbg < 0) { const char* e = std::getenv("NDB_DBG"); dbg = e ? std::atoi(e) : 0; }
-        a.dbg = dbg;
-    }
     if (wg.pair) a.idesc = make_idesc_f16(2 * kBlockM, a.block_n, prm->operand_format, 0, 0);
     if (prm->stat_parts != nullptr) {
         NDB_CHECK_ARG(prm->out_kind != NDB_OUT_F32_NCHW);
@@ -728,8 +862,32 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
         }
     }
 
+    // staged TMA-store epilogue: NHWC output, plain or same-size residual, whole 32-column chunks, and the 32 rows of a
+    // warp must form a {box_w, box_h} pixel box inside one image
+    {
+        static int off = -1;
+        if (off < 0) off = std::getenv("NDB_DISABLE_BULK_EPILOGUE") != nullptr ? 1 : 0;
+        const bool stats = prm->stat_parts != nullptr;
+        const int box_w = a.TW < 32 ? a.TW : 32, box_h = 32 / box_w;
+        const bool geom_ok = (a.TW % 32 == 0 || (32 % a.TW == 0 && a.TH % box_h == 0)) && (a.TH * a.TW) % 32 == 0;
+        const bool kind_ok = prm->out_kind == NDB_OUT_F32_NHWC ||
+                             (prm->out_kind == NDB_OUT_F16_NHWC && !stats && a.res_mode == NDB_RES_NONE);
+        const int es = prm->out_kind == NDB_OUT_F32_NHWC ? 4 : 2;
+        a.epi_bulk = (!off && geom_ok && kind_ok && (a.res_mode == NDB_RES_NONE || a.res_mode == NDB_RES_SAME) &&
+                      a.block_n % 32 == 0 && (prm->cout * es) % 16 == 0 && (reinterpret_cast<uintptr_t>(prm->out) & 15) == 0)
+                         ? 1 : 0;
+        if (a.epi_bulk) {
+            uint64_t dims[4] = {(uint64_t)prm->cout, (uint64_t)prm->W, (uint64_t)prm->H, (uint64_t)prm->N};
+            uint64_t strides[3] = {(uint64_t)prm->cout * es, (uint64_t)prm->W * prm->cout * es,
+                                   (uint64_t)prm->H * prm->W * prm->cout * es};
+            uint32_t box[4] = {32u, (uint32_t)box_w, (uint32_t)box_h, 1u};
+            int rc = encode_tmap(&maps.out, prm->out, es, es == 4 ? 128 : 64, 4, dims, strides, box);
+            if (rc != NDB_OK) return rc;
+        }
+    }
+
     const int stage_bytes = kATileBytes + a.b_rows * 128;
-    const int epi_bytes = kEpiWarps * (kStageFloats * (int)sizeof(float) + 64 * (int)sizeof(long long)) +
+    const int epi_bytes = kEpiWarps * (kStageFloats * (int)sizeof(float) + 128 * (int)sizeof(long long)) +
                           2 * 4 * a.block_n * (int)sizeof(float2) +
                           (prm->stat_parts ? a.TN * prm->cout * (int)sizeof(float2) : 0);
     const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - epi_bytes;
@@ -750,26 +908,16 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
         attr_set = true;
     }
     const bool stats = a.stat_parts != nullptr;
-    if (!wg.pair) {
-        if (stats) conv_gemm_kernel<true, false><<<wg.grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(maps, a);
-        else conv_gemm_kernel<false, false><<<wg.grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(maps, a);
-    } else {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(wg.grid);
-        cfg.blockDim = dim3(kThreads);
-        cfg.dynamicSmemBytes = smem_bytes;
-        cfg.stream = (cudaStream_t)stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        cudaError_t e = stats ? cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, true>, maps, a)
-                              : cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false, true>, maps, a);
-        if (e != cudaSuccess) {
-            std::fprintf(stderr, "[ndb200] cluster launch of conv_gemm_kernel failed: %s\n", cudaGetErrorString(e));
-            return NDB_ERR_CUDA;
-        }
+    cudaError_t le;
+    if (!wg.pair)
+        le = stats ? launch_kernel(conv_gemm_kernel<true, false>, dim3(wg.grid), dim3(kThreads), smem_bytes, (cudaStream_t)stream, 1, maps, a)
+                   : launch_kernel(conv_gemm_kernel<false, false>, dim3(wg.grid), dim3(kThreads), smem_bytes, (cudaStream_t)stream, 1, maps, a);
+    else
+        le = stats ? launch_kernel(conv_gemm_kernel<true, true>, dim3(wg.grid), dim3(kThreads), smem_bytes, (cudaStream_t)stream, 2, maps, a)
+                   : launch_kernel(conv_gemm_kernel<false, true>, dim3(wg.grid), dim3(kThreads), smem_bytes, (cudaStream_t)stream, 2, maps, a);
+    if (le != cudaSuccess) {
+        std::fprintf(stderr, "[ndb200] launch of conv_gemm_kernel failed: %s\n", cudaGetErrorString(le));
+        return NDB_ERR_CUDA;
     }
     return launch_status("ndb_conv_gemm");
 }

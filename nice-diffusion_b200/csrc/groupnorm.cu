@@ -28,6 +28,8 @@ gn_stats_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ 
     // (ticket counter) sums the per-block partials in block order and writes the final (sum, sumsq).
     extern __shared__ float sm[];  // [2][rows_per_block][C]
     __shared__ bool is_last;
+    pdl_launch_dependents();
+    pdl_wait();
     const int C = C0 + C1;
     const int V = C >> 2;
     const int n = blockIdx.y;
@@ -194,6 +196,8 @@ gn_apply_kernel(const GnApplyArgs p) {
         return pu;
     };
 
+    pdl_launch_dependents();
+    pdl_wait();
     // ---- 0. first trip's data ----
     uint4 lo[U], hi[U];
     if (RESAMPLE != NDB_RESAMPLE_DOWN2 && worker) {
@@ -371,7 +375,7 @@ gn_apply_kernel(const GnApplyArgs p) {
 template <int FMT, bool RAW>
 static void launch_gn_apply2(const GnApplyArgs& a, dim3 grid, cudaStream_t st) {
     const size_t smem = 3 * (size_t)(a.C0 + a.C1) * sizeof(float);
-#define NDB_GN_CASE(RS, SL) gn_apply_kernel<FMT, RS, SL, RAW, false><<<grid, kGnThreads, smem, st>>>(a)
+#define NDB_GN_CASE(RS, SL) launch_kernel(gn_apply_kernel<FMT, RS, SL, RAW, false>, grid, dim3(kGnThreads), smem, st, 1, a)
     if (a.resample == NDB_RESAMPLE_NONE) { if (a.silu) NDB_GN_CASE(NDB_RESAMPLE_NONE, true); else NDB_GN_CASE(NDB_RESAMPLE_NONE, false); }
     else if (a.resample == NDB_RESAMPLE_UP2) { if (a.silu) NDB_GN_CASE(NDB_RESAMPLE_UP2, true); else NDB_GN_CASE(NDB_RESAMPLE_UP2, false); }
     else { if (a.silu) NDB_GN_CASE(NDB_RESAMPLE_DOWN2, true); else NDB_GN_CASE(NDB_RESAMPLE_DOWN2, false); }
@@ -383,8 +387,8 @@ static void launch_gn_apply(const GnApplyArgs& a, dim3 grid, cudaStream_t st) {
     if (a.x0_is16) {
         // 16-bit source: the out_norm of a ResBlock (single source, no resampling, no raw copy)
         const size_t smem = 3 * (size_t)(a.C0 + a.C1) * sizeof(float);
-        if (a.silu) gn_apply_kernel<FMT, NDB_RESAMPLE_NONE, true, false, true><<<grid, kGnThreads, smem, st>>>(a);
-        else gn_apply_kernel<FMT, NDB_RESAMPLE_NONE, false, false, true><<<grid, kGnThreads, smem, st>>>(a);
+        if (a.silu) launch_kernel(gn_apply_kernel<FMT, NDB_RESAMPLE_NONE, true, false, true>, grid, dim3(kGnThreads), smem, st, 1, a);
+        else launch_kernel(gn_apply_kernel<FMT, NDB_RESAMPLE_NONE, false, false, true>, grid, dim3(kGnThreads), smem, st, 1, a);
     } else if (a.raw16 != nullptr) launch_gn_apply2<FMT, true>(a, grid, st);
     else launch_gn_apply2<FMT, false>(a, grid, st);
 }
