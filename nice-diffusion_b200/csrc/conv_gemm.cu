@@ -71,6 +71,9 @@ struct ConvArgs {
     int tiles_per_group;       // tiles (m x n) covering one group of TN images
     int b_rows;                // weight rows per CTA per stage (block_n, or block_n / 2 in CTA-pair mode)
     int epi_bulk;              // 1: staged TMA-store epilogue
+    int epi_bufs;              // staging tiles per epilogue warp (2 for short-K GEMMs whose epilogue is on the critical path)
+    int epi_region;            // bytes of the staging region
+    int dbg;                   // bring-up switches (env NDB_DBG; results are garbage): 1 no TMA loads, 2 no MMAs, 4 no TMA stores, 8 no staging writes
 };
 
 // Persistent CTAs own CONTIGUOUS tile ranges: CTA c processes tiles [tile_start(c), tile_start(c+1)). Tiles are ordered
@@ -104,12 +107,14 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment for SWIZZLE_128B tiles
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // (offset arithmetic on the __shared__ pointer, not an integer round trip: keeps the accesses below LDS/STS instead of
+    //  generic LD/ST)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
     const int b_tile_bytes = p.b_rows * 128;
     const int stage_bytes = kATileBytes + b_tile_bytes;
     uint8_t* epi_base = smem + p.stages * stage_bytes;   // 1024-aligned: per-warp staging tiles (bulk 4 KB / legacy 33x32 floats)
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_base + kEpiWarps * kStageFloats * sizeof(float));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_base + p.epi_region);
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full_bar = empty_bar + kMaxStages;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -189,7 +194,10 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                             uint8_t* sa = smem + stage * stage_bytes;
                             uint8_t* sb = sa + kATileBytes;
                             if (elect_one()) {
-                                if (k2) {
+                                if (p.dbg & 1) {
+                                    if (k2) mbar_arrive_cluster(mapa_u32(smem_u32(&full_bar[stage]), 0));
+                                    else mbar_arrive(&full_bar[stage]);
+                                } else if (k2) {
                                     const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);   // leader's barrier
                                     mbar_arrive_expect_tx_cluster(fb, p.a_box_bytes + (uint32_t)b_tile_bytes);
                                     tma_load_4d_2sm(sa, &maps.a[s], fb, ch * kBlockK, w0 + dx, h0 + dy, n0);
@@ -230,6 +238,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < kBlockK / 16; ++k) {
+                            if (p.dbg & 2) break;
                             // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
                             if (k2) umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
                             else umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
@@ -277,8 +286,8 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             // ------------------------------------------------------------------------------------------------
             // bulk path
             // ------------------------------------------------------------------------------------------------
-            uint8_t* sbuf = epi_base + (warp - 2) * 4096;
-            float* sf = reinterpret_cast<float*>(sbuf);
+            uint8_t* sbuf0 = epi_base + (warp - 2) * 4096 * p.epi_bufs;
+            int sb = 0;
             long long* row_tab = epi_rows + (warp - 2) * 128;     // [2 tile parities][32 rows]: residual element offsets
             const bool has_res = p.res_mode == NDB_RES_SAME;
             const bool transposed = kStats || has_res;
@@ -350,20 +359,34 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                         if (has_res)
                             issue_res(resn, buf ^ 1, vmask_next, ((tile + 1) % p.num_n_tiles) * p.block_n + ch_begin * 32 + lane);
                     }
+                    const int c0 = col0 + ch * 32;
+                    // thread = row form of the bias (statistic-free, residual-free GEMMs): loaded while TMEM is read
+                    float4 bias4[8];
+                    if (!transposed) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            bias4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (p.bias != nullptr && c0 + 4 * j < p.cout) bias4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * j));
+                        }
+                    }
                     uint32_t racc[32];
                     tmem_ld32(t_row + ch * 32, racc);
                     tmem_ld_wait();
-                    // the previous TMA store must have drained the staging tile
-                    if (elect_one()) bulk_wait_read_all();
+                    // the TMA store that last used this staging tile must have drained it
+                    uint8_t* sbuf = sbuf0 + sb * 4096;
+                    float* sf = reinterpret_cast<float*>(sbuf);
+                    if (elect_one()) {
+                        if (p.epi_bufs == 2) bulk_wait_read_1(); else bulk_wait_read_all();
+                    }
                     __syncwarp();
-                    const int c0 = col0 + ch * 32;
-                    if (!transposed) {
+                    if (p.epi_bufs == 2) sb ^= 1;
+                    if (p.dbg & 8) {
+                    } else if (!transposed) {
                         // bias in thread = row form, straight into the staging tile
                         if (p.out_kind == NDB_OUT_F32_NHWC) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (p.bias != nullptr && c0 + 4 * j < p.cout) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * j));
+                                const float4 b4 = bias4[j];
                                 *reinterpret_cast<float4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
                                     make_float4(__uint_as_float(racc[4 * j]) + b4.x, __uint_as_float(racc[4 * j + 1]) + b4.y,
                                                 __uint_as_float(racc[4 * j + 2]) + b4.z, __uint_as_float(racc[4 * j + 3]) + b4.w);
@@ -371,11 +394,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                         } else {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-                                if (p.bias != nullptr && c0 + 8 * j < p.cout) {
-                                    b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 8 * j));
-                                    b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 8 * j + 4));
-                                }
+                                const float4 b0 = bias4[2 * j], b1 = bias4[2 * j + 1];
                                 const float v0 = __uint_as_float(racc[8 * j]) + b0.x, v1 = __uint_as_float(racc[8 * j + 1]) + b0.y;
                                 const float v2 = __uint_as_float(racc[8 * j + 2]) + b0.z, v3 = __uint_as_float(racc[8 * j + 3]) + b0.w;
                                 const float v4 = __uint_as_float(racc[8 * j + 4]) + b1.x, v5 = __uint_as_float(racc[8 * j + 5]) + b1.y;
@@ -419,7 +438,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                     }
                     fence_proxy_async();      // generic-proxy writes -> visible to the TMA engine
                     __syncwarp();
-                    if (box_on) {
+                    if (box_on && !(p.dbg & 4)) {
                         if (elect_one()) {
                             tma_store_4d(&maps.out, sbuf, c0, bw, bh, bn);
                             bulk_commit();
@@ -722,14 +741,6 @@ static ConvGeom conv_geom(int N, int H, int W) {
     return g;
 }
 
-static int pick_block_n(int cout_pad) {
-    // 192 first: it divides every ImageNet-64 width (192..2304) and leaves room for a 4-stage smem ring
-    if (cout_pad % 192 == 0) return 192;
-    for (int bn = 256; bn >= 16; bn -= 16)
-        if (cout_pad % bn == 0) return bn;
-    return 0;
-}
-
 // CTA-pair mode is used whenever two M tiles exist and, when statistics are requested, both CTAs of a pair always sweep
 // the same images (even number of m tiles per image) or each tile holds whole images.
 static bool use_pair_mode(const ConvGeom& g, int block_n, bool want_stats) {
@@ -760,6 +771,29 @@ static WorkGeom work_geom(const ConvGeom& g, int num_n_tiles, int block_n, bool 
         w.grid = w.workers;
     }
     return w;
+}
+
+// BLOCK_N by a small cost model: rounds of tiles per worker x tile cost. Narrow tiles run the tensor pipe at a lower rate
+// (shared-memory operand bandwidth per MMA grows relative to its work; rates measured with scripts/blockn_probe.py), but
+// they fill the machine when a layer has few tiles (the 8x8 levels: 16 M tiles).
+static int pick_block_n(int cout_pad, const ConvGeom& g, bool want_stats) {
+    static const int cand[5] = {256, 192, 128, 96, 64};
+    static const double rate[5] = {1.0, 1.0, 0.78, 0.61, 0.5};
+    int best = 0;
+    double best_cost = 0.0;
+    for (int i = 0; i < 5; ++i) {
+        const int bn = cand[i];
+        if (cout_pad % bn != 0) continue;
+        const WorkGeom w = work_geom(g, cout_pad / bn, bn, want_stats);
+        const int rounds = (w.items + w.workers - 1) / w.workers;
+        double cost = rounds * (double)bn / rate[i];
+        if (bn == 256) cost *= 1.02;    // 192 leaves room for one more smem stage: prefer it on ties
+        if (best == 0 || cost < best_cost) { best = bn; best_cost = cost; }
+    }
+    if (best) return best;
+    for (int bn = 256; bn >= 16; bn -= 16)
+        if (cout_pad % bn == 0) return bn;
+    return 0;
 }
 
 }  // namespace ndb
@@ -805,7 +839,7 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     a.tiles_h = (prm->H + a.TH - 1) / a.TH;
     a.tiles_n = (prm->N + a.TN - 1) / a.TN;
     a.num_m_tiles = a.tiles_w * a.tiles_h * a.tiles_n;
-    a.block_n = prm->block_n > 0 ? prm->block_n : pick_block_n(prm->cout_pad);
+    a.block_n = prm->block_n > 0 ? prm->block_n : pick_block_n(prm->cout_pad, conv_geom(prm->N, prm->H, prm->W), prm->stat_parts != nullptr);
     NDB_CHECK_ARG(a.block_n >= 16 && a.block_n <= 256 && a.block_n % 16 == 0 && prm->cout_pad % a.block_n == 0);
     a.num_n_tiles = prm->cout_pad / a.block_n;
     a.cout = prm->cout;
@@ -826,6 +860,11 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     const ConvGeom cg = conv_geom(prm->N, prm->H, prm->W);
     const WorkGeom wg = work_geom(cg, a.num_n_tiles, a.block_n, prm->stat_parts != nullptr);
     a.b_rows = wg.pair ? a.block_n / 2 : a.block_n;
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = std::getenv("NDB_DBG"); dbg = e ? std::atoi(e) : 0; }
+        a.dbg = dbg;
+    }
     if (wg.pair) a.idesc = make_idesc_f16(2 * kBlockM, a.block_n, prm->operand_format, 0, 0);
     if (prm->stat_parts != nullptr) {
         NDB_CHECK_ARG(prm->out_kind != NDB_OUT_F32_NCHW);
@@ -887,7 +926,9 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     }
 
     const int stage_bytes = kATileBytes + a.b_rows * 128;
-    const int epi_bytes = kEpiWarps * (kStageFloats * (int)sizeof(float) + 128 * (int)sizeof(long long)) +
+    a.epi_bufs = (a.epi_bulk && a.total_kblocks <= 24) ? 2 : 1;
+    a.epi_region = a.epi_bufs == 2 ? kEpiWarps * 2 * 4096 : kEpiWarps * kStageFloats * (int)sizeof(float);
+    const int epi_bytes = a.epi_region + kEpiWarps * 128 * (int)sizeof(long long) +
                           2 * 4 * a.block_n * (int)sizeof(float2) +
                           (prm->stat_parts ? a.TN * prm->cout * (int)sizeof(float2) : 0);
     const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - epi_bytes;
@@ -928,7 +969,7 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
 extern "C" int ndb_conv_stats_layout(int N, int H, int W, int cout_pad, int block_n, int32_t* counts) {
     if (N <= 0 || H <= 0 || W <= 0 || cout_pad <= 0) return NDB_ERR_INVALID;
     const ConvGeom g = conv_geom(N, H, W);
-    const int bn = block_n > 0 ? block_n : pick_block_n(cout_pad);
+    const int bn = block_n > 0 ? block_n : pick_block_n(cout_pad, g, true);
     if (bn <= 0 || cout_pad % bn != 0) return NDB_ERR_INVALID;
     const int n_tiles = cout_pad / bn;
     const WorkGeom w = work_geom(g, n_tiles, bn, true);
