@@ -97,7 +97,10 @@ gn_stats_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ 
 // ------------------------------------------------------------------------------------------------------
 // apply
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float silu_f(float v) { return v * __frcp_rn(1.f + __expf(-v)); }
+// SiLU with the two special-function approximations (ex2.approx, rcp.approx: ~2 ulp each, far below the 16-bit rounding of
+// the result). The IEEE __frcp_rn costs a Newton step plus a guarded slow-path call per element and made this kernel
+// issue-bound (33 calls per 4-pixel trip in SASS).
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.f + __expf(-v)); }
 
 template <int FMT>
 __device__ __forceinline__ uint32_t pack2h(float a, float b) {
