@@ -118,6 +118,12 @@ def cpu_reference_arm(workload, steps, warmup, sample_batch=None):
         cfg = dict(cfg); cfg['num_classes'] = 1001
     if sample_batch is None:
         sample_batch = {'in64': 2, 'emnist': 16, 'in128': 1}[workload]
+    # all host cores this process may use (torchrun pins OMP_NUM_THREADS=1 in its children; undo that for this arm)
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncores = os.cpu_count() or 1
+    torch.set_num_threads(max(1, ncores))
     sd = random_state_dict(cfg, seed=0)
     okw = {k: v for k, v in dkw.items() if k != 'loss_type'}
 

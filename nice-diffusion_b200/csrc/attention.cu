@@ -1,12 +1,15 @@
 // Fused multi-head self-attention on tcgen05: S = Q K^T and O += P V run on the tensor cores with fp32
-// accumulators in TMEM; the online softmax runs in registers, one query row per thread. The [T,T] score
-// matrix never touches HBM (the reference materialises it: model.py:273-277).
+// accumulators in TMEM; the online softmax runs in registers, two threads per query row (each owns 64 of the 128 keys
+// of a block, read out of TMEM once). The [T,T] score matrix never touches HBM (the reference materialises it:
+// model.py:273-277).
 //
 // One CTA = one (batch, head, 128-query block). Q/K/V tiles are read straight out of the qkv 1x1-conv
 // output ([B][T][3C], fp16) with 4-D TMA boxes {d, column-block, rows, batch}; the inner extent is the true
 // head dim d, so head dims that are not a multiple of 64 are zero-filled up to the next 64 by TMA.
-//   warps 0-3 : softmax + correction + epilogue (thread i owns query row i / TMEM lane i)
-//   warp  4   : one thread issues TMA loads and tcgen05.mma
+//   warps 0-7 : softmax + correction + epilogue. Warp w works on TMEM lane quarter (w & 3) -- query rows 32 (w & 3) .. +31
+//               -- and key half (w >> 2); the two warps of a quarter exchange their row maxima through shared memory
+//               (one 64-thread named barrier per block) and keep separate partial row sums until the end.
+//   warp  8   : one elected thread issues TMA loads and tcgen05.mma
 // TMEM: S at columns [0,128), O at [128,128+Dp).
 // K/V tiles are double-buffered; with d <= 64 two CTAs fit per SM so one CTA's softmax overlaps the other's MMAs.
 #include "common.cuh"
@@ -19,6 +22,7 @@ namespace ndb {
 constexpr int kAttnBM = 128;  // queries per CTA
 constexpr int kAttnBN = 128;  // keys per iteration
 constexpr int kChunkBytes = 128 * 128;  // one [128 rows x 64 x 16-bit] swizzled tile
+constexpr int kAttnThreads = 288;       // 8 softmax warps + 1 TMA/MMA warp
 
 struct AttnArgs {
     int B, T, heads, d, order;
@@ -50,7 +54,8 @@ __device__ __forceinline__ uint32_t pack2a(float a, float b) {
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(160)
+// Two CTAs per SM (shared memory: 2 x ~114 KB); keep the register count under 65536 / (2 * 288) = 113.
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0u) __trap();
@@ -75,8 +80,9 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
     uint64_t* p_full = bars + 6;
     uint64_t* pv_done = bars + 7;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+    uint16_t* xchg = reinterpret_cast<uint16_t*>(bars + 10);   // [2 key halves][128 rows]: row maxima (bf16, rounded up)
 
-    if (threadIdx.x == 128) {
+    if (threadIdx.x == 256) {
         prefetch_tmap(&qkv_map);
         mbar_init(q_full, 1);
         for (int i = 0; i < 2; ++i) {
@@ -84,7 +90,7 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
             mbar_init(&v_full[i], 1);
         }
         mbar_init(s_full, 1);
-        mbar_init(p_full, 128);
+        mbar_init(p_full, 256);
         mbar_init(pv_done, 1);
         fence_barrier_init();
     }
@@ -106,7 +112,7 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
     if (p.order == 0) { cq = h; ck = p.heads + h; cv = 2 * p.heads + h; }
     else { cq = 3 * h; ck = 3 * h + 1; cv = 3 * h + 2; }
 
-    if (warp == 4) {
+    if (warp == 8) {
         // The whole warp runs this warp-uniform loop and one elected lane issues the TMA / MMA instructions, so their
         // descriptor operands stay in uniform registers (no per-instruction R2UR waterfall).
         {
@@ -176,20 +182,31 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
         }
     } else {
         // ===================== softmax / correction / epilogue =====================
-        const int row = warp * 32 + lane;
-        const uint32_t lane_addr = uint32_t(warp * 32) << 16;
-        float m_run = -INFINITY, l_run = 0.f;
+        const int q = warp & 3, hf = warp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = uint32_t(q * 32) << 16;
+        const int key0 = hf * 64;                      // this thread's keys inside a block
+        const int oc_half = Dp >> 1;                   // this warp's O columns: [hf * Dp/2, +Dp/2)
+        float m_run = -INFINITY, l_run = 0.f;          // l_run: partial sum over this thread's keys
+        // 64-thread named barrier of this row quarter (immediate ids: a register id makes ptxas reserve all 16 barriers)
+        auto pair_sync = [&]() {
+            if (q == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+            else if (q == 1) asm volatile("bar.sync 2, 64;" ::: "memory");
+            else if (q == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
+            else asm volatile("bar.sync 4, 64;" ::: "memory");
+        };
         for (int j = 0; j < nkv; ++j) {
             mbar_wait(s_full, j & 1);
             tc_fence_after();
-            const int kv_valid = p.T - j * kAttnBN;  // keys >= kv_valid in this block are padding
-            const bool full = kv_valid >= kAttnBN;
-            // pass 1: row max (four independent chains)
+            const int kv_valid = p.T - j * kAttnBN - key0;  // this thread's keys >= kv_valid are padding
+            const bool full = kv_valid >= 64;
+            // pass 1: maximum over this thread's 64 keys (two 32-column TMEM reads; the scores are read again in pass 2 --
+            // holding all 64 in registers raises the register count past what two resident CTAs allow)
             float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
-            for (int c0 = 0; c0 < kAttnBN; c0 += 32) {
+            for (int c0 = 0; c0 < 64; c0 += 32) {
                 uint32_t r[32];
-                tmem_ld32(tmem_S + lane_addr + c0, r);
+                tmem_ld32(tmem_S + lane_addr + key0 + c0, r);
                 tmem_ld_wait();
                 if (full) {
 #pragma unroll
@@ -200,7 +217,14 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
                         if (c0 + i < kv_valid) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[i]));
                 }
             }
-            const float m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+            // Both warps of a row must use the SAME block maximum. They exchange 16-bit values (the two-CTAs-per-SM shared
+            // memory budget has no room for 1 KB of floats): each side rounds its own maximum UP to bf16 first -- any
+            // upper bound of the scores is a valid softmax shift.
+            uint32_t mu = __float_as_uint(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])));
+            mu = (mu & 0x80000000u) ? (mu & 0xffff0000u) : ((mu + 0xffffu) & 0xffff0000u);
+            xchg[hf * 128 + row] = (uint16_t)(mu >> 16);
+            pair_sync();
+            const float m_blk = fmaxf(__uint_as_float(mu), __uint_as_float((uint32_t)xchg[(hf ^ 1) * 128 + row] << 16));
             const float m_new = fmaxf(m_run, m_blk);
             const float alpha = ex2_fast((m_run - m_new) * p.scale_log2e);  // 0 when m_run = -inf
             const bool need_fix = (j > 0) && (m_new > m_run);
@@ -211,69 +235,86 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
             }
             if (__any_sync(0xffffffffu, need_fix)) {
 #pragma unroll 1
-                for (int c0 = 0; c0 < Dp; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_O + lane_addr + c0, r);
+                for (int c0 = hf * oc_half; c0 < (hf + 1) * oc_half; c0 += 32) {
+                    uint32_t o[32];
+                    tmem_ld32(tmem_O + lane_addr + c0, o);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-                    tmem_st32(tmem_O + lane_addr + c0, r);
+                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    tmem_st32(tmem_O + lane_addr + c0, o);
                 }
                 tmem_st_wait();
             }
             l_run *= alpha;
             m_run = m_new;
-            // pass 2: p = exp2((s - m) * scale*log2e) -> fp16 P tile in the K-major SWIZZLE_128B layout
+            // p = exp2((s - m) * scale*log2e) -> 16-bit P tile in the K-major SWIZZLE_128B layout; this thread's 64 keys are
+            // exactly the 128-byte line of row `row` in K-chunk `hf`
             const float mb = m_new * p.scale_log2e;
             float ls[4] = {0.f, 0.f, 0.f, 0.f};
+            uint8_t* line = sP + hf * kChunkBytes + row * 128;
+            // (two copies of the loop: with the padding test folded in as predication every element pays three extra
+            //  issue slots even when the block is full -- the kernel is issue-bound)
+            if (full) {
 #pragma unroll 1
-            for (int c0 = 0; c0 < kAttnBN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem_S + lane_addr + c0, r);
-                tmem_ld_wait();
-                uint32_t pk[16];
-                if (full) {
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_S + lane_addr + key0 + c0, r);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float p0 = ex2_fast(fmaf(__uint_as_float(r[i]), p.scale_log2e, -mb));
-                        const float p1 = ex2_fast(fmaf(__uint_as_float(r[i + 1]), p.scale_log2e, -mb));
-                        ls[(i >> 1) & 3] += p0 + p1;
-                        pk[i >> 1] = pack2a<FMT>(p0, p1);
-                    }
-                } else {
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t pk[4];
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float p0 = (c0 + i < kv_valid) ? ex2_fast(fmaf(__uint_as_float(r[i]), p.scale_log2e, -mb)) : 0.f;
-                        const float p1 = (c0 + i + 1 < kv_valid) ? ex2_fast(fmaf(__uint_as_float(r[i + 1]), p.scale_log2e, -mb)) : 0.f;
-                        ls[(i >> 1) & 3] += p0 + p1;
-                        pk[i >> 1] = pack2a<FMT>(p0, p1);
+                        for (int k = 0; k < 4; ++k) {
+                            const int i = c * 8 + 2 * k;
+                            const float p0 = ex2_fast(fmaf(__uint_as_float(r[i]), p.scale_log2e, -mb));
+                            const float p1 = ex2_fast(fmaf(__uint_as_float(r[i + 1]), p.scale_log2e, -mb));
+                            ls[k] += p0 + p1;
+                            pk[k] = pack2a<FMT>(p0, p1);
+                        }
+                        *reinterpret_cast<uint4*>(line + ((((c0 >> 3) + c) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
                 }
-                // 32 keys = 64 bytes = four 16-byte chunks of this row's 128-byte line in K-chunk (c0 / 64)
-                uint8_t* line = sP + (c0 >> 6) * kChunkBytes + row * 128;
-                const int chunk0 = (c0 & 63) >> 3;  // first 16-byte chunk index (0 or 4)
+            } else {
+#pragma unroll 1
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_S + lane_addr + key0 + c0, r);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int phys = (chunk0 + q) ^ (row & 7);
-                    *reinterpret_cast<uint4*>(line + phys * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int i = c * 8 + 2 * k;
+                            float p0 = ex2_fast(fmaf(__uint_as_float(r[i]), p.scale_log2e, -mb));
+                            float p1 = ex2_fast(fmaf(__uint_as_float(r[i + 1]), p.scale_log2e, -mb));
+                            if (c0 + i >= kv_valid) p0 = 0.f;
+                            if (c0 + i + 1 >= kv_valid) p1 = 0.f;
+                            ls[k] += p0 + p1;
+                            pk[k] = pack2a<FMT>(p0, p1);
+                        }
+                        *reinterpret_cast<uint4*>(line + ((((c0 >> 3) + c) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
                 }
             }
-            const float l_blk = (ls[0] + ls[1]) + (ls[2] + ls[3]);
-            l_run += l_blk;
+            l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
             fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
             tc_fence_before();
             mbar_arrive(p_full);
         }
-        // ---- epilogue: O / l -> fp16 [B][T][C] ----
-        mbar_wait(pv_done, (nkv - 1) & 1);
+        // ---- epilogue: O / l -> 16-bit [B][T][C]; the row sum is the two key halves' partial sums ----
+        mbar_wait(pv_done, (nkv - 1) & 1);   // the last P V has retired: O is final and the P tile is free
         tc_fence_after();
-        const float inv_l = 1.f / l_run;
+        float* lx = reinterpret_cast<float*>(sP);
+        lx[hf * 128 + row] = l_run;
+        pair_sync();
+        const float inv_l = 1.f / (lx[row] + lx[128 + row]);
         const int qrow = q0 + row;
         uint16_t* orow = p.out + ((size_t)b * p.T + qrow) * p.C + (size_t)h * p.d;
 #pragma unroll 1
-        for (int c0 = 0; c0 < Dp; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_O + lane_addr + c0, r);
+        for (int c0 = hf * oc_half; c0 < (hf + 1) * oc_half; c0 += 32) {
+            uint32_t o[32];
+            tmem_ld32(tmem_O + lane_addr + c0, o);
             tmem_ld_wait();
             if (qrow < p.T) {
 #pragma unroll
@@ -282,7 +323,7 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
                         uint32_t w[4];
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            w[k] = pack2a<FMT>(__uint_as_float(r[i + 2 * k]) * inv_l, __uint_as_float(r[i + 2 * k + 1]) * inv_l);
+                            w[k] = pack2a<FMT>(__uint_as_float(o[i + 2 * k]) * inv_l, __uint_as_float(o[i + 2 * k + 1]) * inv_l);
                         *reinterpret_cast<uint4*>(orow + c0 + i) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
@@ -315,10 +356,10 @@ extern "C" int ndb_attention(const void* qkv, void* out, int B, int T, int heads
     const int Dp = a.dp_chunks * 64;
     a.kv_stages = (a.dp_chunks <= 2) ? 2 : 1;
     // smem: Q + kv_stages*(K+V) + P(2 chunks) + barriers
-    size_t smem = (size_t)(a.dp_chunks * (1 + 2 * a.kv_stages) + 2) * kChunkBytes + 128;
+    size_t smem = (size_t)(a.dp_chunks * (1 + 2 * a.kv_stages) + 2) * kChunkBytes + 640;
     if (smem > 227 * 1024) {
         a.kv_stages = 1;
-        smem = (size_t)(a.dp_chunks * 3 + 2) * kChunkBytes + 128;
+        smem = (size_t)(a.dp_chunks * 3 + 2) * kChunkBytes + 640;
     }
     NDB_CHECK_ARG(smem <= 227 * 1024);
     a.fmt = operand_format;
@@ -347,8 +388,8 @@ extern "C" int ndb_attention(const void* qkv, void* out, int B, int T, int heads
     }
     dim3 grid((T + kAttnBM - 1) / kAttnBM, heads, B);
     if (operand_format == 0)
-        launch_kernel(attention_kernel<0>, grid, dim3(160), smem, (cudaStream_t)stream, 1, map, a);
+        launch_kernel(attention_kernel<0>, grid, dim3(kAttnThreads), smem, (cudaStream_t)stream, 1, map, a);
     else
-        launch_kernel(attention_kernel<1>, grid, dim3(160), smem, (cudaStream_t)stream, 1, map, a);
+        launch_kernel(attention_kernel<1>, grid, dim3(kAttnThreads), smem, (cudaStream_t)stream, 1, map, a);
     return launch_status("ndb_attention");
 }
