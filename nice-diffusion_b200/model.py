@@ -18,6 +18,7 @@ snapshot is refreshed automatically when any parameter's storage or version chan
 There is no CPU / eager fallback: calling forward on a CPU tensor raises.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -188,7 +189,7 @@ class DiffusionModel(nn.Module):
         # store the ResBlock-internal tensor h (in_conv output) in 16 bits: supported, but measured no faster on B200
         # (the apply kernel is latency- not bandwidth-bound and 2-byte epilogue stores are slower) and it costs ~20 %
         # of the error budget, so it is off
-        self.h_fp16 = False
+        self.h_fp16 = bool(int(os.environ.get('NDB_H_FP16', '0')))
         self._engines = {}
 
     # ------------------------------------------------------------------------------------------

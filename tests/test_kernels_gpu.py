@@ -144,6 +144,67 @@ def test_conv_epilogue_fused_groupnorm_statistics(cuda_dev, N, H, W, Cin, Cout, 
     assert rel_err(a.permute(0, 3, 1, 2), ref) < 1.5e-3 and rel_err(bq.permute(0, 3, 1, 2), ref) < 1.5e-3
 
 
+EPI_CASES = [
+    # N, H, W, Cin, Cout: every pixel-box shape of the staged TMA-store epilogue (W = 8, 16, 32, 64, 128), an odd batch
+    # (leftover half tile in CTA-pair mode), a ragged image (legacy epilogue) and a channel count that is not a multiple of 32
+    (5, 8, 8, 64, 192), (3, 16, 16, 64, 192), (2, 32, 32, 64, 384), (1, 64, 64, 64, 192), (1, 8, 128, 64, 256),
+    (3, 14, 14, 64, 192), (2, 16, 16, 64, 144),
+]
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout', EPI_CASES)
+def test_conv_epilogue_variants(cuda_dev, N, H, W, Cin, Cout):
+    """Same GEMM through every epilogue flavour: BLOCK_N x {plain, residual} x {no statistics, statistics} x {fp32, fp16}."""
+    ops, L = _ops()
+    g = torch.Generator(device='cpu').manual_seed(N * 7 + H + Cout)
+    x = torch.randn(N, Cin, H, W, generator=g).to(cuda_dev)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)).to(cuda_dev)
+    b = (0.3 * torch.randn(Cout, generator=g)).to(cuda_dev)
+    r = torch.randn(N, Cout, H, W, generator=g).to(cuda_dev)
+    x16, wp = nhwc(x).half(), ops.pack_conv_weight(w)
+    base = F.conv2d(x.half().float(), w.half().float(), b, padding=1)
+    for bn in (0, 256, 192, 128, 96, 64, 48):
+        if bn and Cout % bn:
+            continue
+        for res in (False, True):
+            ref = base + r if res else base
+            rr = nhwc(r) if res else None
+            out = ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, residual=rr, residual_mode=L.RES_SAME, block_n=bn)
+            assert rel_err(out.permute(0, 3, 1, 2), ref) < 2e-5, (bn, res)
+            if ops.conv_stats_supported(N, H, W):
+                st = ops.conv_stats_alloc(N, H, W, Cout, cuda_dev, block_n=bn)
+                st[0].fill_(float('nan'))
+                out2 = ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, residual=rr, residual_mode=L.RES_SAME, stats=st,
+                                     block_n=bn)
+                assert torch.equal(out, out2), (bn, res)
+                o = out2.double().flatten(1, 2)
+                tot = ops.stats_totals(st)
+                assert torch.allclose(tot[:, :, 0], o.sum(1), rtol=1e-5, atol=2e-3), (bn, res)
+                assert torch.allclose(tot[:, :, 1], (o * o).sum(1), rtol=1e-5, atol=2e-3), (bn, res)
+            if not res:
+                o16 = ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, out_kind=L.OUT_F16_NHWC, block_n=bn)
+                assert torch.equal(o16, out.half()), bn     # same fp32 value, one rounding
+
+
+def test_conv_short_k_many_tiles(cuda_dev):
+    """1x1 GEMM with few K blocks and many tiles per CTA: the double-buffered staging tiles and the residual prefetch that
+    runs one chunk ahead across tile boundaries (the qkv / proj shapes of the attention blocks)."""
+    ops, L = _ops()
+    g = torch.Generator(device='cpu').manual_seed(77)
+    N, H, W, Cin, Cout = 8, 32, 32, 128, 768
+    x = torch.randn(N, Cin, H, W, generator=g).to(cuda_dev)
+    w = (torch.randn(Cout, Cin, 1, 1, generator=g) / math.sqrt(Cin)).to(cuda_dev)
+    b = (0.3 * torch.randn(Cout, generator=g)).to(cuda_dev)
+    r = torch.randn(N, Cout, H, W, generator=g).to(cuda_dev)
+    x16, wp = nhwc(x).half(), ops.pack_conv_weight(w)
+    base = F.conv2d(x.half().float(), w.half().float(), b)
+    for bn in (0, 64, 192):
+        out = ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, residual=nhwc(r), residual_mode=L.RES_SAME, block_n=bn)
+        assert rel_err(out.permute(0, 3, 1, 2), base + r) < 2e-5, bn
+        o16 = ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, out_kind=L.OUT_F16_NHWC, block_n=bn)
+        assert rel_err(o16.permute(0, 3, 1, 2), base) < 1e-3, bn
+
+
 def test_linear_as_gemm(cuda_dev):
     """The per-ResBlock step_embedding Linear layers run as one 1x1 'conv' over a [1,1,B,E] image."""
     ops, L = _ops()
@@ -249,6 +310,27 @@ def test_attention(cuda_dev, B, T, heads, d, order):
     w = torch.softmax((q @ k.transpose(2, 3)) * d ** -0.5, dim=-1)
     ref = (w @ v).transpose(1, 2).reshape(B, T, C)
     assert rel_err(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize('T,gain', [(384, 6.0), (200, 12.0)])
+def test_attention_peaky_scores(cuda_dev, T, gain):
+    """Large, growing scores: every key block raises the running maximum (O is rescaled each block), the two threads of
+    a row hold very different partial maxima / sums, and the last block is padded."""
+    ops, L = _ops()
+    g = torch.Generator(device='cpu').manual_seed(T)
+    B, heads, d = 2, 2, 64
+    C = heads * d
+    qkv = torch.randn(B, T, 3 * C, generator=g)
+    ramp = torch.linspace(0.2, 1.0, T).view(1, T, 1)
+    qkv[:, :, C:2 * C] *= gain * ramp                      # later keys score higher
+    qkv = qkv.to(cuda_dev).half()
+    out = ops.attention(qkv, B, T, heads, d, order=0)
+    f = qkv.float()
+    q, k, v = f.reshape(B, T, 3, heads, d).permute(2, 0, 3, 1, 4).unbind(0)
+    w = torch.softmax((q @ k.transpose(2, 3)) * d ** -0.5, dim=-1)
+    ref = (w @ v).transpose(1, 2).reshape(B, T, C)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out, ref) < 3e-3
 
 
 def test_embed(cuda_dev):
