@@ -97,10 +97,16 @@ gn_stats_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ 
 // ------------------------------------------------------------------------------------------------------
 // apply
 // ------------------------------------------------------------------------------------------------------
-// SiLU with the two special-function approximations (ex2.approx, rcp.approx: ~2 ulp each, far below the 16-bit rounding of
-// the result). The IEEE __frcp_rn costs a Newton step plus a guarded slow-path call per element and made this kernel
-// issue-bound (33 calls per 4-pixel trip in SASS).
-__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+// SiLU(v) = v * sigmoid(v) = h + h * tanh(h) with h = v / 2: ONE special-function op (tanh.approx, |error| <= 2^-10.99
+// relative -- the size of the 16-bit rounding applied to the result right after) and two FMA-pipe ops. The exact
+// v / (1 + exp(-v)) form needs two MUFU ops per element (ex2 + rcp), which kept the XU pipe at > 50 % and this kernel
+// issue-bound; the IEEE reciprocal before that cost a guarded slow-path call per element.
+__device__ __forceinline__ float silu_f(float v) {
+    const float h = 0.5f * v;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
 
 template <int FMT>
 __device__ __forceinline__ uint32_t pack2h(float a, float b) {
