@@ -101,8 +101,8 @@ gn_stats_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ 
 // relative -- the size of the 16-bit rounding applied to the result right after) and two FMA-pipe ops. The exact
 // v / (1 + exp(-v)) form needs two MUFU ops per element (ex2 + rcp), which kept the XU pipe at > 50 % and this kernel
 // issue-bound; the IEEE reciprocal before that cost a guarded slow-path call per element.
-__device__ __forceinline__ float silu_f(float v) {
-    const float h = 0.5f * v;
+// takes h = v / 2 (the factor is folded into the per-channel affine coefficients)
+__device__ __forceinline__ float silu_half(float h) {
     float t;
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
     return fmaf(h, t, h);
@@ -277,6 +277,7 @@ gn_apply_kernel(const GnApplyArgs p) {
             ak *= s1;
             bk = bk * s1 + __ldg(p.shift + (size_t)n * p.ld_ss + c);
         }
+        if (SILU) { ak *= 0.5f; bk *= 0.5f; }   // SiLU is evaluated from v / 2 (silu_half)
         sa[c] = ak; sb[c] = bk;
         if (RAW) sp[c] = pr;
     }
@@ -322,7 +323,7 @@ gn_apply_kernel(const GnApplyArgs p) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         float t = a[k] * xv[q][k] + b[k];
-                        if (SILU) t = silu_f(t);
+                        if (SILU) t = silu_half(t);
                         acc += t;
                         if (RAW) racc += xv[q][k] + pre[k];
                     }
@@ -346,34 +347,81 @@ gn_apply_kernel(const GnApplyArgs p) {
                 }
             }
         } else {
-            for (int po = p_begin + r; po < p_end; po += U * p.rows_per_block) {
-                if (!(v == tv && po == p_begin + r)) {   // the very first trip was requested before the prologue
+            // this thread's pixels: p_begin + r, + rows_per_block, ... ; element offsets advance by constant strides (no
+            // per-pixel 64-bit index arithmetic in the loop)
+            const int rows = p.rows_per_block;
+            int cnt = (p_end - (p_begin + r) + rows - 1) / rows;           // > 0 for workers with a pixel
+            const size_t esz = IN16 ? 2 : 4;
+            const uint32_t out_stride = (uint32_t)rows * (uint32_t)C;       // elements between two of this thread's pixels
+            uint16_t* op = outq + (size_t)(p_begin + r) * C;
+            uint16_t* rp = RAW ? rawq + (size_t)(p_begin + r) * C : nullptr;
+            bool first = (v == tv);                                        // the very first trip was requested before the prologue
+            if (RESAMPLE == NDB_RESAMPLE_NONE) {
+                const uint32_t in_stride = (uint32_t)rows * (uint32_t)ldc * (uint32_t)esz;   // bytes
+                const char* ip = reinterpret_cast<const char*>(srcp) + (size_t)(p_begin + r) * ldc * esz;
+                for (; cnt > 0; cnt -= U, ip += (size_t)U * in_stride, op += (size_t)U * out_stride, rp += RAW ? (size_t)U * out_stride : 0) {
+                    if (!first) {
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            if (u < cnt) {
+                                const char* px = ip + u * in_stride;
+                                lo[u] = __ldg(reinterpret_cast<const uint4*>(px));
+                                if (!IN16) hi[u] = __ldg(reinterpret_cast<const uint4*>(px + 16));
+                            }
+                        }
+                    }
+                    first = false;
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        const int pu = po + u * p.rows_per_block;
-                        if (pu < p_end) load8(srcp, ldc, in_pixel(pu), lo[u], hi[u]);
+                        if (u < cnt) {
+                            float xv[8];
+                            unpack8(lo[u], hi[u], xv);
+                            float y[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const float t = fmaf(a[k], xv[k], b[k]);
+                                y[k] = SILU ? silu_half(t) : t;
+                            }
+                            *reinterpret_cast<uint4*>(op + u * out_stride) = make_uint4(pack2h<FMT>(y[0], y[1]), pack2h<FMT>(y[2], y[3]),
+                                                                                        pack2h<FMT>(y[4], y[5]), pack2h<FMT>(y[6], y[7]));
+                            if (RAW)
+                                *reinterpret_cast<uint4*>(rp + u * out_stride) =
+                                    make_uint4(pack2h<FMT>(xv[0] + pre[0], xv[1] + pre[1]), pack2h<FMT>(xv[2] + pre[2], xv[3] + pre[3]),
+                                               pack2h<FMT>(xv[4] + pre[4], xv[5] + pre[5]), pack2h<FMT>(xv[6] + pre[6], xv[7] + pre[7]));
+                        }
                     }
                 }
+            } else {
+                // nearest-neighbour x2: the source pixel of an output pixel is not an affine function of its index
+                for (int po = p_begin + r; po < p_end; po += U * rows) {
+                    if (!first) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int pu = po + u * p.rows_per_block;
-                    if (pu < p_end) {
-                        float xv[8];
-                        unpack8(lo[u], hi[u], xv);
-                        float y[8];
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            float t = a[k] * xv[k] + b[k];
-                            if (SILU) t = silu_f(t);
-                            y[k] = t;
+                        for (int u = 0; u < U; ++u) {
+                            const int pu = po + u * rows;
+                            if (pu < p_end) load8(srcp, ldc, in_pixel(pu), lo[u], hi[u]);
                         }
-                        const size_t o = (size_t)pu * C;
-                        *reinterpret_cast<uint4*>(outq + o) = make_uint4(pack2h<FMT>(y[0], y[1]), pack2h<FMT>(y[2], y[3]),
-                                                                         pack2h<FMT>(y[4], y[5]), pack2h<FMT>(y[6], y[7]));
-                        if (RAW)
-                            *reinterpret_cast<uint4*>(rawq + o) =
-                                make_uint4(pack2h<FMT>(xv[0] + pre[0], xv[1] + pre[1]), pack2h<FMT>(xv[2] + pre[2], xv[3] + pre[3]),
-                                           pack2h<FMT>(xv[4] + pre[4], xv[5] + pre[5]), pack2h<FMT>(xv[6] + pre[6], xv[7] + pre[7]));
+                    }
+                    first = false;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int pu = po + u * rows;
+                        if (pu < p_end) {
+                            float xv[8];
+                            unpack8(lo[u], hi[u], xv);
+                            float y[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const float t = fmaf(a[k], xv[k], b[k]);
+                                y[k] = SILU ? silu_half(t) : t;
+                            }
+                            const size_t o = (size_t)pu * C;
+                            *reinterpret_cast<uint4*>(outq + o) = make_uint4(pack2h<FMT>(y[0], y[1]), pack2h<FMT>(y[2], y[3]),
+                                                                             pack2h<FMT>(y[4], y[5]), pack2h<FMT>(y[6], y[7]));
+                            if (RAW)
+                                *reinterpret_cast<uint4*>(rawq + o) =
+                                    make_uint4(pack2h<FMT>(xv[0] + pre[0], xv[1] + pre[1]), pack2h<FMT>(xv[2] + pre[2], xv[3] + pre[3]),
+                                               pack2h<FMT>(xv[4] + pre[4], xv[5] + pre[5]), pack2h<FMT>(xv[6] + pre[6], xv[7] + pre[7]));
+                        }
                     }
                 }
             }
