@@ -308,6 +308,18 @@ def main():
                                  'what': 'algorithmic FLOPs of one UNet forward x batch / graph-replayed step time'},
                 'other_kernels_ms': {k: v['ms'] for k, v in prof.items() if isinstance(v, dict) and k != 'conv_gemm'}}
 
+    # DRAM traffic of the dominant kernel: from the committed ncu pass of the same step (profiles/), not measured live
+    try:
+        import glob
+        cand = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', '*_conv_traffic.json')))
+        if cand and args.config == 'in64' and B == WORKLOADS['in64'][2]:
+            tr = json.load(open(cand[-1]))
+            roofline['traffic'] = tr['dram_bytes_per_launch_avg']
+            roofline['traffic_unit'] = 'bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the %d ' \
+                                       'conv_gemm launches of one step; %s)' % (tr['launches'], os.path.basename(cand[-1]))
+    except Exception:
+        pass
+
     cpu = None
     if not args.no_cpu_baseline:
         r = cpu_reference_arm(args.config, 2, 1)

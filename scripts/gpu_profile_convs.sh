@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 CMD="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --eager"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -20 gpurun_out/plain_$TAG.log; exit 1; }
 NDB_CUDA_PROFILER=1 ncu --profile-from-start off --clock-control none -k regex:$KRE \
-    --section SpeedOfLight --section WarpStateStats --section SchedulerStats --section MemoryWorkloadAnalysis --section LaunchStats \
+    --metrics dram__bytes_read.sum,dram__bytes_write.sum --section SpeedOfLight --section WarpStateStats --section SchedulerStats --section MemoryWorkloadAnalysis --section LaunchStats \
     -f -o gpurun_out/sections_$TAG $CMD > gpurun_out/ncu_sections_$TAG.log 2>&1
 echo "sections rc=$?"; tail -2 gpurun_out/ncu_sections_$TAG.log
 ls -la gpurun_out | grep $TAG

@@ -42,3 +42,62 @@ for f in ('bench_%s.json' % tag, 'bench_ref_%s.json' % tag):
     if os.path.exists(os.path.join(src, f)):
         shutil.copy(os.path.join(src, f), os.path.join(dst, f))
 print('\n'.join(out)); print('\n'.join(txt))
+
+# ---- extras (when present): per-launch sections of every conv GEMM, gn_apply / attention captures, other bench lines
+def raw_rows(rep):
+    r = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rr = list(csv.reader(r.splitlines()))
+    return (rr[0], rr[1], rr[2:]) if len(rr) > 2 else (None, None, [])
+
+
+sec = os.path.join(src, 'sections_convs_%s.ncu-rep' % tag)
+if os.path.exists(sec):
+    h, u, rows_ = raw_rows(sec)
+    cols = ['launch__grid_size', 'launch__cluster_size', 'gpu__time_duration.sum', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+            'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_active',
+            'smsp__issue_active.avg.pct_of_peak_sustained_active', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+            'launch__shared_mem_per_block_dynamic']
+    cols = [c for c in cols if c in h]
+    with open(os.path.join(dst, '%s_conv_sections.csv' % tag), 'w') as f:
+        w = csv.writer(f)
+        w.writerow(['launch'] + ['%s [%s]' % (c, u[h.index(c)]) for c in cols])
+        tot_t = tot_b = 0.0
+        for i, r in enumerate(rows_):
+            w.writerow([i] + [r[h.index(c)] for c in cols])
+            tot_t += float(r[h.index('gpu__time_duration.sum')])
+            if 'dram__bytes_read.sum' in h:
+                def tobytes(v, unit):
+                    return float(v) * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[unit]
+                tot_b += tobytes(r[h.index('dram__bytes_read.sum')], u[h.index('dram__bytes_read.sum')]) + \
+                    tobytes(r[h.index('dram__bytes_write.sum')], u[h.index('dram__bytes_write.sum')])
+    n = len(rows_)
+    json.dump({'kernel': 'conv_gemm_kernel', 'launches': n, 'sum_gpu_time_us': tot_t, 'dram_bytes_per_launch_avg': tot_b / max(n, 1),
+               'dram_bytes_per_step': tot_b, 'source': 'ncu dram__bytes_read.sum + dram__bytes_write.sum over the %d launches of one step' % n},
+              open(os.path.join(dst, '%s_conv_traffic.json' % tag), 'w'), indent=1)
+    print('conv sections: %d launches, %.1f us, %.1f MB DRAM traffic per launch' % (n, tot_t, tot_b / max(n, 1) / 1e6))
+
+for kname in ('gn', 'attn'):
+    rep = os.path.join(src, 'prof_%s_%s.ncu-rep' % (kname, tag))
+    if not os.path.exists(rep):
+        continue
+    h, u, rows_ = raw_rows(rep)
+    want2 = ['Kernel Name', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread', 'gpu__time_duration.sum',
+             'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+             'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+             'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+             'smsp__inst_executed.sum', 'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_registers',
+             'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+             'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+             'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio']
+    t2 = ['ncu --set full --clock-control none --import-source on; units: ' +
+          ', '.join('%s[%s]' % (x, u[h.index(x)]) for x in want2 if x in h and u[h.index(x)])]
+    for r in rows_:
+        t2.append('---')
+        for x in want2:
+            if x in h:
+                t2.append('  %-80s %s' % (x, r[h.index(x)][:90]))
+    open(os.path.join(dst, '%s_%s_kernel_ncu.txt' % (tag, kname)), 'w').write('\n'.join(t2) + '\n')
+for f in ('bench_emnist_%s.json' % tag, 'bench_in128_%s.json' % tag, 'layers_%s.txt' % tag, 'bench_n2_%s.json' % tag,
+          'bench_ref_n2_%s.json' % tag):
+    if os.path.exists(os.path.join(src, f)):
+        shutil.copy(os.path.join(src, f), os.path.join(dst, f))
