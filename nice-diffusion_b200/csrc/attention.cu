@@ -79,7 +79,8 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
     uint64_t* s_full = bars + 5;
     uint64_t* p_full = bars + 6;
     uint64_t* pv_done = bars + 7;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* s_free = bars + 8;     // all softmax threads have pulled S_j out of TMEM: S_{j+1} may overwrite it
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
     uint16_t* xchg = reinterpret_cast<uint16_t*>(bars + 10);   // [2 key halves][128 rows]: row maxima (bf16, rounded up)
 
     if (threadIdx.x == 256) {
@@ -92,6 +93,7 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
         mbar_init(s_full, 1);
         mbar_init(p_full, 256);
         mbar_init(pv_done, 1);
+        mbar_init(s_free, 256);
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -129,31 +131,34 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
             load_tile(sK, &k_full[0], ck, 0);
             load_tile(sV, &v_full[0], cv, 0);
             mbar_wait(q_full, 0);
+            auto issue_S = [&](int j) {      // S = Q K_j^T into TMEM (K tile j must have been requested)
+                const int st = (p.kv_stages == 2) ? (j & 1) : 0;
+                const uint32_t use_parity = (p.kv_stages == 2) ? ((j >> 1) & 1) : (j & 1);
+                mbar_wait(&k_full[st], use_parity);
+                tc_fence_after();
+                const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + st * dpc * kChunkBytes);
+                if (elect_one()) {
+                    for (int i = 0; i < Dp / 16; ++i) {
+                        const uint32_t off = (i >> 2) * kChunkBytes + (i & 3) * 32;
+                        umma_f16(tmem_S, make_desc_k_sw128(qa + off), make_desc_k_sw128(ka + off), p.idesc_qk, i ? 1u : 0u);
+                    }
+                    umma_commit(s_full);
+                }
+                __syncwarp();
+            };
+            issue_S(0);
             for (int j = 0; j < nkv; ++j) {
                 const int st = (p.kv_stages == 2) ? (j & 1) : 0;
                 const uint32_t use_parity = (p.kv_stages == 2) ? ((j >> 1) & 1) : (j & 1);
-                // ---- S = Q K_j^T ----
-                mbar_wait(&k_full[st], use_parity);
-                tc_fence_after();
-                {
-                    const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + st * dpc * kChunkBytes);
-                    if (elect_one()) {
-                        for (int i = 0; i < Dp / 16; ++i) {
-                            const uint32_t off = (i >> 2) * kChunkBytes + (i & 3) * 32;
-                            umma_f16(tmem_S, make_desc_k_sw128(qa + off), make_desc_k_sw128(ka + off), p.idesc_qk, i ? 1u : 0u);
-                        }
-                        umma_commit(s_full);
-                    }
-                    __syncwarp();
-                }
-                // ---- prefetch K/V for block j+1 ----
-                if (j + 1 < nkv) {
-                    const int st2 = (p.kv_stages == 2) ? ((j + 1) & 1) : 0;
-                    if (p.kv_stages == 2) {
-                        if (j >= 1) mbar_wait(pv_done, (j - 1) & 1);  // stage st2 was last read by block j-1
-                        load_tile(sK + st2 * dpc * kChunkBytes, &k_full[st2], ck, (j + 1) * kAttnBN);
-                        load_tile(sV + st2 * dpc * kChunkBytes, &v_full[st2], cv, (j + 1) * kAttnBN);
-                    }
+                if (j + 1 < nkv && p.kv_stages == 2) {
+                    // ---- prefetch K/V for block j+1 (its stage was last read by block j-1) ----
+                    const int st2 = (j + 1) & 1;
+                    if (j >= 1) mbar_wait(pv_done, (j - 1) & 1);
+                    load_tile(sK + st2 * dpc * kChunkBytes, &k_full[st2], ck, (j + 1) * kAttnBN);
+                    load_tile(sV + st2 * dpc * kChunkBytes, &v_full[st2], cv, (j + 1) * kAttnBN);
+                    // ---- S_{j+1} as soon as the softmax warps hold S_j in registers: it runs under their exp phase ----
+                    mbar_wait(s_free, j & 1);
+                    issue_S(j + 1);
                 }
                 // ---- O += P_j V_j ----
                 mbar_wait(p_full, j & 1);
@@ -177,6 +182,8 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
                     mbar_wait(pv_done, j & 1);
                     load_tile(sK, &k_full[0], ck, (j + 1) * kAttnBN);
                     load_tile(sV, &v_full[0], cv, (j + 1) * kAttnBN);
+                    mbar_wait(s_free, j & 1);
+                    issue_S(j + 1);
                 }
             }
         }
@@ -252,49 +259,44 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
             const float mb = m_new * p.scale_log2e;
             float ls[4] = {0.f, 0.f, 0.f, 0.f};
             uint8_t* line = sP + hf * kChunkBytes + row * 128;
-            // (two copies of the loop: with the padding test folded in as predication every element pays three extra
-            //  issue slots even when the block is full -- the kernel is issue-bound)
+            // pass 2 pulls all 64 scores into registers and releases S at once, so the S_{j+1} MMA overlaps the exp phase.
+            // (Two copies of the exp loop: with the padding test folded in as predication every element pays three extra
+            //  issue slots even when the block is full -- the kernel is issue-bound.)
+            uint32_t r[64];
+            tmem_ld32(tmem_S + lane_addr + key0, r);
+            tmem_ld32(tmem_S + lane_addr + key0 + 32, r + 32);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(s_free);
             if (full) {
-#pragma unroll 1
-                for (int c0 = 0; c0 < 64; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_S + lane_addr + key0 + c0, r);
-                    tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint32_t pk[4];
+                for (int c = 0; c < 8; ++c) {
+                    uint32_t pk[4];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int i = c * 8 + 2 * k;
-                            const float p0 = ex2_fast(fmaf(__uint_as_float(r[i]), p.scale_log2e, -mb));
-                            const float p1 = ex2_fast(fmaf(__uint_as_float(r[i + 1]), p.scale_log2e, -mb));
-                            ls[k] += p0 + p1;
-                            pk[k] = pack2a<FMT>(p0, p1);
-                        }
-                        *reinterpret_cast<uint4*>(line + ((((c0 >> 3) + c) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = c * 8 + 2 * k;
+                        const float p0 = ex2_fast(fmaf(__uint_as_float(r[i]), p.scale_log2e, -mb));
+                        const float p1 = ex2_fast(fmaf(__uint_as_float(r[i + 1]), p.scale_log2e, -mb));
+                        ls[k] += p0 + p1;
+                        pk[k] = pack2a<FMT>(p0, p1);
                     }
+                    *reinterpret_cast<uint4*>(line + ((c ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
             } else {
-#pragma unroll 1
-                for (int c0 = 0; c0 < 64; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_S + lane_addr + key0 + c0, r);
-                    tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint32_t pk[4];
+                for (int c = 0; c < 8; ++c) {
+                    uint32_t pk[4];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int i = c * 8 + 2 * k;
-                            float p0 = ex2_fast(fmaf(__uint_as_float(r[i]), p.scale_log2e, -mb));
-                            float p1 = ex2_fast(fmaf(__uint_as_float(r[i + 1]), p.scale_log2e, -mb));
-                            if (c0 + i >= kv_valid) p0 = 0.f;
-                            if (c0 + i + 1 >= kv_valid) p1 = 0.f;
-                            ls[k] += p0 + p1;
-                            pk[k] = pack2a<FMT>(p0, p1);
-                        }
-                        *reinterpret_cast<uint4*>(line + ((((c0 >> 3) + c) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = c * 8 + 2 * k;
+                        float p0 = ex2_fast(fmaf(__uint_as_float(r[i]), p.scale_log2e, -mb));
+                        float p1 = ex2_fast(fmaf(__uint_as_float(r[i + 1]), p.scale_log2e, -mb));
+                        if (i >= kv_valid) p0 = 0.f;
+                        if (i + 1 >= kv_valid) p1 = 0.f;
+                        ls[k] += p0 + p1;
+                        pk[k] = pack2a<FMT>(p0, p1);
                     }
+                    *reinterpret_cast<uint4*>(line + ((c ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
             }
             l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
