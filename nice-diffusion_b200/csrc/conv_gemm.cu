@@ -225,17 +225,23 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            // K-major SWIZZLE_128B descriptor (see make_desc_k_sw128): constant high word, low word = (address >> 4) | LBO
+            constexpr uint64_t kDescHi = (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61) | (uint64_t(1) << 16);
+            const uint32_t desc_lo0 = (smem_u32(smem) & 0x3FFFF) >> 4;
+            const uint32_t desc_step = (uint32_t)stage_bytes >> 4;
             for (int tile = tile_begin; tile < tile_end; ++tile) {
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
+                // The issue loop is the critical path for narrow N tiles (4 MMAs of 48..96 cycles per K block): the operand
+                // descriptors advance by one multiply-add per stage.
                 for (int kb = 0; kb < p.total_kblocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-                    const uint64_t adesc = make_desc_k_sw128(sa);
-                    const uint64_t bdesc = make_desc_k_sw128(sa + kATileBytes);
+                    const uint32_t a_lo = desc_lo0 + (uint32_t)stage * desc_step;
                     if (elect_one()) {
+                        const uint64_t adesc = kDescHi | a_lo;
+                        const uint64_t bdesc = kDescHi | (a_lo + (uint32_t)(kATileBytes >> 4));
 #pragma unroll
                         for (int k = 0; k < kBlockK / 16; ++k) {
                             if (p.dbg & 2) break;

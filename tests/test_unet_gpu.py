@@ -103,3 +103,35 @@ def test_weight_refresh_and_errors(cuda_dev):
     # no CPU fallback
     with pytest.raises(_lib.NdbError):
         model(x, t, y)
+
+
+def test_full_size_batch_properties_in64(cuda_dev):
+    """BASELINE size (ImageNet-64 UNet, 32 images per GPU), checked through properties that do not need the CPU oracle:
+    * the golden sample of the reference, embedded at two positions of a full batch, still matches the reference output;
+    * a sample's output does not depend on its batch neighbours or position (per-sample GroupNorm / attention): rows of
+      the B=32 run equal the same samples run as a batch of 2 up to operand-rounding noise (a different tile -> CTA
+      assignment changes the fp32 summation order of the GroupNorm statistics by ~1e-7, which flips the fp16 rounding of a
+      few operands downstream: same order as the 16-bit error budget, far below a real cross-sample leak, which is O(1));
+    * re-running the full batch (graph replay) is bit-identical."""
+    cfg, sd, model = build('in64', 1234, cuda_dev)
+    g = np.load(os.path.join(GOLD, 'unet_in64.npz'))
+    gx, gt, gy = (torch.from_numpy(g[k]) for k in ('x', 't', 'y'))
+    ref = torch.from_numpy(g['out'])
+    B = 32
+    gen = torch.Generator(device='cpu').manual_seed(99)
+    x = torch.randn(B, 3, 64, 64, generator=gen)
+    t = torch.tensor([2.0 + 4 * (i % 250) for i in range(B)])          # entries of the R=250 timestep map
+    y = torch.randint(0, 1000, (B,), generator=gen)
+    n = gx.shape[0]
+    for pos in (0, B - n):
+        x[pos:pos + n], t[pos:pos + n], y[pos:pos + n] = gx, gt.float(), gy
+    d = cuda_dev
+    with torch.no_grad():
+        full = model(x.to(d), t.to(d), y.to(d))
+        again = model(x.to(d), t.to(d), y.to(d))
+        pair = model(x[5:7].to(d), t[5:7].to(d), y[5:7].to(d))
+    assert torch.equal(full, again)
+    for pos in (0, B - n):
+        assert norm_err(full[pos:pos + n].cpu(), ref) < TOL
+    assert norm_err(full[5:7].cpu(), pair.cpu()) < 1.5e-3
+    assert torch.isfinite(full).all()
