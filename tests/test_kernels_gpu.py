@@ -205,6 +205,61 @@ def test_conv_short_k_many_tiles(cuda_dev):
         assert rel_err(o16.permute(0, 3, 1, 2), base) < 1e-3, bn
 
 
+def _guarded(shape, dtype, dev, guard=4096):
+    """A tensor carved out of a larger NaN-filled buffer: returns (view, check) where check() asserts that nothing outside
+    the view was written (compute-sanitizer stand-in for the stores the kernels issue, TMA boxes included)."""
+    n = int(np.prod(shape))
+    big = torch.full((n + 2 * guard,), float('nan'), dtype=dtype, device=dev)
+    view = big[guard:guard + n].view(*shape)
+
+    def check(full=True):
+        torch.cuda.synchronize()
+        assert torch.isnan(big[:guard].float()).all() and torch.isnan(big[guard + n:].float()).all(), 'out-of-bounds write'
+        if full:
+            assert torch.isfinite(view.float()).all(), 'unwritten output element'
+    return view, check
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout', [(5, 8, 8, 64, 192), (3, 16, 16, 64, 96), (1, 64, 64, 64, 64), (3, 14, 14, 64, 80),
+                                            (1, 8, 8, 64, 192), (7, 32, 32, 64, 40)])
+def test_kernels_write_exactly_their_outputs(cuda_dev, N, H, W, Cin, Cout):
+    """Guard-band check of every store path: GEMM epilogues (TMA boxes clipped at image / channel borders, the all-padding
+    half tile of an odd CTA pair, legacy per-row stores), statistics slots, GroupNorm apply, attention."""
+    ops, L = _ops()
+    g = torch.Generator(device='cpu').manual_seed(N + Cout)
+    x16 = torch.randn(N, H, W, Cin, generator=g).to(cuda_dev).half()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)).to(cuda_dev)
+    wp = ops.pack_conv_weight(w)
+    b = torch.randn(Cout, generator=g).to(cuda_dev)
+    r = torch.randn(N, H, W, Cout, generator=g).to(cuda_dev)
+    for kind, dt, shape in ((L.OUT_F32_NHWC, torch.float32, (N, H, W, Cout)), (L.OUT_F16_NHWC, torch.float16, (N, H, W, Cout)),
+                            (L.OUT_F32_NCHW, torch.float32, (N, Cout, H, W))):
+        for res in ((None, r) if kind == L.OUT_F32_NHWC else (None,)):
+            out, chk = _guarded(shape, dt, cuda_dev)
+            ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, residual=res, residual_mode=L.RES_SAME, out_kind=kind, out=out)
+            chk()
+    if ops.conv_stats_supported(N, H, W) and Cout % 32 == 0:
+        st = ops.conv_stats_alloc(N, H, W, Cout, cuda_dev)
+        parts, chk_p = _guarded(tuple(st[0].shape), torch.float32, cuda_dev)
+        out, chk = _guarded((N, H, W, Cout), torch.float32, cuda_dev)
+        ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, residual=r, residual_mode=L.RES_SAME, out=out, stats=(parts,) + tuple(st[1:]))
+        chk()
+        chk_p(full=False)                 # slots an image does not use stay untouched; the guard band must too
+        cnt = st[1]
+        for n in range(N):
+            assert torch.isfinite(parts[n, :int(cnt[n])]).all()
+        gamma = torch.ones(Cout, device=cuda_dev); beta = torch.zeros(Cout, device=cuda_dev)
+        a, chk_a = _guarded((N, H, W, Cout), torch.float16, cuda_dev)
+        ops.gn_apply(out, (parts,) + tuple(st[1:]), gamma, beta, silu=True, out=a)
+        chk_a()
+    if Cout % 64 == 0 or Cout % 32 == 0:
+        heads, d = 1, 32
+        qkv = torch.randn(N, H * W, 3 * heads * d, generator=g).to(cuda_dev).half()
+        o, chk_o = _guarded((N, H * W, heads * d), torch.float16, cuda_dev)
+        ops.attention(qkv, N, H * W, heads, d, out=o)
+        chk_o()
+
+
 def test_linear_as_gemm(cuda_dev):
     """The per-ResBlock step_embedding Linear layers run as one 1x1 'conv' over a [1,1,B,E] image."""
     ops, L = _ops()
