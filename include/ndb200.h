@@ -87,7 +87,7 @@ typedef struct {
 
 int ndb_conv_gemm(const ndb_conv_params* p, void* stream);
 /* Returns stat_smax for this geometry and fills counts[N] (HOST pointer) with the slots written per image. */
-int ndb_conv_stats_layout(int N, int H, int W, int cout_pad, int block_n, int32_t* counts);
+int ndb_conv_stats_layout(int N, int H, int W, int cout_pad, int block_n, int k_total, int32_t* counts);
 int ndb_conv_stats_supported(int N, int H, int W);   /* 1 if stat_parts is available for this geometry */
 
 /* OIHW fp32 (nn.Conv2d / Conv1d / Linear weight, kernel 1 or 3) -> [taps][cout_pad][cin] 16-bit, rows >= cout zero.

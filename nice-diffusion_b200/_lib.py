@@ -72,7 +72,7 @@ SIGNATURES = {
     'ndb_device_supported': (_I, []),
     'ndb_last_error': (C.c_char_p, []),
     'ndb_conv_gemm': (_I, [C.POINTER(ConvParams), _P]),
-    'ndb_conv_stats_layout': (_I, [_I, _I, _I, _I, _I, _P]),
+    'ndb_conv_stats_layout': (_I, [_I, _I, _I, _I, _I, _I, _P]),
     'ndb_conv_stats_supported': (_I, [_I, _I, _I]),
     'ndb_pack_conv_weight': (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     'ndb_gn_stats': (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P, _P]),

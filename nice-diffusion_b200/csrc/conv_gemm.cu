@@ -749,10 +749,17 @@ static ConvGeom conv_geom(int N, int H, int W) {
 
 // CTA-pair mode is used whenever two M tiles exist and, when statistics are requested, both CTAs of a pair always sweep
 // the same images (even number of m tiles per image) or each tile holds whole images.
-static bool use_pair_mode(const ConvGeom& g, int block_n, bool want_stats) {
+// Minimum reduction length (in 64-element K blocks) for the CTA-pair kernel. Back-to-back replays of one short-K GEMM
+// (scripts/blockn_probe.py with NDB_DISABLE_2CTA; warm L2) favour the single-CTA kernel below ~24 K blocks (16x16 576->1728:
+// 18.5 vs 23.6 us), but inside the denoising step (cold L2, different neighbours) pairs are equal or faster on every qkv /
+// proj layer (23.0 vs 25.4 us for the same shape), so the threshold stays at 1. The statistics layout depends on this
+// choice, which is why ndb_conv_stats_layout() takes the reduction length.
+constexpr int kPairMinKBlocks = 1;
+static bool use_pair_mode(const ConvGeom& g, int block_n, bool want_stats, int kblocks) {
     static int disabled = -1;
     if (disabled < 0) disabled = std::getenv("NDB_DISABLE_2CTA") != nullptr ? 1 : 0;
     if (disabled) return false;
+    if (kblocks < kPairMinKBlocks) return false;
     if (g.num_m_tiles < 2 || (block_n / 2) % 8 != 0) return false;
     if (want_stats && g.TN == 1 && ((g.tiles_w * g.tiles_h) % 2 != 0)) return false;
     return true;
@@ -763,9 +770,9 @@ struct WorkGeom {
     int items, workers, grid;
 };
 
-static WorkGeom work_geom(const ConvGeom& g, int num_n_tiles, int block_n, bool want_stats) {
+static WorkGeom work_geom(const ConvGeom& g, int num_n_tiles, int block_n, bool want_stats, int kblocks) {
     WorkGeom w;
-    w.pair = use_pair_mode(g, block_n, want_stats);
+    w.pair = use_pair_mode(g, block_n, want_stats, kblocks);
     if (w.pair) {
         w.items = ((g.num_m_tiles + 1) / 2) * num_n_tiles;
         const int max_workers = num_sms() / 2;
@@ -782,7 +789,7 @@ static WorkGeom work_geom(const ConvGeom& g, int num_n_tiles, int block_n, bool 
 // BLOCK_N by a small cost model: rounds of tiles per worker x tile cost. Narrow tiles run the tensor pipe at a lower rate
 // (shared-memory operand bandwidth per MMA grows relative to its work; rates measured with scripts/blockn_probe.py), but
 // they fill the machine when a layer has few tiles (the 8x8 levels: 16 M tiles).
-static int pick_block_n(int cout_pad, const ConvGeom& g, bool want_stats) {
+static int pick_block_n(int cout_pad, const ConvGeom& g, bool want_stats, int kblocks) {
     static const int cand[5] = {256, 192, 128, 96, 64};
     static const double rate[5] = {1.0, 1.0, 0.78, 0.61, 0.5};
     int best = 0;
@@ -790,7 +797,7 @@ static int pick_block_n(int cout_pad, const ConvGeom& g, bool want_stats) {
     for (int i = 0; i < 5; ++i) {
         const int bn = cand[i];
         if (cout_pad % bn != 0) continue;
-        const WorkGeom w = work_geom(g, cout_pad / bn, bn, want_stats);
+        const WorkGeom w = work_geom(g, cout_pad / bn, bn, want_stats, kblocks);
         const int rounds = (w.items + w.workers - 1) / w.workers;
         double cost = rounds * (double)bn / rate[i];
         if (bn == 256) cost *= 1.02;    // 192 leaves room for one more smem stage: prefer it on ties
@@ -845,7 +852,10 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     a.tiles_h = (prm->H + a.TH - 1) / a.TH;
     a.tiles_n = (prm->N + a.TN - 1) / a.TN;
     a.num_m_tiles = a.tiles_w * a.tiles_h * a.tiles_n;
-    a.block_n = prm->block_n > 0 ? prm->block_n : pick_block_n(prm->cout_pad, conv_geom(prm->N, prm->H, prm->W), prm->stat_parts != nullptr);
+    int kblocks_total = 0;
+    for (int s = 0; s < prm->num_segments; ++s) kblocks_total += prm->seg[s].taps * (prm->seg[s].C / kBlockK);
+    a.block_n = prm->block_n > 0 ? prm->block_n
+                                 : pick_block_n(prm->cout_pad, conv_geom(prm->N, prm->H, prm->W), prm->stat_parts != nullptr, kblocks_total);
     NDB_CHECK_ARG(a.block_n >= 16 && a.block_n <= 256 && a.block_n % 16 == 0 && prm->cout_pad % a.block_n == 0);
     a.num_n_tiles = prm->cout_pad / a.block_n;
     a.cout = prm->cout;
@@ -864,7 +874,7 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     a.stat_parts = reinterpret_cast<float2*>(prm->stat_parts);
     a.tiles_per_group = a.tiles_w * a.tiles_h * a.num_n_tiles;
     const ConvGeom cg = conv_geom(prm->N, prm->H, prm->W);
-    const WorkGeom wg = work_geom(cg, a.num_n_tiles, a.block_n, prm->stat_parts != nullptr);
+    const WorkGeom wg = work_geom(cg, a.num_n_tiles, a.block_n, prm->stat_parts != nullptr, kblocks_total);
     a.b_rows = wg.pair ? a.block_n / 2 : a.block_n;
     {
         static int dbg = -1;
@@ -969,16 +979,18 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     return launch_status("ndb_conv_gemm");
 }
 
-// Layout of the fused statistics output for a conv with this geometry: returns the number of partial slots per image
+// Layout of the fused statistics output for a conv with this geometry and reduction length k_total (= sum over the
+// segments of taps * C; it decides between the CTA-pair and the single-CTA kernel): returns the number of partial slots per image
 // (stat_smax) and fills counts[N] (host memory) with the slots actually written for each image; <0 on error.
 // stat_parts must hold N * stat_smax * cout float2.
-extern "C" int ndb_conv_stats_layout(int N, int H, int W, int cout_pad, int block_n, int32_t* counts) {
-    if (N <= 0 || H <= 0 || W <= 0 || cout_pad <= 0) return NDB_ERR_INVALID;
+extern "C" int ndb_conv_stats_layout(int N, int H, int W, int cout_pad, int block_n, int k_total, int32_t* counts) {
+    if (N <= 0 || H <= 0 || W <= 0 || cout_pad <= 0 || k_total <= 0 || k_total % kBlockK != 0) return NDB_ERR_INVALID;
+    const int kblocks = k_total / kBlockK;
     const ConvGeom g = conv_geom(N, H, W);
-    const int bn = block_n > 0 ? block_n : pick_block_n(cout_pad, g, true);
+    const int bn = block_n > 0 ? block_n : pick_block_n(cout_pad, g, true, kblocks);
     if (bn <= 0 || cout_pad % bn != 0) return NDB_ERR_INVALID;
     const int n_tiles = cout_pad / bn;
-    const WorkGeom w = work_geom(g, n_tiles, bn, true);
+    const WorkGeom w = work_geom(g, n_tiles, bn, true, kblocks);
     return stats_slots(g.tiles_n, g.tiles_w * g.tiles_h * n_tiles, n_tiles, g.TN, w.pair, w.items, w.workers, counts, N);
 }
 

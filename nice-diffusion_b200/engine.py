@@ -117,12 +117,12 @@ class UNetEngine:
     def _emit_stats_kernel(self, t, stats):
         self.steps.append(lambda: ops.gn_stats(t, stats0=stats, workspace=self.gn_ws))
 
-    def _conv_stats_layout(self, H, W, cout):
-        key = (H, W, cout)
+    def _conv_stats_layout(self, H, W, cout, k_total):
+        key = (H, W, cout, k_total)
         if key not in self._layouts:
             import ctypes
             counts = (ctypes.c_int32 * self.B)()
-            smax = int(L.load().ndb_conv_stats_layout(self.B, H, W, ops.pad16(cout), 0, counts))
+            smax = int(L.load().ndb_conv_stats_layout(self.B, H, W, ops.pad16(cout), 0, k_total, counts))
             if smax < 1:
                 raise L.NdbError('ndb_conv_stats_layout failed')
             self._layouts[key] = (smax, torch.tensor(list(counts), dtype=torch.int32, device=self.device))
@@ -137,7 +137,8 @@ class UNetEngine:
         stats = None
         fused = want_stats and ops.conv_stats_supported(B, H, W)
         if fused:
-            smax, counts = self._conv_stats_layout(H, W, cout)
+            k_total = sum(a.shape[-1] * w.shape[0] for a, w in segs)
+            smax, counts = self._conv_stats_layout(H, W, cout, k_total)
             stats = self._stats_buf(cout, smax, counts)
             self.steps.append(lambda: ops.conv_gemm(segs, B, H, W, cout, out=out, fmt=fmt, stats=stats, **kw))
         else:

@@ -125,13 +125,14 @@ def conv_stats_supported(N, H, W):
     return bool(L.load().ndb_conv_stats_supported(N, H, W))
 
 
-def conv_stats_alloc(N, H, W, cout, device, cout_pad=None, block_n=0):
+def conv_stats_alloc(N, H, W, cout, device, k_total, cout_pad=None, block_n=0):
     """Buffers for the statistics a conv epilogue writes for its output: (parts float32 [N, smax, cout, 2],
-    counts int32 [N]) -- see ndb_conv_stats_layout."""
+    counts int32 [N]) -- see ndb_conv_stats_layout. k_total = reduction length of the GEMM that will write them
+    (sum over its segments of taps * C): it selects the kernel variant and with it the slot layout."""
     import ctypes
     cp = pad16(cout) if cout_pad is None else cout_pad
     counts = (ctypes.c_int32 * N)()
-    smax = int(L.load().ndb_conv_stats_layout(N, H, W, cp, block_n, counts))
+    smax = int(L.load().ndb_conv_stats_layout(N, H, W, cp, block_n, int(k_total), counts))
     if smax < 1:
         raise L.NdbError('ndb_conv_stats_layout failed ({})'.format(smax))
     parts = torch.zeros((N, smax, cout, 2), dtype=torch.float32, device=device)

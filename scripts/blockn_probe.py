@@ -20,7 +20,7 @@ for (N, H, W, Cin, Cout, k, res, stats, o16) in shapes:
     for bn in (256, 192, 128, 96, 64):
         if Cout % bn:
             continue
-        st = ops.conv_stats_alloc(N, H, W, Cout, dev, block_n=bn) if stats else None
+        st = ops.conv_stats_alloc(N, H, W, Cout, dev, Cin * k * k, block_n=bn) if stats else None
         f = lambda: ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, residual=r, residual_mode=L.RES_SAME, out=out, stats=st,
                                   out_kind=L.OUT_F16_NHWC if o16 else L.OUT_F32_NHWC, block_n=bn)
         for _ in range(3): f()

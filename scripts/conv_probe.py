@@ -16,7 +16,7 @@ for (N, H, W, Cin, Cout, k, res, stats, o16) in shapes:
     b = torch.randn(Cout, device=dev)
     r = torch.randn(N, H, W, Cout, device=dev) if res else None
     out = torch.empty(N, H, W, Cout, device=dev, dtype=torch.float16 if o16 else torch.float32)
-    st = ops.conv_stats_alloc(N, H, W, Cout, dev) if stats else None
+    st = ops.conv_stats_alloc(N, H, W, Cout, dev, Cin * k * k) if stats else None
     f = lambda: ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, residual=r, residual_mode=L.RES_SAME, out=out, stats=st,
                               out_kind=L.OUT_F16_NHWC if o16 else L.OUT_F32_NHWC)
     for _ in range(3): f()

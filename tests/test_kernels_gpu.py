@@ -125,14 +125,14 @@ def test_conv_epilogue_fused_groupnorm_statistics(cuda_dev, N, H, W, Cin, Cout, 
     b = (0.5 * torch.randn(Cout, generator=g)).to(cuda_dev)
     r = nhwc(torch.randn(N, Cout, H, W, generator=g).to(cuda_dev)) if res else None
     x16, wp = nhwc(x).half(), ops.pack_conv_weight(w)
-    st = ops.conv_stats_alloc(N, H, W, Cout, cuda_dev)
+    st = ops.conv_stats_alloc(N, H, W, Cout, cuda_dev, Cin * 9)
     st[0].fill_(float('nan'))
     out = ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, residual=r, residual_mode=L.RES_SAME, stats=st)
     o = out.double().flatten(1, 2)                      # [N, HW, C]
     tot = ops.stats_totals(st)
     assert torch.allclose(tot[:, :, 0], o.sum(1), rtol=1e-5, atol=2e-3)
     assert torch.allclose(tot[:, :, 1], (o * o).sum(1), rtol=1e-5, atol=2e-3)
-    st2 = ops.conv_stats_alloc(N, H, W, Cout, cuda_dev)
+    st2 = ops.conv_stats_alloc(N, H, W, Cout, cuda_dev, Cin * 9)
     out2 = ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, residual=r, residual_mode=L.RES_SAME, stats=st2)
     assert torch.equal(out, out2) and torch.equal(ops.stats_totals(st), ops.stats_totals(st2))
     # a GroupNorm fed by the fused statistics == one fed by the standalone statistics kernel == torch
@@ -147,8 +147,9 @@ def test_conv_epilogue_fused_groupnorm_statistics(cuda_dev, N, H, W, Cin, Cout, 
 EPI_CASES = [
     # N, H, W, Cin, Cout: every pixel-box shape of the staged TMA-store epilogue (W = 8, 16, 32, 64, 128), an odd batch
     # (leftover half tile in CTA-pair mode), a ragged image (legacy epilogue) and a channel count that is not a multiple of 32
-    (5, 8, 8, 64, 192), (3, 16, 16, 64, 192), (2, 32, 32, 64, 384), (1, 64, 64, 64, 192), (1, 8, 128, 64, 256),
-    (3, 14, 14, 64, 192), (2, 16, 16, 64, 144),
+    # Cin = 192 -> 27 K blocks: the CTA-pair kernel; Cin = 64 -> 9 K blocks: the single-CTA kernel
+    (5, 8, 8, 192, 192), (3, 16, 16, 192, 192), (2, 32, 32, 64, 384), (1, 64, 64, 192, 192), (1, 8, 128, 64, 256),
+    (3, 14, 14, 192, 192), (2, 16, 16, 64, 144), (5, 8, 8, 64, 192),
 ]
 
 
@@ -172,7 +173,7 @@ def test_conv_epilogue_variants(cuda_dev, N, H, W, Cin, Cout):
             out = ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, residual=rr, residual_mode=L.RES_SAME, block_n=bn)
             assert rel_err(out.permute(0, 3, 1, 2), ref) < 2e-5, (bn, res)
             if ops.conv_stats_supported(N, H, W):
-                st = ops.conv_stats_alloc(N, H, W, Cout, cuda_dev, block_n=bn)
+                st = ops.conv_stats_alloc(N, H, W, Cout, cuda_dev, Cin * 9, block_n=bn)
                 st[0].fill_(float('nan'))
                 out2 = ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, residual=rr, residual_mode=L.RES_SAME, stats=st,
                                      block_n=bn)
@@ -221,7 +222,8 @@ def _guarded(shape, dtype, dev, guard=4096):
 
 
 @pytest.mark.parametrize('N,H,W,Cin,Cout', [(5, 8, 8, 64, 192), (3, 16, 16, 64, 96), (1, 64, 64, 64, 64), (3, 14, 14, 64, 80),
-                                            (1, 8, 8, 64, 192), (7, 32, 32, 64, 40)])
+                                            (1, 8, 8, 64, 192), (7, 32, 32, 64, 40), (5, 8, 8, 192, 192), (1, 64, 64, 192, 64),
+                                            (3, 16, 16, 192, 96)])
 def test_kernels_write_exactly_their_outputs(cuda_dev, N, H, W, Cin, Cout):
     """Guard-band check of every store path: GEMM epilogues (TMA boxes clipped at image / channel borders, the all-padding
     half tile of an odd CTA pair, legacy per-row stores), statistics slots, GroupNorm apply, attention."""
@@ -239,7 +241,7 @@ def test_kernels_write_exactly_their_outputs(cuda_dev, N, H, W, Cin, Cout):
             ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, residual=res, residual_mode=L.RES_SAME, out_kind=kind, out=out)
             chk()
     if ops.conv_stats_supported(N, H, W) and Cout % 32 == 0:
-        st = ops.conv_stats_alloc(N, H, W, Cout, cuda_dev)
+        st = ops.conv_stats_alloc(N, H, W, Cout, cuda_dev, Cin * 9)
         parts, chk_p = _guarded(tuple(st[0].shape), torch.float32, cuda_dev)
         out, chk = _guarded((N, H, W, Cout), torch.float32, cuda_dev)
         ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, residual=r, residual_mode=L.RES_SAME, out=out, stats=(parts,) + tuple(st[1:]))
