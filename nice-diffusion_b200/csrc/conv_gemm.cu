@@ -28,6 +28,12 @@
 
 namespace ndb {
 
+#ifdef NDB_BRINGUP
+#define NDB_DBG_BIT(p, b) ((p).dbg & (b))
+#else
+#define NDB_DBG_BIT(p, b) 0
+#endif
+
 constexpr int kMaxSeg = NDB_MAX_SEGMENTS;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                        // 64 x 16-bit = one 128-byte swizzle row
@@ -73,7 +79,8 @@ struct ConvArgs {
     int epi_bulk;              // 1: staged TMA-store epilogue
     int epi_bufs;              // staging tiles per epilogue warp (2 for short-K GEMMs whose epilogue is on the critical path)
     int epi_region;            // bytes of the staging region
-    int dbg;                   // bring-up switches (env NDB_DBG; results are garbage): 1 no TMA loads, 2 no MMAs, 4 no TMA stores, 8 no staging writes
+    int dbg;                   // bring-up switches, compiled in with -DNDB_BRINGUP only (env NDB_DBG; results are garbage):
+                               // 1 no TMA loads, 2 no MMAs, 4 no TMA stores, 8 no staging writes
 };
 
 // Persistent CTAs own CONTIGUOUS tile ranges: CTA c processes tiles [tile_start(c), tile_start(c+1)). Tiles are ordered
@@ -194,7 +201,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                             uint8_t* sa = smem + stage * stage_bytes;
                             uint8_t* sb = sa + kATileBytes;
                             if (elect_one()) {
-                                if (p.dbg & 1) {
+                                if (NDB_DBG_BIT(p, 1)) {
                                     if (k2) mbar_arrive_cluster(mapa_u32(smem_u32(&full_bar[stage]), 0));
                                     else mbar_arrive(&full_bar[stage]);
                                 } else if (k2) {
@@ -244,7 +251,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                         const uint64_t bdesc = kDescHi | (a_lo + (uint32_t)(kATileBytes >> 4));
 #pragma unroll
                         for (int k = 0; k < kBlockK / 16; ++k) {
-                            if (p.dbg & 2) break;
+                            if (NDB_DBG_BIT(p, 2)) break;
                             // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
                             if (k2) umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
                             else umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
@@ -386,7 +393,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                     }
                     __syncwarp();
                     if (p.epi_bufs == 2) sb ^= 1;
-                    if (p.dbg & 8) {
+                    if (NDB_DBG_BIT(p, 8)) {
                     } else if (!transposed) {
                         // bias in thread = row form, straight into the staging tile
                         if (p.out_kind == NDB_OUT_F32_NHWC) {
@@ -444,7 +451,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                     }
                     fence_proxy_async();      // generic-proxy writes -> visible to the TMA engine
                     __syncwarp();
-                    if (box_on && !(p.dbg & 4)) {
+                    if (box_on && !NDB_DBG_BIT(p, 4)) {
                         if (elect_one()) {
                             tma_store_4d(&maps.out, sbuf, c0, bw, bh, bn);
                             bulk_commit();
