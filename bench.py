@@ -151,7 +151,28 @@ def cpu_reference_arm(workload, steps, warmup, sample_batch=None):
                            steps, warmup, workload, sample_batch, per_image), batch=sample_batch)
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE line (the JSON result): everything else any library prints there (e.g. NCCL's version banner
+    under NCCL_DEBUG) is sent to stderr by pointing fd 1 at fd 2 for the rest of the process."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=100)
@@ -195,7 +216,7 @@ def main():
                 'cpu_baseline': {'value': r['value'], 'unit': 'images/sec', 'cores': r['cores'], 'kind': 'port',
                                  'sample': r['sample']},
                 'e2e': {'value': r['value'], 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-        print(json.dumps(line))
+        _emit(line)
         return
 
     # ------------------------------------------------------------------ ndb200 arm
@@ -329,7 +350,7 @@ def main():
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'fp16', 'data': 'synthetic', 'config': config, 'clocks': clk,
             'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu}
-    print(json.dumps(line))
+    _emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
