@@ -59,6 +59,9 @@ class UNetEngine:
         self.fmt = model.operand_format
         self.dt16 = ops.dtype16(self.fmt)
         self.steps = []          # list of zero-arg callables, one kernel launch each
+        self.n_embed_steps = 0   # leading steps (embedding front end) that run on a side stream ...
+        self.join_idx = None     # ... until the first step that consumes the step embedding
+        self.side = None
         self.packers = []        # callables that (re)fill the weight arena from the live parameters
         self.graph = None
         self.sig = None
@@ -194,6 +197,7 @@ class UNetEngine:
         a_view = act16.view(1, 1, B, E)
         self.steps.append(lambda: ops.conv_gemm([(a_view, w_all)], 1, 1, B, total, bias=b_all,
                                                 out=self.emb_all, fmt=fmt, cout_pad=total))
+        self.n_embed_steps = len(self.steps)
 
         # ---- workspace of the standalone statistics kernel (stem output, uncovered geometries) ----
         ws_bytes = 0
@@ -312,6 +316,8 @@ class UNetEngine:
                            out=pool.get((B, Ho, Wo, Cout), self.dt16))
         else:
             h = self._conv([(a1, w_in)], Ho, Wo, Cout, want_stats=True, bias=bias_in)
+        if self.join_idx is None:
+            self.join_idx = len(self.steps)     # first consumer of the step embedding
         self.steps.append(lambda: ops.gn_apply(h.t, h.stats, g2, b2, scale=scale, shift=shift, pre_add=pre, silu=True,
                                                out=a2, fmt=fmt, eps=eps2))
         if conv_skip:
@@ -393,8 +399,25 @@ class UNetEngine:
     # execution
     # ------------------------------------------------------------------------------------------
     def _launch_all(self):
-        for f in self.steps:
-            f()
+        """The embedding front end (timestep / class embedding MLP + the GEMM of all step-embedding Linears: small grids,
+        independent of x) runs on a side stream next to the stem conv, its statistics and the first norm + conv; the
+        streams join at the first kernel that reads the embedding. Under graph capture this becomes a fork / join."""
+        ne = self.n_embed_steps
+        if ne == 0 or self.join_idx is None:
+            for f in self.steps:
+                f()
+            return
+        cur = torch.cuda.current_stream(self.device)
+        if self.side is None:
+            self.side = torch.cuda.Stream(device=self.device)
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            for f in self.steps[:ne]:
+                f()
+        for i in range(ne, len(self.steps)):
+            if i == self.join_idx:
+                cur.wait_stream(self.side)
+            self.steps[i]()
 
     def run_static(self):
         """Run the plan on the static input buffers (x_in, t_in, y_in) -> self.out."""
