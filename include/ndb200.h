@@ -166,6 +166,12 @@ int ndb_embed(const float* t, const int64_t* y, const float* freqs, int B, int m
 int ndb_stem_conv(const float* x_nchw, const float* w_oihw, const float* bias, float* out_nhwc, int N, int Cin,
                   int H, int W, int Cout, void* stream);
 
+/* the same conv as ONE tensor-core K block: gathers the 3x3 neighbourhood of every pixel of an NCHW fp32 image with
+ * Cin <= 7 channels into a 64-wide 16-bit operand row out[n][h][w][tap*Cin + c] (zero padded; tap = ky*3+kx), so that
+ * ndb_conv_gemm runs the stem as a 1x1 GEMM with weight[o][tap*Cin + c] = w[o][c][ky][kx] -- and gets the fused bias,
+ * TMA-store epilogue and GroupNorm statistics of every other conv (model.py:367). */
+int ndb_stem_im2col(const float* x_nchw, void* out, int N, int Cin, int H, int W, int operand_format, void* stream);
+
 /* generic fp32 NHWC resample (standalone Upsample / Downsample without conv, model.py:77,111) and layout casts */
 int ndb_resample_f32(const float* x, float* out, int N, int H, int W, int C, int mode, void* stream);
 int ndb_cast_nhwc16(const float* x, void* out, int64_t numel, int operand_format, void* stream);

@@ -84,6 +84,7 @@ SIGNATURES = {
     'ndb_resample_f32': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     'ndb_cast_nhwc16': (_I, [_P, _P, _I64, _I, _P]),
     'ndb_im2col_s2': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    'ndb_stem_im2col': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     'ndb_sampler_step': (_I, [C.POINTER(StepParams), _P]),
     'ndb_advance_step': (_I, [_P, _I, _P, _I, _P, _P]),
     'ndb_philox_normal': (_I, [_P, _I, _I64, _U64, _P, C.c_int32, _P]),

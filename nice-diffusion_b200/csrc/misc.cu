@@ -220,6 +220,38 @@ __global__ void cast16_kernel(const float* __restrict__ x, uint16_t* __restrict_
     }
 }
 
+// Stem conv as a GEMM: out[n][h][w][tap*CIN + c] = x[n][c][h+ky-1][w+kx-1] (zero outside the image), tap = ky*3+kx, the
+// 9*CIN <= 64 gathered values of a pixel zero-padded to ONE 64-element K block. x is NCHW fp32 (the model input); thread =
+// pixel, consecutive threads read consecutive w (coalesced per (c, ky, kx)), each writes its 128-byte row as 8 x 16 bytes.
+template <int CIN>
+__global__ void stem_im2col_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, int N, int H, int W, int fmt) {
+    const long long total = (long long)N * H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(i % W);
+        const int h = (int)((i / W) % H);
+        const int n = (int)(i / ((long long)W * H));
+        const float* xn = x + (long long)n * CIN * H * W;
+        uint32_t pk[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) pk[k] = 0u;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+            const bool in = hh >= 0 && hh < H && ww >= 0 && ww < W;
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) {
+                const float f = in ? __ldg(xn + ((long long)c * H + hh) * W + ww) : 0.f;
+                const int k = tap * CIN + c;
+                pk[k >> 1] |= (uint32_t)to16(f, fmt) << ((k & 1) * 16);
+            }
+        }
+        uint4* o = reinterpret_cast<uint4*>(out + i * 64);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    }
+}
+
 // out[tap][n][ho][wo][c] = x[n][2ho+ky-1][2wo+kx-1][c] (zero outside), tap = ky*3+kx
 __global__ void im2col_s2_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, int N, int H, int W, int C,
                                  int Ho, int Wo, int fmt) {
@@ -319,6 +351,24 @@ extern "C" int ndb_cast_nhwc16(const float* x, void* out, int64_t numel, int ope
     NDB_CHECK_ARG(x && out && numel % 4 == 0);
     cast16_kernel<<<grid_for(numel / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (uint16_t*)out, numel, operand_format);
     return launch_status("ndb_cast_nhwc16");
+}
+
+extern "C" int ndb_stem_im2col(const float* x_nchw, void* out, int N, int Cin, int H, int W, int operand_format, void* stream) {
+    NDB_CHECK_ARG(x_nchw && out && N > 0 && H > 0 && W > 0);
+    NDB_CHECK_ARG(Cin >= 1 && Cin <= 7);
+    const int grid = grid_for((long long)N * H * W, 128);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint16_t* o = (uint16_t*)out;
+    switch (Cin) {
+        case 1: stem_im2col_kernel<1><<<grid, 128, 0, st>>>(x_nchw, o, N, H, W, operand_format); break;
+        case 2: stem_im2col_kernel<2><<<grid, 128, 0, st>>>(x_nchw, o, N, H, W, operand_format); break;
+        case 3: stem_im2col_kernel<3><<<grid, 128, 0, st>>>(x_nchw, o, N, H, W, operand_format); break;
+        case 4: stem_im2col_kernel<4><<<grid, 128, 0, st>>>(x_nchw, o, N, H, W, operand_format); break;
+        case 5: stem_im2col_kernel<5><<<grid, 128, 0, st>>>(x_nchw, o, N, H, W, operand_format); break;
+        case 6: stem_im2col_kernel<6><<<grid, 128, 0, st>>>(x_nchw, o, N, H, W, operand_format); break;
+        default: stem_im2col_kernel<7><<<grid, 128, 0, st>>>(x_nchw, o, N, H, W, operand_format); break;
+    }
+    return launch_status("ndb_stem_im2col");
 }
 
 extern "C" int ndb_im2col_s2(const float* x, void* out, int N, int H, int W, int C, int operand_format, void* stream) {

@@ -273,6 +273,27 @@ def stem_conv(x_nchw, w, bias, out=None):
     return out
 
 
+def stem_im2col(x_nchw, out=None, fmt=L.FMT_FP16):
+    """[N,Cin,H,W] fp32 -> [N,H,W,64] 16-bit rows (tap*Cin + c, zero padded): the stem conv's GEMM operand."""
+    L.require_device(x_nchw, 'stem_im2col')
+    N, Cin, H, W = x_nchw.shape
+    if out is None:
+        out = torch.empty((N, H, W, 64), dtype=dtype16(fmt), device=x_nchw.device)
+    _begin()
+    L.check(L.load().ndb_stem_im2col(L.ptr(x_nchw), L.ptr(out), N, Cin, H, W, fmt, L.stream_ptr()), 'ndb_stem_im2col')
+    _count('stem_im2col')
+    return out
+
+
+def stem_weight_as_1x1(w):
+    """OIHW [Cout,Cin,3,3] -> [Cout,64,1,1] with column tap*Cin + c (the layout ndb_stem_im2col produces), zero padded."""
+    Cout, Cin = w.shape[0], w.shape[1]
+    assert w.shape[2] == 3 and w.shape[3] == 3 and 9 * Cin <= 64
+    w2 = torch.zeros((Cout, 64, 1, 1), dtype=w.dtype, device=w.device)
+    w2[:, :9 * Cin, 0, 0] = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin)
+    return w2
+
+
 def resample_f32(x, mode, out=None):
     N, H, W, Cc = x.shape
     Ho, Wo = (2 * H, 2 * W) if mode == L.RESAMPLE_UP2 else (H // 2, W // 2)

@@ -435,3 +435,23 @@ def test_stem_resample_cast_im2col_uint8(cuda_dev):
     img = torch.rand(2, 3, 8, 8, generator=g).to(cuda_dev) * 2.4 - 1.2
     ref8 = ((img + 1) * 127.5).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1)
     assert torch.equal(ops.to_uint8(img), ref8)
+
+
+@pytest.mark.parametrize('N,Cin,H,W,Cout', [(3, 3, 64, 64, 192), (2, 1, 28, 28, 64), (1, 7, 16, 16, 128), (2, 3, 128, 128, 64)])
+def test_stem_conv_as_one_k_block_gemm(cuda_dev, N, Cin, H, W, Cout):
+    """ndb_stem_im2col + a 1x1 GEMM over the gathered 3x3 neighbourhood == conv3x3(pad 1) of the NCHW input (model.py:367)."""
+    ops, L = _ops()
+    g = torch.Generator(device='cpu').manual_seed(N * 10 + Cin)
+    x = torch.randn(N, Cin, H, W, generator=g).to(cuda_dev)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)).to(cuda_dev)
+    b = (0.1 * torch.randn(Cout, generator=g)).to(cuda_dev)
+    cols = ops.stem_im2col(x)
+    assert cols.shape == (N, H, W, 64)
+    # the gathered operand itself: column tap*Cin + c holds x[n, c, h+ky-1, w+kx-1]
+    ref_cols = F.unfold(x.half().float(), 3, padding=1).view(N, Cin, 9, H, W).permute(0, 3, 4, 2, 1).reshape(N, H, W, 9 * Cin)
+    assert torch.equal(cols[..., :9 * Cin].float(), ref_cols) and (cols[..., 9 * Cin:] == 0).all()
+    wp = ops.pack_conv_weight(ops.stem_weight_as_1x1(w))
+    out = ops.conv_gemm([(cols, wp)], N, H, W, Cout, bias=b)
+    ref16 = F.conv2d(x.half().float(), w.half().float(), b, padding=1)
+    assert rel_err(out.permute(0, 3, 1, 2), ref16) < 2e-5
+    assert rel_err(out.permute(0, 3, 1, 2), F.conv2d(x, w, b, padding=1)) < 3e-3
