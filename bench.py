@@ -296,6 +296,8 @@ def main():
         out_host.copy_(out, non_blocking=True)
         e1.record()
         barrier()
+        if not bool(torch.isfinite(out_host).all()):
+            raise SystemExit('bench.py: the end-to-end chain produced non-finite images')
         ems = e0.elapsed_time(e1)
         if dist is not None:
             tmax = torch.tensor([ems], device=dev)
