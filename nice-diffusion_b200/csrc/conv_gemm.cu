@@ -13,13 +13,13 @@
 // Warp roles (352 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue,
 // warp 10 = GroupNorm-statistics reducer (only active when chan_stats is requested).
 // Epilogue: each warp owns 32 accumulator rows (its TMEM lane quarter) and half of the tile's 32-column chunks.
-//   bulk path (NHWC outputs whose 32 rows form a {w, h} box -- every power-of-two image size): the chunk is pulled out of
+//   bulk path (NHWC outputs; tiles have power-of-two extents, so the 32 rows of a warp always form a {w, h} pixel box): the chunk is pulled out of
 //   TMEM (thread = row) into a per-warp 4 KB SWIZZLE_128B staging tile with conflict-free 16-byte stores; when a residual
 //   or GroupNorm statistics are wanted the warp then walks the tile with lanes along channels (conflict-free again), adds
 //   bias + residual in place and takes the column sums; ONE TMA store writes the box back. Residual values are fetched
 //   with lanes along channels (32 coalesced 128-byte requests in flight per warp) one chunk AHEAD of the chunk being
 //   processed, across tile boundaries, so their latency hides behind the previous chunk.
-//   legacy path (NCHW head, 2x up/down-sampled residuals, odd image sizes): padded transpose tile + per-row stores.
+//   legacy path (NCHW head, 2x up/down-sampled residuals): padded transpose tile + per-row stores.
 #include "common.cuh"
 #include "ptx.cuh"
 #include <cuda_fp16.h>
@@ -735,15 +735,27 @@ struct ConvGeom {
     int TW, TH, TN, tiles_w, tiles_h, tiles_n, num_m_tiles;
 };
 
+// M tiles are boxes of TN images x TH rows x TW columns with POWER-OF-TWO extents (<= 128 pixels): an image whose width or
+// height is not a power of two (EMNIST: 28, 14, 7) is covered by boxes that overhang its border -- TMA zero-fills the
+// overhang on load and clips it on store, the epilogue masks it out of the statistics -- so every 32-row group of a tile is
+// a {w, h} pixel box and all sizes run the same staged TMA-store epilogue with fused statistics (at most 12.5 % / 23 % of the
+// rows are padding at 28 / 7 pixels).
+static int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
 static ConvGeom conv_geom(int N, int H, int W) {
     ConvGeom g;
-    g.TW = W < kBlockM ? W : kBlockM;
+    const int Wv = next_pow2(W), Hv = next_pow2(H);     // virtual (padded) image extents
+    g.TW = Wv < kBlockM ? Wv : kBlockM;
     g.TH = kBlockM / g.TW;
-    if (g.TH > H) g.TH = H;
+    if (g.TH > Hv) g.TH = Hv;
     if (g.TH < 1) g.TH = 1;
     g.TN = 1;
-    if (g.TH == H && g.TW == W) {
-        g.TN = kBlockM / (H * W);
+    if (g.TH == Hv && g.TW == Wv) {
+        g.TN = kBlockM / (Hv * Wv);
         if (g.TN < 1) g.TN = 1;
         if (g.TN > N) g.TN = N;
     }
@@ -752,6 +764,12 @@ static ConvGeom conv_geom(int N, int H, int W) {
     g.tiles_n = (N + g.TN - 1) / g.TN;
     g.num_m_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
     return g;
+}
+
+// image slots inside a tile must be whole warps (statistics warp: 4 / TN row quarters per image)
+static bool stats_geom_ok(const ConvGeom& g) {
+    if (g.TN == 1) return true;
+    return (g.TN == 2 || g.TN == 4) && (g.TH * g.TW) % 32 == 0 && g.TN * g.TH * g.TW == kBlockM;
 }
 
 // CTA-pair mode is used whenever two M tiles exist and, when statistics are requested, both CTAs of a pair always sweep
@@ -845,24 +863,14 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
 
     ConvArgs a{};
     a.N = prm->N; a.H = prm->H; a.W = prm->W;
-    a.TW = prm->W < kBlockM ? prm->W : kBlockM;
-    a.TH = kBlockM / a.TW;
-    if (a.TH > prm->H) a.TH = prm->H;
-    if (a.TH < 1) a.TH = 1;
-    a.TN = 1;
-    if (a.TH == prm->H && a.TW == prm->W) {
-        a.TN = kBlockM / (prm->H * prm->W);
-        if (a.TN < 1) a.TN = 1;
-        if (a.TN > prm->N) a.TN = prm->N;
-    }
-    a.tiles_w = (prm->W + a.TW - 1) / a.TW;
-    a.tiles_h = (prm->H + a.TH - 1) / a.TH;
-    a.tiles_n = (prm->N + a.TN - 1) / a.TN;
-    a.num_m_tiles = a.tiles_w * a.tiles_h * a.tiles_n;
+    const ConvGeom cg = conv_geom(prm->N, prm->H, prm->W);
+    a.TW = cg.TW; a.TH = cg.TH; a.TN = cg.TN;
+    a.tiles_w = cg.tiles_w; a.tiles_h = cg.tiles_h; a.tiles_n = cg.tiles_n;
+    a.num_m_tiles = cg.num_m_tiles;
     int kblocks_total = 0;
     for (int s = 0; s < prm->num_segments; ++s) kblocks_total += prm->seg[s].taps * (prm->seg[s].C / kBlockK);
     a.block_n = prm->block_n > 0 ? prm->block_n
-                                 : pick_block_n(prm->cout_pad, conv_geom(prm->N, prm->H, prm->W), prm->stat_parts != nullptr, kblocks_total);
+                                 : pick_block_n(prm->cout_pad, cg, prm->stat_parts != nullptr, kblocks_total);
     NDB_CHECK_ARG(a.block_n >= 16 && a.block_n <= 256 && a.block_n % 16 == 0 && prm->cout_pad % a.block_n == 0);
     a.num_n_tiles = prm->cout_pad / a.block_n;
     a.cout = prm->cout;
@@ -880,7 +888,6 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     a.fmt = prm->operand_format;
     a.stat_parts = reinterpret_cast<float2*>(prm->stat_parts);
     a.tiles_per_group = a.tiles_w * a.tiles_h * a.num_n_tiles;
-    const ConvGeom cg = conv_geom(prm->N, prm->H, prm->W);
     const WorkGeom wg = work_geom(cg, a.num_n_tiles, a.block_n, prm->stat_parts != nullptr, kblocks_total);
     a.b_rows = wg.pair ? a.block_n / 2 : a.block_n;
     {
@@ -891,8 +898,7 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     if (wg.pair) a.idesc = make_idesc_f16(2 * kBlockM, a.block_n, prm->operand_format, 0, 0);
     if (prm->stat_parts != nullptr) {
         NDB_CHECK_ARG(prm->out_kind != NDB_OUT_F32_NCHW);
-        // image slots inside a tile must be whole warps
-        NDB_CHECK_ARG(a.TN == 1 || ((a.TN == 2 || a.TN == 4) && (prm->H * prm->W) % 32 == 0 && a.TN * prm->H * prm->W == kBlockM));
+        NDB_CHECK_ARG(stats_geom_ok(cg));
         a.stat_smax = stats_slots(a.tiles_n, a.tiles_per_group, a.num_n_tiles, a.TN, wg.pair, wg.items, wg.workers, nullptr, 0);
         NDB_CHECK_ARG(prm->stat_smax == a.stat_smax);
     }
@@ -1003,7 +1009,5 @@ extern "C" int ndb_conv_stats_layout(int N, int H, int W, int cout_pad, int bloc
 
 // 1 when the epilogue can produce per-image channel statistics for this geometry (else use ndb_gn_stats).
 extern "C" int ndb_conv_stats_supported(int N, int H, int W) {
-    const ConvGeom g = conv_geom(N, H, W);
-    if (g.TN == 1) return 1;
-    return ((g.TN == 2 || g.TN == 4) && (H * W) % 32 == 0 && g.TN * H * W == kBlockM) ? 1 : 0;
+    return stats_geom_ok(conv_geom(N, H, W)) ? 1 : 0;
 }
