@@ -162,9 +162,12 @@ int ndb_embed(const float* t, const int64_t* y, const float* freqs, int B, int m
               float* h1_scratch, float* emb_out, void* act_out, int operand_format, void* stream);
 
 /* ---- stem conv / small direct convs ------------------------------------------------------------------
- * conv3x3 s1 p1 with tiny Cin (model.py:367): x NCHW fp32 [N,Cin,H,W] -> NHWC fp32 [N,H,W,Cout]. */
-int ndb_stem_conv(const float* x_nchw, const float* w_oihw, const float* bias, float* out_nhwc, int N, int Cin,
-                  int H, int W, int Cout, void* stream);
+ * conv3x3 s1 p1 with tiny Cin (model.py:367), exact fp32: x NCHW fp32 [N,Cin,H,W] -> NHWC fp32 [N,H,W,Cout].
+ * stat_parts (nullable; needs H*W % 64 == 0): the GroupNorm statistics of the output in the slot format of
+ * ndb_gn_apply, float2 [N][H*W/64][Cout], slot s of image n = (sum, sum of squares) over its pixels [64 s, 64 s + 64);
+ * every slot is written (counts[n] = H*W/64). */
+int ndb_stem_conv(const float* x_nchw, const float* w_oihw, const float* bias, float* out_nhwc, void* stat_parts, int N,
+                  int Cin, int H, int W, int Cout, void* stream);
 
 /* the same conv as ONE tensor-core K block: gathers the 3x3 neighbourhood of every pixel of an NCHW fp32 image with
  * Cin <= 7 channels into a 64-wide 16-bit operand row out[n][h][w][tap*Cin + c] (zero padded; tap = ky*3+kx), so that

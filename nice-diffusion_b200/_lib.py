@@ -80,7 +80,7 @@ SIGNATURES = {
     'ndb_gn_apply': (_I, [C.POINTER(GnApplyParams), _P]),
     'ndb_attention': (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'ndb_embed': (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
-    'ndb_stem_conv': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    'ndb_stem_conv': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     'ndb_resample_f32': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     'ndb_cast_nhwc16': (_I, [_P, _P, _I64, _I, _P]),
     'ndb_im2col_s2': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),

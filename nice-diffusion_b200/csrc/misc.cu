@@ -105,13 +105,20 @@ embed_l2_kernel(const float* __restrict__ h1, const int64_t* __restrict__ y, int
 // Block = 64 consecutive pixels x 4 channel groups. A thread owns one pixel and CPT = Cout/4 consecutive output channels:
 // it reads its Cin*9 input taps once (L1-resident, shared with its neighbours), keeps the CPT accumulators in registers
 // and streams the weights [tap][cout] from shared memory as warp-wide broadcasts (one LDS.128 feeds four FMAs per lane).
+// The 64 x Cout result tile is staged in shared memory so that (a) it leaves as one contiguous, fully coalesced 64*Cout*4
+// byte store (thread-per-pixel stores are 16 bytes every Cout*4 bytes) and (b) per-channel (sum, sum of squares) over the 64
+// pixels come from conflict-free column reads: with `stat_parts` the kernel emits the GroupNorm statistics of its output
+// as one slot per 64-pixel block, float2 [N][H*W/64][Cout] (needs H*W % 64 == 0), fixed summation order.
 template <int CIN, int CPT>
 __global__ void __launch_bounds__(256)
 stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                 float* __restrict__ out, int N, int H, int W) {
+                 float* __restrict__ out, float2* __restrict__ stat_parts, int N, int H, int W) {
     constexpr int K = CIN * 9;
     constexpr int COUT = 4 * CPT;
-    __shared__ __align__(16) float sw[K * COUT];
+    constexpr int LD = COUT + 4;                 // padded tile row: conflict-free 16-byte stores by consecutive pixels
+    extern __shared__ __align__(16) float stem_smem[];
+    float* sw = stem_smem;                       // [K][COUT]
+    float* tile = stem_smem + K * COUT;          // [64][LD]
     for (int i = threadIdx.x; i < K * COUT; i += blockDim.x) {
         const int co = i % COUT, k = i / COUT;
         sw[i] = w[(size_t)co * K + k];  // OIHW: k = ci*9 + ky*3 + kx
@@ -123,56 +130,90 @@ stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const
     const int pl = threadIdx.x & 63;
     for (int pix0 = blockIdx.x * 64; pix0 < total; pix0 += gridDim.x * 64) {
         const int pix = pix0 + pl;
-        if (pix >= total) continue;
-        const int n = pix / HW;
-        const int rem = pix - n * HW;
-        const int hy = rem / W, wx = rem - hy * W;
-        float v[K];
+        const bool live = pix < total;
+        float acc[CPT];
 #pragma unroll
-        for (int ci = 0; ci < CIN; ++ci) {
-            const float* xp = x + ((size_t)n * CIN + ci) * HW;
+        for (int j = 0; j < CPT; ++j) acc[j] = 0.f;
+        if (live) {
+            const int n = pix / HW;
+            const int rem = pix - n * HW;
+            const int hy = rem / W, wx = rem - hy * W;
+            float v[K];
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int yy = hy + ky - 1;
+            for (int ci = 0; ci < CIN; ++ci) {
+                const float* xp = x + ((size_t)n * CIN + ci) * HW;
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int xx = wx + kx - 1;
-                    v[ci * 9 + ky * 3 + kx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xp + yy * W + xx) : 0.f;
+                for (int ky = 0; ky < 3; ++ky) {
+                    const int yy = hy + ky - 1;
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int xx = wx + kx - 1;
+                        v[ci * 9 + ky * 3 + kx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xp + yy * W + xx) : 0.f;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) acc[j] = bias ? __ldg(bias + cg * CPT + j) : 0.f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float4* wrow = reinterpret_cast<const float4*>(sw + k * COUT + cg * CPT);
+#pragma unroll
+                for (int j = 0; j < CPT / 4; ++j) {
+                    const float4 w4 = wrow[j];
+                    acc[4 * j] += v[k] * w4.x; acc[4 * j + 1] += v[k] * w4.y;
+                    acc[4 * j + 2] += v[k] * w4.z; acc[4 * j + 3] += v[k] * w4.w;
                 }
             }
         }
-        float acc[CPT];
+        // stage the tile (rows of dead pixels are zero: they add nothing to the statistics and are not stored)
+        float4* trow = reinterpret_cast<float4*>(tile + pl * LD + cg * CPT);
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) acc[j] = bias ? __ldg(bias + cg * CPT + j) : 0.f;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float4* wrow = reinterpret_cast<const float4*>(sw + k * COUT + cg * CPT);
-#pragma unroll
-            for (int j = 0; j < CPT / 4; ++j) {
-                const float4 w4 = wrow[j];
-                acc[4 * j] += v[k] * w4.x; acc[4 * j + 1] += v[k] * w4.y;
-                acc[4 * j + 2] += v[k] * w4.z; acc[4 * j + 3] += v[k] * w4.w;
-            }
+        for (int j = 0; j < CPT / 4; ++j) trow[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        __syncthreads();
+        const int rows = min(64, total - pix0);
+        float4* og = reinterpret_cast<float4*>(out + (size_t)pix0 * COUT);
+        for (int i = threadIdx.x; i < rows * (COUT / 4); i += blockDim.x) {
+            const int r = i / (COUT / 4), c4 = i - r * (COUT / 4);
+            og[i] = *reinterpret_cast<const float4*>(tile + r * LD + 4 * c4);
         }
-        float4* o = reinterpret_cast<float4*>(out + (size_t)pix * COUT + cg * CPT);
-#pragma unroll
-        for (int j = 0; j < CPT / 4; ++j) o[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        if (stat_parts != nullptr && threadIdx.x < COUT) {
+            float sx = 0.f, sy = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 64; ++r) {
+                const float t = tile[r * LD + threadIdx.x];
+                sx += t;
+                sy += t * t;
+            }
+            stat_parts[(size_t)(pix0 >> 6) * COUT + threadIdx.x] = make_float2(sx, sy);   // (n * HW/64 + slot) == pix0 / 64
+        }
+        __syncthreads();
     }
 }
 
 template <int CIN>
-static int launch_stem(const float* x, const float* w, const float* bias, float* out, int N, int H, int W, int Cout,
-                       cudaStream_t st) {
+static int launch_stem(const float* x, const float* w, const float* bias, float* out, float2* stat_parts, int N, int H, int W,
+                       int Cout, cudaStream_t st) {
     long long blocks = ((long long)N * H * W + 63) / 64;
-    const long long cap = (long long)num_sms() * 16;
+    const long long cap = (long long)num_sms() * 3;
     if (blocks > cap) blocks = cap;
+    const size_t smem = ((size_t)CIN * 9 * Cout + 64 * (size_t)(Cout + 4)) * sizeof(float);
+#define NDB_STEM_CASE(CPT)                                                                                              \
+    {                                                                                                                   \
+        static bool attr = false;                                                                                       \
+        if (!attr) {                                                                                                    \
+            cudaFuncSetAttribute(stem_conv_kernel<CIN, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);  \
+            attr = true;                                                                                                \
+        }                                                                                                               \
+        stem_conv_kernel<CIN, CPT><<<(int)blocks, 256, smem, st>>>(x, w, bias, out, stat_parts, N, H, W);               \
+    }
     switch (Cout) {
-        case 64: stem_conv_kernel<CIN, 16><<<(int)blocks, 256, 0, st>>>(x, w, bias, out, N, H, W); break;
-        case 128: stem_conv_kernel<CIN, 32><<<(int)blocks, 256, 0, st>>>(x, w, bias, out, N, H, W); break;
-        case 192: stem_conv_kernel<CIN, 48><<<(int)blocks, 256, 0, st>>>(x, w, bias, out, N, H, W); break;
-        case 256: stem_conv_kernel<CIN, 64><<<(int)blocks, 256, 0, st>>>(x, w, bias, out, N, H, W); break;
+        case 64: NDB_STEM_CASE(16) break;
+        case 128: NDB_STEM_CASE(32) break;
+        case 192: NDB_STEM_CASE(48) break;
+        case 256: NDB_STEM_CASE(64) break;
         default: return NDB_ERR_UNSUPPORTED;
     }
+#undef NDB_STEM_CASE
     return NDB_OK;
 }
 
@@ -319,17 +360,19 @@ extern "C" int ndb_embed(const float* t, const int64_t* y, const float* freqs, i
     return launch_status("ndb_embed");
 }
 
-extern "C" int ndb_stem_conv(const float* x_nchw, const float* w_oihw, const float* bias, float* out_nhwc, int N,
-                             int Cin, int H, int W, int Cout, void* stream) {
+extern "C" int ndb_stem_conv(const float* x_nchw, const float* w_oihw, const float* bias, float* out_nhwc, void* stat_parts,
+                             int N, int Cin, int H, int W, int Cout, void* stream) {
     NDB_CHECK_ARG(x_nchw && w_oihw && out_nhwc);
     NDB_CHECK_ARG(Cin >= 1 && Cin <= 4);
+    NDB_CHECK_ARG(stat_parts == nullptr || (H * W) % 64 == 0);
     cudaStream_t st = (cudaStream_t)stream;
+    float2* sp = reinterpret_cast<float2*>(stat_parts);
     int rc;
     switch (Cin) {
-        case 1: rc = launch_stem<1>(x_nchw, w_oihw, bias, out_nhwc, N, H, W, Cout, st); break;
-        case 2: rc = launch_stem<2>(x_nchw, w_oihw, bias, out_nhwc, N, H, W, Cout, st); break;
-        case 3: rc = launch_stem<3>(x_nchw, w_oihw, bias, out_nhwc, N, H, W, Cout, st); break;
-        default: rc = launch_stem<4>(x_nchw, w_oihw, bias, out_nhwc, N, H, W, Cout, st); break;
+        case 1: rc = launch_stem<1>(x_nchw, w_oihw, bias, out_nhwc, sp, N, H, W, Cout, st); break;
+        case 2: rc = launch_stem<2>(x_nchw, w_oihw, bias, out_nhwc, sp, N, H, W, Cout, st); break;
+        case 3: rc = launch_stem<3>(x_nchw, w_oihw, bias, out_nhwc, sp, N, H, W, Cout, st); break;
+        default: rc = launch_stem<4>(x_nchw, w_oihw, bias, out_nhwc, sp, N, H, W, Cout, st); break;
     }
     if (rc != NDB_OK) {
         std::fprintf(stderr, "[ndb200] ndb_stem_conv: unsupported width %d (model_channels must be 64, 128, 192 or 256)\n", Cout);

@@ -227,9 +227,14 @@ class UNetEngine:
             x = self._conv([(cols, stem_wp)], R, R, C0, want_stats=True, bias=stem_b)
         else:
             stem_w = self._copy_param(stem.weight); stem_b = self._copy_param(stem.bias)
-            x = _Act(self.pool.get((B, R, R, C0), torch.float32), self._stats_buf(C0))
-            self.steps.append(lambda: ops.stem_conv(self.x_in, stem_w, stem_b, out=x.t))
-            self._emit_stats_kernel(x.t, x.stats)
+            if (R * R) % 64 == 0 and R * R // 64 <= 64:
+                # the stem kernel also emits the statistics of its output (one slot per 64-pixel block)
+                x = _Act(self.pool.get((B, R, R, C0), torch.float32), ops.stem_stats_alloc(B, R, R, C0, dev))
+                self.steps.append(lambda: ops.stem_conv(self.x_in, stem_w, stem_b, out=x.t, stats=x.stats))
+            else:
+                x = _Act(self.pool.get((B, R, R, C0), torch.float32), self._stats_buf(C0))
+                self.steps.append(lambda: ops.stem_conv(self.x_in, stem_w, stem_b, out=x.t))
+                self._emit_stats_kernel(x.t, x.stats)
         xs = [x]
         cur = x
         for seq in list(m.downsampling)[1:]:

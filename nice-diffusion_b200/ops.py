@@ -260,17 +260,31 @@ def embed(t, y, freqs, w0, b0, w2, b2, class_emb, emb_out=None, act_out=None, fm
     return emb_out, act_out
 
 
-def stem_conv(x_nchw, w, bias, out=None):
+def stem_conv(x_nchw, w, bias, out=None, stats=None):
+    """Exact fp32 stem conv. stats = (parts float32 [N, H*W/64, Cout, 2], counts int32 [N]) from stem_stats_alloc: the
+    kernel also writes the output's GroupNorm statistics (one slot per 64-pixel block)."""
     L.require_device(x_nchw, 'stem_conv')
     N, Cin, H, W = x_nchw.shape
     Cout = w.shape[0]
     if out is None:
         out = torch.empty((N, H, W, Cout), dtype=torch.float32, device=x_nchw.device)
+    sp = None
+    if stats is not None:
+        assert (H * W) % 64 == 0 and tuple(stats[0].shape) == (N, H * W // 64, Cout, 2)
+        sp = stats[0].data_ptr()
     _begin()
-    L.check(L.load().ndb_stem_conv(L.ptr(x_nchw), L.ptr(w), L.ptr(bias), L.ptr(out), N, Cin, H, W, Cout,
+    L.check(L.load().ndb_stem_conv(L.ptr(x_nchw), L.ptr(w), L.ptr(bias), L.ptr(out), sp, N, Cin, H, W, Cout,
                                    L.stream_ptr()), 'ndb_stem_conv')
     _count('stem_conv')
     return out
+
+
+def stem_stats_alloc(N, H, W, cout, device):
+    """Statistics buffers in the layout ndb_stem_conv writes: every one of the H*W/64 slots of an image is used."""
+    assert (H * W) % 64 == 0
+    smax = H * W // 64
+    return (torch.zeros((N, smax, cout, 2), dtype=torch.float32, device=device),
+            torch.full((N,), smax, dtype=torch.int32, device=device))
 
 
 def stem_im2col(x_nchw, out=None, fmt=L.FMT_FP16):

@@ -455,3 +455,33 @@ def test_stem_conv_as_one_k_block_gemm(cuda_dev, N, Cin, H, W, Cout):
     ref16 = F.conv2d(x.half().float(), w.half().float(), b, padding=1)
     assert rel_err(out.permute(0, 3, 1, 2), ref16) < 2e-5
     assert rel_err(out.permute(0, 3, 1, 2), F.conv2d(x, w, b, padding=1)) < 3e-3
+
+
+@pytest.mark.parametrize('N,Cin,H,W,Cout', [(3, 3, 64, 64, 192), (2, 1, 16, 16, 64), (5, 3, 8, 24, 128), (2, 4, 32, 32, 256)])
+def test_stem_conv_fused_statistics(cuda_dev, N, Cin, H, W, Cout):
+    """Exact-fp32 stem conv: output == F.conv2d, statistics slots (one per 64-pixel block) == sums of the stored output, and
+    a GroupNorm fed by them == torch; guard band around the output untouched; bit-identical re-run."""
+    ops, L = _ops()
+    g = torch.Generator(device='cpu').manual_seed(N + Cin + Cout)
+    x = torch.randn(N, Cin, H, W, generator=g).to(cuda_dev)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(9 * Cin)).to(cuda_dev)
+    b = (0.3 * torch.randn(Cout, generator=g)).to(cuda_dev)
+    st = ops.stem_stats_alloc(N, H, W, Cout, cuda_dev)
+    st[0].fill_(float('nan'))
+    out, chk = _guarded((N, H, W, Cout), torch.float32, cuda_dev)
+    ops.stem_conv(x, w, b, out=out, stats=st)
+    chk()
+    ref = F.conv2d(x, w, b, padding=1)
+    assert rel_err(out.permute(0, 3, 1, 2), ref) < 1e-5
+    o = out.double().flatten(1, 2)
+    tot = ops.stats_totals(st)
+    assert torch.allclose(tot[:, :, 0], o.sum(1), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(tot[:, :, 1], (o * o).sum(1), rtol=1e-5, atol=1e-3)
+    st2 = ops.stem_stats_alloc(N, H, W, Cout, cuda_dev)
+    out2 = ops.stem_conv(x, w, b, stats=st2)
+    assert torch.equal(out, out2) and torch.equal(st[0], st2[0])
+    gamma = (1 + 0.1 * torch.randn(Cout, generator=g)).to(cuda_dev)
+    beta = (0.1 * torch.randn(Cout, generator=g)).to(cuda_dev)
+    a = ops.gn_apply(out, st, gamma, beta, silu=True)
+    refn = F.silu(F.group_norm(ref, 32, gamma, beta, eps=1e-5))
+    assert rel_err(a.permute(0, 3, 1, 2), refn) < 1.5e-3
