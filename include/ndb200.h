@@ -140,6 +140,9 @@ typedef struct {
                                           epilogue as a plain residual */
     int32_t operand_format;
     float eps;
+    int32_t cpg;                       /* channels per group; 0 = (C0 + C1) / 32. Non-zero: this call normalises a channel SLICE
+                                          of a wider GroupNorm(32) input (the skip half of a concatenated tensor) whose groups
+                                          do not straddle the slice: (C0 + C1) / cpg <= 32 groups, gamma / beta already offset */
 } ndb_gn_apply_params;
 
 int ndb_gn_apply(const ndb_gn_apply_params* p, void* stream);

@@ -50,7 +50,7 @@ class GnApplyParams(C.Structure):
                 ('pre_add', C.c_void_p), ('ld_pre', C.c_int32),
                 ('silu', C.c_int32), ('resample', C.c_int32),
                 ('out', C.c_void_p), ('raw16', C.c_void_p), ('x0_is16', C.c_int32), ('pool32', C.c_void_p),
-                ('operand_format', C.c_int32), ('eps', C.c_float)]
+                ('operand_format', C.c_int32), ('eps', C.c_float), ('cpg', C.c_int32)]
 
 
 class StepParams(C.Structure):

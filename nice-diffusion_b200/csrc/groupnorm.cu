@@ -130,6 +130,7 @@ struct GnApplyArgs {
     const float* pre_add; int ld_pre;
     int silu, resample;
     uint16_t* out; uint16_t* raw16;
+    int cpg;         // channels per group; 0 = (C0 + C1) / 32. A slice of a wider normalised tensor passes the parent's value
     int x0_is16;     // x0 holds 16-bit values (operand_format) instead of fp32
     float* pool32;   // DOWN2 only: fp32 2x2 mean of the raw input (the x_resample operand of a down ResBlock)
     float eps;
@@ -152,7 +153,8 @@ gn_apply_kernel(const GnApplyArgs p) {
     const int C = p.C0 + p.C1;
     const int V8 = C >> 3;
     const int n = blockIdx.y;
-    const int cpg = C / kGroups;
+    const int cpg = p.cpg > 0 ? p.cpg : C / kGroups;
+    const int ngroups = C / cpg;          // <= 32
     float* sa = sm_ab;
     float* sb = sm_ab + C;
     float* sp = sm_ab + 2 * C;
@@ -227,7 +229,7 @@ gn_apply_kernel(const GnApplyArgs p) {
         double S = 0.0, SS = 0.0;
         const int cnt0 = p.counts0[n];
         const int cnt1 = p.parts1 ? p.counts1[n] : 0;
-        for (int k = sub; k < cpg; k += 8) {
+        for (int k = sub; g < ngroups && k < cpg; k += 8) {
             const int c = g * cpg + k;
             double s1 = 0.0, s2 = 0.0;
             // the slot partials of a channel are fetched four at a time (independent loads; a one-load-per-iteration loop
@@ -256,7 +258,7 @@ gn_apply_kernel(const GnApplyArgs p) {
             S += __shfl_xor_sync(0xffffffffu, S, o);
             SS += __shfl_xor_sync(0xffffffffu, SS, o);
         }
-        if (sub == 0) {
+        if (sub == 0 && g < ngroups) {
             const double inv_cnt = 1.0 / ((double)cpg * P);
             const double mean = S * inv_cnt;
             double var = SS * inv_cnt - mean * mean;
@@ -526,6 +528,8 @@ extern "C" int ndb_gn_apply(const ndb_gn_apply_params* q, void* stream) {
     a.out = (uint16_t*)q->out; a.raw16 = (uint16_t*)q->raw16;
     a.pool32 = q->pool32;
     a.x0_is16 = q->x0_is16;
+    a.cpg = q->cpg;
+    if (q->cpg > 0) NDB_CHECK_ARG(C % q->cpg == 0 && C / q->cpg <= kGroups);
     if (q->x0_is16) NDB_CHECK_ARG(q->x1 == nullptr && q->resample == NDB_RESAMPLE_NONE && q->raw16 == nullptr);
     NDB_CHECK_ARG(q->pool32 == nullptr || q->resample == NDB_RESAMPLE_DOWN2);
     a.eps = q->eps;

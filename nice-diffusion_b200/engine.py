@@ -64,6 +64,10 @@ class UNetEngine:
         self.n_embed_steps = 0   # leading steps (embedding front end) that run on a side stream ...
         self.join_idx = None     # ... until the first step that consumes the step embedding
         self.side = None
+        self.early = []          # (launch, event): skip-half norms of the up path, run on a second side stream from ...
+        self.early_fork_idx = None   # ... the first step of the middle block (the low-resolution levels leave HBM idle)
+        self.side2 = None
+        self.n_aux_steps = 0     # entries of self.steps that are stream waits, not kernels
         self.packers = []        # callables that (re)fill the weight arena from the live parameters
         self.graph = None
         self.sig = None
@@ -81,12 +85,14 @@ class UNetEngine:
         self.packers.append(lambda: buf.copy_(p.detach()))
         return buf
 
-    def _packed(self, p, cout_pad=None):
+    def _packed(self, p, cout_pad=None, cin_off=0, cin_len=None):
         cout = p.shape[0]
         k = p.shape[2] if p.dim() >= 3 else 1
         cp = ops.pad16(cout) if cout_pad is None else cout_pad
-        buf = torch.empty((k * k, cp, p.shape[1]), dtype=self.dt16, device=self.device)
-        self.packers.append(lambda: ops.pack_conv_weight(p.detach().to(self.device), cout_pad=cp, fmt=self.fmt, out=buf))
+        cl = p.shape[1] - cin_off if cin_len is None else cin_len
+        buf = torch.empty((k * k, cp, cl), dtype=self.dt16, device=self.device)
+        self.packers.append(lambda: ops.pack_conv_weight(p.detach().to(self.device), cout_pad=cp, cin_off=cin_off, cin_len=cl,
+                                                         fmt=self.fmt, out=buf))
         return buf
 
     def _bias_sum(self, p1, p2):
@@ -240,6 +246,7 @@ class UNetEngine:
         for seq in list(m.downsampling)[1:]:
             cur = self._run_sequential(seq, cur, None, input_saved=True)
             xs.append(cur)
+        self.early_fork_idx = len(self.steps)
         cur = self._run_sequential(m.middle_block, cur, None, input_saved=True)
         for seq in m.upsampling:
             skip = xs.pop()
@@ -255,7 +262,7 @@ class UNetEngine:
         self.steps.append(lambda: ops.gn_apply(cur.t, cur.stats, g, bt, silu=True, out=a, fmt=fmt, eps=gn.eps))
         self.steps.append(lambda: ops.conv_gemm([(a, wp)], B, H, H, m.out_channels, bias=bp,
                                                 out_kind=L.OUT_F32_NCHW, out=self.out, fmt=fmt))
-        self.num_kernels = len(self.steps) + 1   # the embedding front end is two launches
+        self.num_kernels = len(self.steps) - self.n_aux_steps + len(self.early) + 1   # the embedding front end is two launches
 
     def _all_channels(self):
         cs = set()
@@ -302,10 +309,24 @@ class UNetEngine:
 
         g1 = self._copy_param(rb.in_norm.weight); b1 = self._copy_param(rb.in_norm.bias)
         g2 = self._copy_param(rb.out_norm.weight); b2 = self._copy_param(rb.out_norm.bias)
-        w_in = self._packed(rb.in_conv.weight); bias_in = self._copy_param(rb.in_conv.bias)
+        bias_in = self._copy_param(rb.in_conv.bias)
         w_out = self._packed(rb.out_conv.weight)
+        # Concatenated input [x ; skip] whose GroupNorm groups do not straddle the seam: the skip half depends only on the
+        # down path, so its norm + SiLU + 16-bit cast run EARLY on a side stream (forked at the middle block, when the small
+        # feature maps leave HBM bandwidth idle); the convs read the two halves as separate K segments.
+        cpg = Cin // 32
+        split = (skip is not None and rb.mode == 'same' and conv_skip and Cin % 32 == 0 and C0 % cpg == 0
+                 and self.early_fork_idx is not None and not os.environ.get('NDB_DISABLE_SPLIT_NORM'))
+        if split:
+            w_in_a = self._packed(rb.in_conv.weight, cin_off=0, cin_len=C0)
+            w_in_b = self._packed(rb.in_conv.weight, cin_off=C0, cin_len=C1)
+            w_skip_a = self._packed(rb.skip.weight, cin_off=0, cin_len=C0)
+            w_skip_b = self._packed(rb.skip.weight, cin_off=C0, cin_len=C1)
+        else:
+            w_in = self._packed(rb.in_conv.weight)
         if conv_skip:
-            w_skip = self._packed(rb.skip.weight)
+            if not split:
+                w_skip = self._packed(rb.skip.weight)
             bias_out = self._bias_sum(rb.out_conv.bias, rb.skip.bias)
         else:
             bias_out = self._copy_param(rb.out_conv.bias)
@@ -318,30 +339,48 @@ class UNetEngine:
             scale = shift = None
             pre = self.emb_all[:, off:off + Cout]
 
-        a1 = pool.get((B, Ho, Wo, Cin), self.dt16)
-        raw = pool.get((B, Ho, Wo, Cin), self.dt16) if conv_skip else None
-        a2 = pool.get((B, Ho, Wo, Cout), self.dt16)
         eps1, eps2 = rb.in_norm.eps, rb.out_norm.eps
-        x1 = skip.t if skip is not None else None
-        s1 = skip.stats if skip is not None else None
-
-        # down blocks with an identity skip: the apply kernel (which reads x anyway) also leaves avg_pool2d(x) in fp32,
-        # so the out_conv epilogue adds it as a plain residual instead of gathering four taps per element
-        pooled = pool.get((B, Ho, Wo, Cin), torch.float32) if (rb.mode == 'down' and not conv_skip) else None
-        self.steps.append(lambda: ops.gn_apply(x.t, x.stats, g1, b1, x1=x1, stats1=s1, silu=True, resample=mode,
-                                               out=a1, raw16=raw, fmt=fmt, eps=eps1, pool32=pooled))
-        if self.model.h_fp16 and ops.conv_stats_supported(B, Ho, Wo):
-            # `h` only feeds the out_norm: 16-bit storage halves its write + read (statistics still come from the fp32
-            # accumulators in the epilogue)
-            h = self._conv([(a1, w_in)], Ho, Wo, Cout, want_stats=True, bias=bias_in, out_kind=L.OUT_F16_NHWC,
-                           out=pool.get((B, Ho, Wo, Cout), self.dt16))
+        a2 = pool.get((B, Ho, Wo, Cout), self.dt16)
+        pooled = None
+        if split:
+            a1 = pool.get((B, H, W, C0), self.dt16)
+            raw = pool.get((B, H, W, C0), self.dt16)
+            a1b = torch.empty((B, H, W, C1), dtype=self.dt16, device=self.device)     # live from the fork to this block
+            rawb = torch.empty((B, H, W, C1), dtype=self.dt16, device=self.device)
+            g1a, b1a, g1b, b1b = g1[:C0], b1[:C0], g1[C0:], b1[C0:]
+            sk = skip
+            ev = torch.cuda.Event()
+            self.early.append((lambda: ops.gn_apply(sk.t, sk.stats, g1b, b1b, silu=True, out=a1b, raw16=rawb, fmt=fmt,
+                                                    eps=eps1, cpg=cpg), ev))
+            self.steps.append(lambda: ops.gn_apply(x.t, x.stats, g1a, b1a, silu=True, out=a1, raw16=raw, fmt=fmt, eps=eps1,
+                                                   cpg=cpg))
+            self.steps.append(lambda: torch.cuda.current_stream(self.device).wait_event(ev))
+            self.n_aux_steps += 1
+            h = self._conv([(a1, w_in_a), (a1b, w_in_b)], Ho, Wo, Cout, want_stats=True, bias=bias_in)
         else:
-            h = self._conv([(a1, w_in)], Ho, Wo, Cout, want_stats=True, bias=bias_in)
+            a1 = pool.get((B, Ho, Wo, Cin), self.dt16)
+            raw = pool.get((B, Ho, Wo, Cin), self.dt16) if conv_skip else None
+            x1 = skip.t if skip is not None else None
+            s1 = skip.stats if skip is not None else None
+            # down blocks with an identity skip: the apply kernel (which reads x anyway) also leaves avg_pool2d(x) in fp32,
+            # so the out_conv epilogue adds it as a plain residual instead of gathering four taps per element
+            pooled = pool.get((B, Ho, Wo, Cin), torch.float32) if (rb.mode == 'down' and not conv_skip) else None
+            self.steps.append(lambda: ops.gn_apply(x.t, x.stats, g1, b1, x1=x1, stats1=s1, silu=True, resample=mode,
+                                                   out=a1, raw16=raw, fmt=fmt, eps=eps1, pool32=pooled))
+            if self.model.h_fp16 and ops.conv_stats_supported(B, Ho, Wo):
+                # `h` only feeds the out_norm: 16-bit storage halves its write + read (statistics still come from the fp32
+                # accumulators in the epilogue)
+                h = self._conv([(a1, w_in)], Ho, Wo, Cout, want_stats=True, bias=bias_in, out_kind=L.OUT_F16_NHWC,
+                               out=pool.get((B, Ho, Wo, Cout), self.dt16))
+            else:
+                h = self._conv([(a1, w_in)], Ho, Wo, Cout, want_stats=True, bias=bias_in)
         if self.join_idx is None:
             self.join_idx = len(self.steps)     # first consumer of the step embedding
         self.steps.append(lambda: ops.gn_apply(h.t, h.stats, g2, b2, scale=scale, shift=shift, pre_add=pre, silu=True,
                                                out=a2, fmt=fmt, eps=eps2))
-        if conv_skip:
+        if split:
+            out = self._conv([(a2, w_out), (raw, w_skip_a), (rawb, w_skip_b)], Ho, Wo, Cout, want_stats=True, bias=bias_out)
+        elif conv_skip:
             # 1x1 (or 3x3 when use_conv) skip conv as an extra K range of the same GEMM
             out = self._conv([(a2, w_out), (raw, w_skip)], Ho, Wo, Cout, want_stats=True, bias=bias_out)
         else:
@@ -424,20 +463,28 @@ class UNetEngine:
         independent of x) runs on a side stream next to the stem conv, its statistics and the first norm + conv; the
         streams join at the first kernel that reads the embedding. Under graph capture this becomes a fork / join."""
         ne = self.n_embed_steps
-        if ne == 0 or self.join_idx is None:
-            for f in self.steps:
-                f()
-            return
         cur = torch.cuda.current_stream(self.device)
-        if self.side is None:
-            self.side = torch.cuda.Stream(device=self.device)
-        self.side.wait_stream(cur)
-        with torch.cuda.stream(self.side):
-            for f in self.steps[:ne]:
-                f()
-        for i in range(ne, len(self.steps)):
-            if i == self.join_idx:
+        fork_embed = ne > 0 and self.join_idx is not None
+        if fork_embed:
+            if self.side is None:
+                self.side = torch.cuda.Stream(device=self.device)
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                for f in self.steps[:ne]:
+                    f()
+        for i in range(ne if fork_embed else 0, len(self.steps)):
+            if fork_embed and i == self.join_idx:
                 cur.wait_stream(self.side)
+            if self.early and i == self.early_fork_idx:
+                # skip-half norms of the up path: everything they read exists by now; each records an event its consumer
+                # waits on
+                if self.side2 is None:
+                    self.side2 = torch.cuda.Stream(device=self.device)
+                self.side2.wait_stream(cur)
+                with torch.cuda.stream(self.side2):
+                    for f, ev in self.early:
+                        f()
+                        ev.record(self.side2)
             self.steps[i]()
 
     def run_static(self):

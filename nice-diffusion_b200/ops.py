@@ -182,7 +182,7 @@ def stats_totals(stats):
 
 
 def gn_apply(x0, stats0, gamma, beta, x1=None, stats1=None, scale=None, shift=None, pre_add=None, silu=True,
-             resample=L.RESAMPLE_NONE, out=None, raw16=None, want_raw16=False, fmt=L.FMT_FP16, eps=1e-5, pool32=None):
+             resample=L.RESAMPLE_NONE, out=None, raw16=None, want_raw16=False, fmt=L.FMT_FP16, eps=1e-5, pool32=None, cpg=0):
     L.require_device(x0, 'gn_apply')
     N, H, W, C0 = x0.shape
     C1 = x1.shape[-1] if x1 is not None else 0
@@ -219,6 +219,7 @@ def gn_apply(x0, stats0, gamma, beta, x1=None, stats1=None, scale=None, shift=No
     p.pool32 = pool32.data_ptr() if pool32 is not None else None
     p.operand_format = fmt
     p.eps = eps
+    p.cpg = cpg
     _begin()
     L.check(L.load().ndb_gn_apply(C.byref(p), L.stream_ptr()), 'ndb_gn_apply')
     _count('gn_apply', 0, 'N{} {}x{} C{} rs{} raw{}'.format(N, H, W, C0 + C1, resample, int(raw16 is not None)))
