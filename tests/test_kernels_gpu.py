@@ -485,3 +485,25 @@ def test_stem_conv_fused_statistics(cuda_dev, N, Cin, H, W, Cout):
     a = ops.gn_apply(out, st, gamma, beta, silu=True)
     refn = F.silu(F.group_norm(ref, 32, gamma, beta, eps=1e-5))
     assert rel_err(a.permute(0, 3, 1, 2), refn) < 1.5e-3
+
+
+@pytest.mark.parametrize('C0,C1', [(192, 192), (128, 128), (64, 192), (768, 256)])
+def test_groupnorm_apply_channel_slices(cuda_dev, C0, C1):
+    """GroupNorm(32) over a concatenated tensor whose groups do not straddle the seam == the two halves normalised separately
+    with the parent's group width (`cpg`): what lets the engine run the skip half of an up block early."""
+    ops, L = _ops()
+    g = torch.Generator(device='cpu').manual_seed(C0 + C1)
+    N, H, W = 3, 8, 8
+    cpg = (C0 + C1) // 32
+    assert C0 % cpg == 0
+    x0 = torch.randn(N, H, W, C0, generator=g).to(cuda_dev) * 2 + 0.5
+    x1 = torch.randn(N, H, W, C1, generator=g).to(cuda_dev) - 1.0
+    gamma = (1 + 0.1 * torch.randn(C0 + C1, generator=g)).to(cuda_dev)
+    beta = (0.1 * torch.randn(C0 + C1, generator=g)).to(cuda_dev)
+    s0, s1 = ops.gn_stats(x0), ops.gn_stats(x1)
+    full, raw = ops.gn_apply(x0, s0, gamma, beta, x1=x1, stats1=s1, silu=True, want_raw16=True)
+    a, ra = ops.gn_apply(x0, s0, gamma[:C0], beta[:C0], silu=True, want_raw16=True, cpg=cpg)
+    b, rb = ops.gn_apply(x1, s1, gamma[C0:], beta[C0:], silu=True, want_raw16=True, cpg=cpg)
+    assert torch.equal(torch.cat([a, b], -1), full) and torch.equal(torch.cat([ra, rb], -1), raw)
+    ref = F.silu(F.group_norm(torch.cat([x0, x1], -1).permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-5))
+    assert rel_err(full.permute(0, 3, 1, 2), ref) < 1.5e-3
