@@ -185,3 +185,20 @@ def test_invalid_arguments_return_error_codes_without_a_gpu():
     assert lib.ndb_gn_apply(None, None) == _lib.ERR_INVALID
     assert lib.ndb_sampler_step(None, None) == _lib.ERR_INVALID
     assert lib.ndb_gn_stats_workspace_bytes(2, 64, 64) > 0
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package, the CLI or the C sources may reference it (bench.py may,
+    for its cpu_baseline / --impl reference legs only)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r'^\s*(from|import)\s+oracle\b', re.M)
+    checked = 0
+    for base, _, files in os.walk(os.path.join(root, 'nice-diffusion_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(base, f), errors='ignore').read()
+                assert not pat.search(text), os.path.join(base, f)
+                checked += 1
+    for f in ('scripts/sample.py', 'nice_diffusion_b200.py'):
+        assert not pat.search(open(os.path.join(root, f)).read()), f
+    assert checked > 10
