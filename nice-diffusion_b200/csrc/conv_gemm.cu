@@ -303,7 +303,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             int sb = 0;
             long long* row_tab = epi_rows + (warp - 2) * 128;     // [2 tile parities][32 rows]: residual element offsets
             const bool has_res = p.res_mode == NDB_RES_SAME;
-            const bool transposed = kStats || has_res;
+            const bool transposed = has_res;     // in-place pass with lanes along channels (bias + residual)
             // the box covered by this warp's 32 rows
             const int r0 = q * 32;
             const int btn = r0 / pix_per_img;
@@ -418,6 +418,23 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                                 // 64-byte rows, SWIZZLE_64B: 16-byte chunk index ^ bits [1,2] of the row
                                 *reinterpret_cast<uint4*>(sbuf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = w4;
                             }
+                        }
+                        if (kStats) {
+                            // statistics without a residual: the staged values are final, the lanes-along-channels pass only
+                            // READS them for the column sums (no write-back: less shared-memory traffic next to the MMAs)
+                            __syncwarp();
+                            const int col = c0 + lane;
+                            const unsigned okmask = (col < p.cout) ? vmask : 0u;
+                            const int lswz = lane >> 2, lw = lane & 3;
+                            float cs = 0.f, css = 0.f;
+#pragma unroll
+                            for (int r = 0; r < 32; ++r) {
+                                const float t = sf[r * 32 + (((lswz ^ (r & 7)) << 2) | lw)];
+                                const float v = ((okmask >> r) & 1u) ? t : 0.f;
+                                cs += v;
+                                css += v * v;
+                            }
+                            part_smem[(stat_buf * 4 + q) * p.block_n + ch * 32 + lane] = make_float2(cs, css);
                         }
                     } else {
 #pragma unroll
