@@ -255,6 +255,8 @@ def main():
 
     # ---- kernel-only timing: K graph replays of one denoising step, inputs resident in HBM ----
     runner = diff.make_step_runner(x_host.to(dev), {'y': labels_host.to(dev)})
+    if args.eager:
+        runner.eng.serial = True          # profiling runs: one stream, kernels do not overlap
     for _ in range(args.warmup):
         runner.step()
     barrier()

@@ -416,14 +416,16 @@ class _StepRunner:
         """Eager pass of one step with CUDA events around every launch (bench.py roofline). Restores the state."""
         d, eng, st = self.diff, self.eng, self.st
         saved = (eng.x_in.clone(), st['t_step'].clone(), eng.t_in.clone())
-        self._launch()                      # warm
-        torch.cuda.synchronize(d.device)
-        ops.PROFILE = []
+        eng.serial = True                   # one stream: overlapping kernels would inflate each other's event times
         try:
+            self._launch()                  # warm
+            torch.cuda.synchronize(d.device)
+            ops.PROFILE = []
             self._launch()
             torch.cuda.synchronize(d.device)
             summary = ops.profile_summary(ops.PROFILE)
         finally:
             ops.PROFILE = None
+            eng.serial = False
         eng.x_in.copy_(saved[0]); st['t_step'].copy_(saved[1]); eng.t_in.copy_(saved[2])
         return summary

@@ -68,6 +68,7 @@ class UNetEngine:
         self.early_fork_idx = None   # ... the first step of the middle block (the low-resolution levels leave HBM idle)
         self.side2 = None
         self.n_aux_steps = 0     # entries of self.steps that are stream waits, not kernels
+        self.serial = False      # True: no side streams (per-kernel timing passes want kernels that do not overlap)
         self.packers = []        # callables that (re)fill the weight arena from the live parameters
         self.graph = None
         self.sig = None
@@ -464,6 +465,14 @@ class UNetEngine:
         streams join at the first kernel that reads the embedding. Under graph capture this becomes a fork / join."""
         ne = self.n_embed_steps
         cur = torch.cuda.current_stream(self.device)
+        if self.serial:
+            for i, f in enumerate(self.steps):
+                if self.early and i == self.early_fork_idx:
+                    for g, ev in self.early:
+                        g()
+                        ev.record(cur)
+                f()
+            return
         fork_embed = ne > 0 and self.join_idx is not None
         if fork_embed:
             if self.side is None:

@@ -18,6 +18,7 @@ diff = Diffusion(model=model, device=dev, **dkw); diff.noise = 'philox'
 x = torch.randn(B, model.in_channels, model.resolution, model.resolution, device=dev)
 y = torch.randint(1, 20, (B,), device=dev)
 runner = diff.make_step_runner(x, {'y': y})
+runner.eng.serial = True     # one stream: per-launch events must not overlap
 runner._launch(); runner._launch(); torch.cuda.synchronize()
 reps = 3
 acc = collections.OrderedDict()
