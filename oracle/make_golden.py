@@ -92,7 +92,8 @@ SCHEDULE_CASES = [(1000, 250, 'cosine'), (1000, 25, 'cosine'), (1000, 50, 'linea
                   (1000, 300, 'cosine'), (100, 10, 'constant'), (4000, 100, 'cosine')]
 
 
-def main():
+def main(only_unet=None):
+    """only_unet: list of config names -> regenerate just those UNet fixtures (skips schedules and trajectories)."""
     from oracle import CONFIGS
     from oracle.schedule import Tables
     from oracle.unet import unet_forward
@@ -106,8 +107,13 @@ def main():
 
     # ---- 1. schedules / respacing / tables ------------------------------------------------
     sched = {}
+    unet_cases = (('tiny', 2), ('tiny_legacy', 2), ('tiny_pool', 2), ('emnist', 2), ('in64', 1), ('in128', 1))
+    if only_unet:
+        SCHEDULE_LOCAL, unet_cases = [], tuple(c for c in unet_cases if c[0] in only_unet)
+    else:
+        SCHEDULE_LOCAL = SCHEDULE_CASES
     dummy = rm.DiffusionModel(**{k: v for k, v in CONFIGS['tiny'].items()})
-    for (T, R, name) in SCHEDULE_CASES:
+    for (T, R, name) in SCHEDULE_LOCAL:
         ref = rd.Diffusion(model=dummy, original_num_steps=T, rescaled_num_steps=R,
                            sampling_var_type='learned_interpolation', loss_type='hybrid',
                            beta_schedule=name, device=dev)
@@ -120,10 +126,11 @@ def main():
             assert a.dtype == np.float64 and np.array_equal(a, b), (key, n)
             sched[key + '/' + n] = a
         print('schedule', key, 'len', len(tab.betas), 'bit-exact')
-    np.savez_compressed(os.path.join(OUT, 'schedule.npz'), **sched)
+    if not only_unet:
+        np.savez_compressed(os.path.join(OUT, 'schedule.npz'), **sched)
 
     # ---- 2. UNet forward ---------------------------------------------------------------------
-    for cname, batch in (('tiny', 2), ('tiny_legacy', 2), ('tiny_pool', 2), ('emnist', 2), ('in64', 1)):
+    for cname, batch in unet_cases:
         cfg = CONFIGS[cname]
         sd = random_state_dict(cfg, seed=1234)
         ref_model = rm.DiffusionModel(**cfg).eval()
@@ -143,7 +150,7 @@ def main():
         np.savez_compressed(os.path.join(OUT, 'unet_{}.npz'.format(cname)), **save)
 
     # ---- 3. sampler trajectories ------------------------------------------------------------
-    for name, (cname, dkw, use_clf) in SAMPLER_CASES.items():
+    for name, (cname, dkw, use_clf) in ({} if only_unet else SAMPLER_CASES).items():
         cfg = CONFIGS[cname]
         sd = random_state_dict(cfg, seed=4321)
         ref_model = rm.DiffusionModel(**cfg).eval()
@@ -203,4 +210,5 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    import sys
+    main(only_unet=sys.argv[1].split(',') if len(sys.argv) > 1 else None)

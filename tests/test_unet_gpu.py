@@ -32,7 +32,7 @@ def norm_err(a, b):
     return float((a - b).abs().max() / b.abs().max())
 
 
-@pytest.mark.parametrize('name', ['tiny', 'tiny_legacy', 'tiny_pool', 'emnist', 'in64'])
+@pytest.mark.parametrize('name', ['tiny', 'tiny_legacy', 'tiny_pool', 'emnist', 'in64', 'in128'])
 def test_forward_matches_reference_golden(cuda_dev, name):
     cfg, sd, model = build(name, 1234, cuda_dev)
     g = np.load(os.path.join(GOLD, 'unet_{}.npz'.format(name)))
