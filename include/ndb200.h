@@ -245,8 +245,14 @@ int ndb_philox_normal(float* out, int B, int64_t per_sample, uint64_t seed, cons
 int ndb_qsample(const float* x0, const float* noise, const float* t, const float* sqrt_abar,
                 const float* sqrt_1m_abar, float* out, int B, int64_t per_sample, void* stream);
 
-/* [-1,1] float NCHW -> uint8 NHWC image, ((x+1)*127.5).clamp(0,255) truncated (sample.py:94,149). */
-int ndb_to_uint8(const float* x_nchw, uint8_t* out_nhwc, int B, int C, int H, int W, void* stream);
+/* [-1,1] float NCHW -> uint8 NHWC image, ((x+1)*127.5).clamp(0,255) truncated (sample.py:94,168).
+ * gray_invert (C == 1 only): the byte the reference CLI ends up storing for one-channel models -- it inverts the float
+ * image (sample.py:98-100), truncates (:168) and inverts again (:170-171): 255 - trunc(255 - v). */
+int ndb_to_uint8(const float* x_nchw, uint8_t* out_nhwc, int B, int C, int H, int W, int gray_invert, void* stream);
+
+/* measurement aid: writes the device's %globaltimer (ns) to *dst when everything enqueued before it on `stream` has
+ * completed (scripts/timeline.py brackets every launch of a step with these, inside the step's CUDA graph). */
+int ndb_timestamp(uint64_t* dst, void* stream);
 
 #ifdef __cplusplus
 }

@@ -89,7 +89,8 @@ SIGNATURES = {
     'ndb_advance_step': (_I, [_P, _I, _P, _I, _P, _P]),
     'ndb_philox_normal': (_I, [_P, _I, _I64, _U64, _P, C.c_int32, _P]),
     'ndb_qsample': (_I, [_P, _P, _P, _P, _P, _P, _I, _I64, _P]),
-    'ndb_to_uint8': (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    'ndb_to_uint8': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    'ndb_timestamp': (_I, [_P, _P]),
 }
 
 _lib = None
@@ -138,3 +139,8 @@ def require_device(t, what):
     if not t.is_cuda:
         raise NdbError('{}: tensor is on {} -- the ndb200 path runs on a B200 only (no CPU fallback)'.format(
             what, t.device))
+    # kernels are enqueued on the CURRENT device's current stream (stream_ptr): a tensor of another GPU would be
+    # launched on the wrong device. One process per GPU (torch.cuda.set_device) is the supported model.
+    if t.device.index != torch.cuda.current_device():
+        raise NdbError('{}: tensor is on cuda:{} but the current device is cuda:{} -- call torch.cuda.set_device() '
+                       '(one process per GPU)'.format(what, t.device.index, torch.cuda.current_device()))

@@ -382,11 +382,11 @@ extern "C" int ndb_attention(const void* qkv, void* out, int B, int T, int heads
         int rc = encode_tmap_16bit(&map, qkv, 4, dims, strides, box);
         if (rc != NDB_OK) return rc;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.pending()) {
         cudaFuncSetAttribute(attention_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_set = true;
+        attr_once.done();
     }
     dim3 grid((T + kAttnBM - 1) / kAttnBM, heads, B);
     if (operand_format == 0)

@@ -27,16 +27,31 @@ inline int launch_status(const char* what) {
     return NDB_OK;
 }
 
-inline int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
+// Per-device state (SM count, "kernel attributes set" flags) is indexed by the CURRENT device ordinal: function attributes
+// and SM counts belong to a device, and one process may drive several (the engines are keyed by device index).
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    return dev;
 }
+
+inline int num_sms() {
+    static int n[kMaxDevices] = {};
+    const int dev = current_device();
+    if (n[dev] == 0) {
+        cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (n[dev] <= 0) n[dev] = 148;
+    }
+    return n[dev];
+}
+
+// `static PerDeviceOnce once; if (once.pending()) { ...; once.done(); }` -- runs a block once per device
+struct PerDeviceOnce {
+    bool flag[kMaxDevices] = {};
+    bool pending() const { return !flag[current_device()]; }
+    void done() { flag[current_device()] = true; }
+};
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

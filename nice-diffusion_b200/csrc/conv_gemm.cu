@@ -977,7 +977,11 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     const int epi_bytes = a.epi_region + kEpiWarps * 128 * (int)sizeof(long long) +
                           2 * 4 * a.block_n * (int)sizeof(float2) +
                           (prm->stat_parts ? a.TN * prm->cout * (int)sizeof(float2) : 0);
-    const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - epi_bytes;
+    // NDB_GEMM_SMEM_KB (A/B switch): cap this kernel's shared memory so that blocks of the NEXT kernel (programmatic
+    // dependent launch) can become resident next to a draining GEMM CTA
+    static int smem_cap_kb = -1;
+    if (smem_cap_kb < 0) { const char* e = std::getenv("NDB_GEMM_SMEM_KB"); smem_cap_kb = e ? std::atoi(e) : 227; }
+    const int smem_budget = smem_cap_kb * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - epi_bytes;
     int stages = smem_budget / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages > a.total_kblocks) stages = a.total_kblocks < 2 ? 2 : a.total_kblocks;
@@ -985,14 +989,14 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     a.stages = stages;
     const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 256 + epi_bytes;
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.pending()) {
         cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return launch_status("cudaFuncSetAttribute(conv_gemm_kernel)");
-        attr_set = true;
+        attr_once.done();
     }
     const bool stats = a.stat_parts != nullptr;
     cudaError_t le;

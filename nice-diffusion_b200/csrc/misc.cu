@@ -199,10 +199,10 @@ static int launch_stem(const float* x, const float* w, const float* bias, float*
     const size_t smem = ((size_t)CIN * 9 * Cout + 64 * (size_t)(Cout + 4)) * sizeof(float);
 #define NDB_STEM_CASE(CPT)                                                                                              \
     {                                                                                                                   \
-        static bool attr = false;                                                                                       \
-        if (!attr) {                                                                                                    \
+        static PerDeviceOnce attr;                                                                                      \
+        if (attr.pending()) {                                                                                           \
             cudaFuncSetAttribute(stem_conv_kernel<CIN, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);  \
-            attr = true;                                                                                                \
+            attr.done();                                                                                                \
         }                                                                                                               \
         stem_conv_kernel<CIN, CPT><<<(int)blocks, 256, smem, st>>>(x, w, bias, out, stat_parts, N, H, W);               \
     }
@@ -319,7 +319,11 @@ __global__ void im2col_s2_kernel(const float* __restrict__ x, uint16_t* __restri
     }
 }
 
-__global__ void to_uint8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, int B, int C, int H, int W) {
+// gray_invert reproduces what the reference CLI does to one-channel images between the sampler and the file: the float
+// image is inverted (255 - v, scripts/sample.py:98-100), truncated to uint8 (:168) and inverted back (:170-171), i.e. the
+// stored byte is 255 - trunc(255 - v) = ceil(v), not trunc(v).
+__global__ void to_uint8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, int B, int C, int H, int W,
+                                int gray_invert) {
     const long long total = (long long)B * C * H * W;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -330,8 +334,21 @@ __global__ void to_uint8_kernel(const float* __restrict__ x, uint8_t* __restrict
         const int b = (int)(p / ((long long)W * H));
         float v = (x[(((size_t)b * C + c) * H + h) * W + w] + 1.f) * 127.5f;
         v = fminf(fmaxf(v, 0.f), 255.f);
-        out[i] = (uint8_t)v;  // truncation, like tensor.to(torch.uint8)
+        if (gray_invert) {
+            const float a = 255.f - v;
+            out[i] = (uint8_t)(255 - (int)(uint8_t)a);
+        } else {
+            out[i] = (uint8_t)v;  // truncation, like tensor.to(torch.uint8)
+        }
     }
+}
+
+// %globaltimer stamp between two launches of a stream (scripts/timeline.py: in-graph, warm-cache duration of every kernel
+// of a denoising step = difference of the stamps around it, minus the stamp kernel's own cost)
+__global__ void timestamp_kernel(unsigned long long* dst) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *dst = t;
 }
 
 static inline int grid_for(long long work, int threads) {
@@ -423,8 +440,18 @@ extern "C" int ndb_im2col_s2(const float* x, void* out, int N, int H, int W, int
     return launch_status("ndb_im2col_s2");
 }
 
-extern "C" int ndb_to_uint8(const float* x_nchw, uint8_t* out_nhwc, int B, int C, int H, int W, void* stream) {
+extern "C" int ndb_to_uint8(const float* x_nchw, uint8_t* out_nhwc, int B, int C, int H, int W, int gray_invert,
+                            void* stream) {
     NDB_CHECK_ARG(x_nchw && out_nhwc);
-    to_uint8_kernel<<<grid_for((long long)B * C * H * W, 256), 256, 0, (cudaStream_t)stream>>>(x_nchw, out_nhwc, B, C, H, W);
+    NDB_CHECK_ARG(!gray_invert || C == 1);
+    to_uint8_kernel<<<grid_for((long long)B * C * H * W, 256), 256, 0, (cudaStream_t)stream>>>(x_nchw, out_nhwc, B, C, H, W,
+                                                                                               gray_invert);
     return launch_status("ndb_to_uint8");
+}
+
+extern "C" int ndb_timestamp(uint64_t* dst, void* stream) {
+    NDB_CHECK_ARG(dst);
+    // plain launch (no programmatic serialization): starts only after the previous kernel has completed
+    timestamp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(dst));
+    return launch_status("ndb_timestamp");
 }

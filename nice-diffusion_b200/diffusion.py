@@ -115,8 +115,7 @@ class Diffusion:
         self.noise = 'torch'      # 'torch' | 'philox'
         self.seed = 0             # philox seed
         self.sample_ids = None    # LongTensor [B] of global sample indices (philox keying); default arange(B)
-        self._tables_dev = None
-        self._step_graphs = {}
+        self._tables_dev = {}     # sampling_var_type -> device tables (the fixed-variance row depends on it)
 
     # ------------------------------------------------------------------------------------------
     # device tables
@@ -127,7 +126,10 @@ class Diffusion:
 
     def _tables(self):
         """[TAB_COUNT][n] fp32 on the device: each fp64 table cast to fp32 exactly as `extract` does."""
-        if self._tables_dev is None:
+        if self.sampling_var_type not in _VAR_TYPES:
+            raise NotImplementedError(self.sampling_var_type)
+        cached = self._tables_dev.get(self.sampling_var_type)
+        if cached is None:
             n = len(self.betas)
             if self.sampling_var_type == 'large':
                 logvar_min = np.log(np.append(self.posterior_variance[1], self.betas[1:]))   # diffusion.py:259
@@ -146,12 +148,21 @@ class Diffusion:
             rows[L.TAB_ABAR_PREV] = self.alphas_cumprod_prev
             rows[L.TAB_SQRT_1M_ABAR] = self.sqrt_one_minus_alphas_cumprod
             tab = np.stack([np.asarray(r, dtype=np.float64) for r in rows]).reshape(L.TAB_COUNT, n)
-            self._tables_dev = dict(
+            cached = self._tables_dev[self.sampling_var_type] = dict(
                 tab=torch.from_numpy(tab).float().to(self.device).contiguous(),
                 sqrt_abar=torch.from_numpy(self.sqrt_alphas_cumprod).float().to(self.device),
                 sqrt_1m_abar=torch.from_numpy(self.sqrt_one_minus_alphas_cumprod).float().to(self.device),
                 tmap_f32=self.timestep_map.float().contiguous())
-        return self._tables_dev
+        return cached
+
+    def _check_step_index(self, t, what):
+        """The kernels index the tables with t unchecked; the reference's `extract` (torch.gather) raises for an index
+        outside [0, len(betas)) -- so does this, on the host."""
+        n = len(self.betas)
+        lo, hi = (int(t), int(t)) if not torch.is_tensor(t) else (int(t.min().item()), int(t.max().item()))
+        if lo < 0 or hi >= n:
+            raise IndexError('{}: step index {} is out of bounds for a schedule of {} respaced steps'.format(
+                what, lo if lo < 0 else hi, n))
 
     # ------------------------------------------------------------------------------------------
     # forward process
@@ -161,6 +172,7 @@ class Diffusion:
         """diffusion.py:132-153."""
         if steps_to_do is None or steps_to_do > self.rescaled_num_steps:
             steps_to_do = self.rescaled_num_steps
+        self._check_step_index(steps_to_do - 1, 'diffuse')
         timestep = ((steps_to_do - 1) * torch.ones(x_0.shape[0])).to(self.device)
         return self.diffusion_step(x_0, t=timestep, noise=noise)
 
@@ -169,6 +181,7 @@ class Diffusion:
         if noise is None:
             noise = torch.randn_like(x_0).to(self.device)
         tabs = self._tables()
+        self._check_step_index(t, 'diffusion_step')
         x_0 = x_0.to(self.device, torch.float32).contiguous()
         noise = noise.to(self.device, torch.float32).contiguous()
         return ops.qsample(x_0, noise, t.to(self.device).float().contiguous(), tabs['sqrt_abar'], tabs['sqrt_1m_abar'])
@@ -217,6 +230,7 @@ class Diffusion:
     def _step(self, x_t, t, kwargs, clip_x, ddim, noise=None):
         x_t = x_t.contiguous()
         t = t.to(self.device).float().contiguous()
+        self._check_step_index(t, 'denoising_step')
         with torch.no_grad():
             out, null = self._model_pair(x_t, t, kwargs)
         grad = None
@@ -286,6 +300,7 @@ class Diffusion:
             x = x.to(self.device, torch.float32).contiguous()
             if steps_to_do == 0:
                 return x
+            self._check_step_index(steps_to_do - 1, 'denoise')
             if self.guidance == 'classifier':
                 x = self._denoise_stepwise(x, kwargs, steps_to_do, progress, noise)
             else:
@@ -345,14 +360,17 @@ class _StepRunner:
         self.model_batch = Bm = 2 * B if cfg else B
         model, dev = diff.model, diff.device
         self.eng = eng = model.engine_for(torch.empty((Bm, 0), device=dev))
-        eng.refresh_weights()
+        # once per chain: also catches in-place writes through param.data, which no version counter sees
+        eng.refresh_weights(force=True)
         self.tabs = diff._tables()
-        key = (B, cfg, id(eng), diff.use_ddim)
-        st = diff._step_graphs.get(key)
+        # Loop state and captured graphs live ON THE ENGINE whose buffers they point into (an id(engine) key in a dict
+        # of the Diffusion object could be recycled by CPython after the engine is freed, and would replay a graph over
+        # freed memory). One state per image batch; one graph per value of everything the capture bakes in.
+        st = eng.step_graphs.get(('state', B))
         if st is None:
             st = dict(t_step=torch.zeros((B,), dtype=torch.float32, device=dev), noise=torch.zeros_like(x),
                       ids=torch.arange(B, device=dev, dtype=torch.long), graphs={})
-            diff._step_graphs[key] = st
+            eng.step_graphs[('state', B)] = st
         self.st = st
         eng.x_in[:B].copy_(x)
         if cfg:
@@ -370,7 +388,11 @@ class _StepRunner:
             st['ids'].copy_(torch.arange(B, device=dev, dtype=torch.long))
         self.noise_rows = noise
         self.use_philox = noise is None and diff.noise == 'philox'
-        self.gkey = (self.use_philox, int(diff.seed) if self.use_philox else 0)
+        # every scalar below is a kernel argument frozen at capture time; the reference reads them live each step
+        self.gkey = (self.use_philox, int(diff.seed) if self.use_philox else 0, cfg, bool(diff.use_ddim),
+                     diff.sampling_var_type, float(diff.strength) if cfg else 0.0,
+                     float(diff.ddim_eta) if diff.use_ddim else 0.0, self.tabs['tab'].data_ptr(),
+                     self.tabs['tmap_f32'].data_ptr())
         self.kernels_per_step = eng.num_kernels + 2
 
     def _launch(self):

@@ -71,6 +71,8 @@ class UNetEngine:
         self.serial = False      # True: no side streams (per-kernel timing passes want kernels that do not overlap)
         self.packers = []        # callables that (re)fill the weight arena from the live parameters
         self.graph = None
+        self.step_graphs = {}    # per-step CUDA graphs of the sampling loop (diffusion._StepRunner): they point into this
+                                 # engine's buffers, so they live and die with it
         self.sig = None
         self.pool = _Pool(device)
         self._layouts = {}
@@ -81,30 +83,36 @@ class UNetEngine:
     # ------------------------------------------------------------------------------------------
     # weight arena
     # ------------------------------------------------------------------------------------------
-    def _copy_param(self, p, dtype=torch.float32):
-        buf = torch.empty(p.shape, dtype=dtype, device=self.device)
-        self.packers.append(lambda: buf.copy_(p.detach()))
+    # Packers look the parameter up BY NAME on its module every time they run, so a Parameter object that was replaced
+    # (load_state_dict(assign=True), module surgery) is picked up by the next refresh.
+    def _copy_param(self, mod, name, dtype=torch.float32):
+        buf = torch.empty(getattr(mod, name).shape, dtype=dtype, device=self.device)
+        self.packers.append(lambda: buf.copy_(getattr(mod, name).detach()))
         return buf
 
-    def _packed(self, p, cout_pad=None, cin_off=0, cin_len=None):
+    def _packed(self, mod, name, cout_pad=None, cin_off=0, cin_len=None):
+        p = getattr(mod, name)
         cout = p.shape[0]
         k = p.shape[2] if p.dim() >= 3 else 1
         cp = ops.pad16(cout) if cout_pad is None else cout_pad
         cl = p.shape[1] - cin_off if cin_len is None else cin_len
         buf = torch.empty((k * k, cp, cl), dtype=self.dt16, device=self.device)
-        self.packers.append(lambda: ops.pack_conv_weight(p.detach().to(self.device), cout_pad=cp, cin_off=cin_off, cin_len=cl,
-                                                         fmt=self.fmt, out=buf))
+        self.packers.append(lambda: ops.pack_conv_weight(getattr(mod, name).detach().to(self.device), cout_pad=cp,
+                                                         cin_off=cin_off, cin_len=cl, fmt=self.fmt, out=buf))
         return buf
 
-    def _bias_sum(self, p1, p2):
-        buf = torch.empty(p1.shape, dtype=torch.float32, device=self.device)
-        self.packers.append(lambda: torch.add(p1.detach(), p2.detach(), out=buf))
+    def _bias_sum(self, m1, m2):
+        buf = torch.empty(m1.bias.shape, dtype=torch.float32, device=self.device)
+        self.packers.append(lambda: torch.add(m1.bias.detach(), m2.bias.detach(), out=buf))
         return buf
 
     def _signature(self):
         return tuple((p.data_ptr(), p._version) for p in self.model.parameters())
 
     def refresh_weights(self, force=False):
+        """Re-pack the weight arena when any parameter's storage or version changed. In-place writes through
+        `param.data` (EMA copies, `p.data.mul_()`) bump no version counter: callers that may have done that pass
+        force=True -- `Diffusion.denoise` does so at the start of every chain (a few ms, once per chain)."""
         sig = self._signature()
         if force or sig != self.sig:
             with torch.no_grad():
@@ -179,9 +187,9 @@ class UNetEngine:
 
         # ---- embedding front end + one GEMM for every ResBlock's step_embedding Linear ----
         freqs = timestep_embedding_freqs(m.model_channels).to(dev)
-        w0 = self._copy_param(m.step_embed[0].weight); b0 = self._copy_param(m.step_embed[0].bias)
-        w2 = self._copy_param(m.step_embed[2].weight); b2 = self._copy_param(m.step_embed[2].bias)
-        ce = self._copy_param(m.class_embedding.weight) if m.conditional else None
+        w0 = self._copy_param(m.step_embed[0], 'weight'); b0 = self._copy_param(m.step_embed[0], 'bias')
+        w2 = self._copy_param(m.step_embed[2], 'weight'); b2 = self._copy_param(m.step_embed[2], 'bias')
+        ce = self._copy_param(m.class_embedding, 'weight') if m.conditional else None
         act16 = torch.empty((B, E), dtype=self.dt16, device=dev)
         self.emb = torch.empty((B, E), dtype=torch.float32, device=dev)
         h1 = torch.empty((B, E), dtype=torch.float32, device=dev)
@@ -227,13 +235,13 @@ class UNetEngine:
             # error budget (ImageNet-64 forward 8.2e-4 -> 8.9e-4), so the exact fp32 stem stays the default
             cols = torch.empty((B, R, R, 64), dtype=self.dt16, device=dev)
             stem_wp = torch.empty((1, ops.pad16(C0), 64), dtype=self.dt16, device=dev)
-            stem_b = self._copy_param(stem.bias)
+            stem_b = self._copy_param(stem, 'bias')
             self.packers.append(lambda: ops.pack_conv_weight(ops.stem_weight_as_1x1(stem.weight.detach().to(dev).float()),
                                                              cout_pad=ops.pad16(C0), fmt=fmt, out=stem_wp))
             self.steps.append(lambda: ops.stem_im2col(self.x_in, out=cols, fmt=fmt))
             x = self._conv([(cols, stem_wp)], R, R, C0, want_stats=True, bias=stem_b)
         else:
-            stem_w = self._copy_param(stem.weight); stem_b = self._copy_param(stem.bias)
+            stem_w = self._copy_param(stem, 'weight'); stem_b = self._copy_param(stem, 'bias')
             if (R * R) % 64 == 0 and R * R // 64 <= 64:
                 # the stem kernel also emits the statistics of its output (one slot per 64-pixel block)
                 x = _Act(self.pool.get((B, R, R, C0), torch.float32), ops.stem_stats_alloc(B, R, R, C0, dev))
@@ -256,9 +264,9 @@ class UNetEngine:
             cur = new
         # head: GroupNorm -> SiLU -> conv3x3 to out_channels (model.py:446-449), NCHW fp32 out
         gn, conv = m.out[0], m.out[2]
-        g = self._copy_param(gn.weight); bt = self._copy_param(gn.bias)
+        g = self._copy_param(gn, 'weight'); bt = self._copy_param(gn, 'bias')
         a = self.pool.get(tuple(cur.t.shape), self.dt16)
-        wp = self._packed(conv.weight); bp = self._copy_param(conv.bias)
+        wp = self._packed(conv, 'weight'); bp = self._copy_param(conv, 'bias')
         H = cur.t.shape[1]
         self.steps.append(lambda: ops.gn_apply(cur.t, cur.stats, g, bt, silu=True, out=a, fmt=fmt, eps=gn.eps))
         self.steps.append(lambda: ops.conv_gemm([(a, wp)], B, H, H, m.out_channels, bias=bp,
@@ -308,10 +316,10 @@ class UNetEngine:
         if not conv_skip and skip is not None:
             raise L.NdbError('identity skip over a concatenated input is not supported')
 
-        g1 = self._copy_param(rb.in_norm.weight); b1 = self._copy_param(rb.in_norm.bias)
-        g2 = self._copy_param(rb.out_norm.weight); b2 = self._copy_param(rb.out_norm.bias)
-        bias_in = self._copy_param(rb.in_conv.bias)
-        w_out = self._packed(rb.out_conv.weight)
+        g1 = self._copy_param(rb.in_norm, 'weight'); b1 = self._copy_param(rb.in_norm, 'bias')
+        g2 = self._copy_param(rb.out_norm, 'weight'); b2 = self._copy_param(rb.out_norm, 'bias')
+        bias_in = self._copy_param(rb.in_conv, 'bias')
+        w_out = self._packed(rb.out_conv, 'weight')
         # Concatenated input [x ; skip] whose GroupNorm groups do not straddle the seam: the skip half depends only on the
         # down path, so its norm + SiLU + 16-bit cast run EARLY on a side stream (forked at the middle block, when the small
         # feature maps leave HBM bandwidth idle); the convs read the two halves as separate K segments.
@@ -319,18 +327,18 @@ class UNetEngine:
         split = (skip is not None and rb.mode == 'same' and conv_skip and Cin % 32 == 0 and C0 % cpg == 0
                  and self.early_fork_idx is not None and not os.environ.get('NDB_DISABLE_SPLIT_NORM'))
         if split:
-            w_in_a = self._packed(rb.in_conv.weight, cin_off=0, cin_len=C0)
-            w_in_b = self._packed(rb.in_conv.weight, cin_off=C0, cin_len=C1)
-            w_skip_a = self._packed(rb.skip.weight, cin_off=0, cin_len=C0)
-            w_skip_b = self._packed(rb.skip.weight, cin_off=C0, cin_len=C1)
+            w_in_a = self._packed(rb.in_conv, 'weight', cin_off=0, cin_len=C0)
+            w_in_b = self._packed(rb.in_conv, 'weight', cin_off=C0, cin_len=C1)
+            w_skip_a = self._packed(rb.skip, 'weight', cin_off=0, cin_len=C0)
+            w_skip_b = self._packed(rb.skip, 'weight', cin_off=C0, cin_len=C1)
         else:
-            w_in = self._packed(rb.in_conv.weight)
+            w_in = self._packed(rb.in_conv, 'weight')
         if conv_skip:
             if not split:
-                w_skip = self._packed(rb.skip.weight)
-            bias_out = self._bias_sum(rb.out_conv.bias, rb.skip.bias)
+                w_skip = self._packed(rb.skip, 'weight')
+            bias_out = self._bias_sum(rb.out_conv, rb.skip)
         else:
-            bias_out = self._copy_param(rb.out_conv.bias)
+            bias_out = self._copy_param(rb.out_conv, 'bias')
         off = self.emb_off[id(rb)]
         if rb.use_adaptive_gn:
             scale = self.emb_all[:, off:off + Cout]
@@ -400,9 +408,9 @@ class UNetEngine:
         T = H * W
         heads = ab.num_heads
         d = C // heads
-        g = self._copy_param(ab.norm.weight); bt = self._copy_param(ab.norm.bias)
-        w_qkv = self._packed(ab.qkv_nin.weight); b_qkv = self._copy_param(ab.qkv_nin.bias)
-        w_proj = self._packed(ab.proj_out.weight); b_proj = self._copy_param(ab.proj_out.bias)
+        g = self._copy_param(ab.norm, 'weight'); bt = self._copy_param(ab.norm, 'bias')
+        w_qkv = self._packed(ab.qkv_nin, 'weight'); b_qkv = self._copy_param(ab.qkv_nin, 'bias')
+        w_proj = self._packed(ab.proj_out, 'weight'); b_proj = self._copy_param(ab.proj_out, 'bias')
         n16 = pool.get((B, H, W, C), self.dt16)
         qkv = pool.get((B, H, W, 3 * C), self.dt16)
         o16 = pool.get((B, H, W, C), self.dt16)
@@ -430,7 +438,7 @@ class UNetEngine:
             return act
         Cout = layer.conv.weight.shape[0]
         a = pool.get((B, 2 * H, 2 * W, C), self.dt16)
-        wp = self._packed(layer.conv.weight); bp = self._copy_param(layer.conv.bias)
+        wp = self._packed(layer.conv, 'weight'); bp = self._copy_param(layer.conv, 'bias')
         self.steps.append(lambda: ops.cast16(up, out=a, fmt=fmt))
         out = self._conv([(a, wp)], 2 * H, 2 * W, Cout, want_stats=True, bias=bp)
         pool.put(up); pool.put(a)
@@ -449,7 +457,7 @@ class UNetEngine:
         Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
         Cout = layer.conv.weight.shape[0]
         cols = pool.get((9, B, Ho, Wo, C), self.dt16)
-        wp = self._packed(layer.conv.weight); bp = self._copy_param(layer.conv.bias)
+        wp = self._packed(layer.conv, 'weight'); bp = self._copy_param(layer.conv, 'bias')
         segs = [(cols[tap], wp[tap:tap + 1]) for tap in range(9)]
         self.steps.append(lambda: ops.im2col_s2(x.t, out=cols, fmt=fmt))
         out = self._conv(segs, Ho, Wo, Cout, want_stats=True, bias=bp)
@@ -516,6 +524,61 @@ class UNetEngine:
         else:
             self._launch_all()
         return self.out
+
+    @torch.no_grad()
+    def timeline(self, replays=5):
+        """In-graph, warm-cache duration of every launch of the plan: the launches are captured on ONE stream with a
+        %globaltimer stamp (ndb_timestamp) between consecutive kernels, the graph is replayed and the stamp differences
+        averaged. Returns [(kernel name, description, microseconds)], with the stamp kernel's own cost (two stamps back
+        to back) subtracted. Unlike CUDA events around eager launches this does not include host launch latency, and
+        unlike an ncu pass the caches are as warm as in production."""
+        dev = self.device
+        launches = []                 # (callable, is_kernel)
+        for i, f in enumerate(self.steps):
+            if self.early and i == self.early_fork_idx:
+                launches += [(g, True) for g, _ev in self.early]
+            launches.append((f, True))
+        n = len(launches)
+        buf = torch.zeros(n + 3, dtype=torch.int64, device=dev)
+        was_serial, self.serial = self.serial, True
+        names = []
+
+        def run(record):
+            ops.timestamp(buf, 0)
+            ops.timestamp(buf, 1)                      # calibration: stamp[1] - stamp[0] = cost of a stamp
+            for k, (f, _) in enumerate(launches):
+                n0 = len(ops.PROFILE) if record else 0
+                f()
+                if record:
+                    rec = ops.PROFILE[n0:]
+                    names.append((rec[0][0], rec[0][4]) if rec else ('wait', ''))
+                ops.timestamp(buf, 2 + k)
+        try:
+            ops.PROFILE = []
+            s = torch.cuda.Stream(device=dev)
+            s.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(s):
+                run(True)
+            torch.cuda.current_stream(dev).wait_stream(s)
+            torch.cuda.synchronize(dev)
+            ops.PROFILE = None
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run(False)
+            acc = torch.zeros(n + 3, dtype=torch.float64)
+            for _ in range(replays):
+                g.replay()
+                torch.cuda.synchronize(dev)
+                acc += buf.cpu().double()
+            acc /= replays
+        finally:
+            ops.PROFILE = None
+            self.serial = was_serial
+        stamp_cost = float(acc[1] - acc[0])
+        out = []
+        for k in range(n):
+            out.append((names[k][0], names[k][1], max(float(acc[2 + k] - acc[1 + k]) - stamp_cost, 0.0) / 1e3))
+        return out, stamp_cost / 1e3
 
     @torch.no_grad()
     def forward(self, x, timestep, y):

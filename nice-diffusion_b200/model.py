@@ -216,6 +216,29 @@ class DiffusionModel(nn.Module):
         """Drop cached plans / CUDA graphs / packed weights (e.g. before moving the model)."""
         self._engines = {}
 
+    def refresh_weights(self, force=True):
+        """Re-snapshot the parameters into the packed weight arenas of every cached plan. Storage / version changes
+        (load_state_dict, optimizer steps, `param.data = ...` rebinding) are detected automatically at the next
+        forward; in-place writes THROUGH `param.data` (`p.data.copy_(ema)`, `p.data.mul_()`) are invisible to
+        autograd's version counters -- call this after them (Diffusion.denoise does at the start of every chain)."""
+        for eng in self._engines.values():
+            eng.refresh_weights(force=force)
+
+    def load_state_dict(self, *a, **k):
+        out = super().load_state_dict(*a, **k)
+        self.refresh_weights(force=True)      # also covers assign=True, which replaces the Parameter objects
+        return out
+
+    def _where(self):
+        p = next(self.parameters(), None)
+        return None if p is None else (p.device, p.dtype)
+
     def _apply(self, fn, *a, **k):
-        self._engines = {}
-        return super()._apply(fn, *a, **k)
+        # .to() / .cuda() / .float(): plans, graphs and arenas point at device buffers, so they are dropped when the
+        # parameters actually move or change type -- and kept when the call is a no-op (Diffusion.__init__ does
+        # model.to(device) on a model that is usually already there)
+        before = self._where()
+        out = super()._apply(fn, *a, **k)
+        if self._where() != before:
+            self._engines = {}
+        return out

@@ -408,11 +408,21 @@ def qsample(x0, noise, t, sqrt_abar, sqrt_1m_abar, out=None):
     return out
 
 
-def to_uint8(x_nchw, out=None):
+def to_uint8(x_nchw, out=None, gray_invert=False):
+    """[-1,1] fp32 NCHW -> uint8 NHWC exactly as the reference CLI stores it (scripts/sample.py:94,168; with
+    gray_invert the one-channel double inversion of :98-100,170-171)."""
+    L.require_device(x_nchw, 'to_uint8')
+    x_nchw = x_nchw.contiguous()
     B, Cc, H, W = x_nchw.shape
     if out is None:
         out = torch.empty((B, H, W, Cc), dtype=torch.uint8, device=x_nchw.device)
     _begin()
-    L.check(L.load().ndb_to_uint8(L.ptr(x_nchw), L.ptr(out), B, Cc, H, W, L.stream_ptr()), 'ndb_to_uint8')
+    L.check(L.load().ndb_to_uint8(L.ptr(x_nchw), L.ptr(out), B, Cc, H, W, 1 if gray_invert else 0, L.stream_ptr()),
+            'ndb_to_uint8')
     _count('to_uint8')
     return out
+
+
+def timestamp(buf, index):
+    """buf: int64 device tensor; element `index` <- %globaltimer once the stream has drained (not counted in LAUNCHES)."""
+    L.check(L.load().ndb_timestamp(C.c_void_p(buf.data_ptr() + 8 * index), L.stream_ptr()), 'ndb_timestamp')

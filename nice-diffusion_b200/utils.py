@@ -198,3 +198,42 @@ def randomize_zero_init_(model, seed=0):
                 else:
                     p.copy_((0.02 * torch.randn(p.shape, generator=g)).to(p.device))
     return model
+
+
+def images_to_uint8(out, in_channels):
+    """Sampler output [-1,1] NCHW (device) -> the uint8 arrays the reference CLI passes to `plt.imsave`
+    (scripts/sample.py:94-100,165-171): [B,H,W,3] for colour models; for one-channel models the reference inverts the
+    float image, truncates and inverts again, which leaves [B,H,W] = 255 - trunc(255 - v). One ndb_to_uint8 launch."""
+    from . import ops
+    gray = in_channels == 1
+    img8 = ops.to_uint8(out.float(), gray_invert=gray).cpu().numpy()
+    return img8[..., 0] if gray else img8
+
+
+def reference_image_formula(out_cpu, in_channels):
+    """The same conversion spelled with the reference's own torch ops on a CPU tensor (what the tests compare
+    `images_to_uint8` against, byte for byte)."""
+    import torch
+    out = ((out_cpu + 1) * 127.5).clamp(0, 255)
+    if in_channels == 1:
+        out = torch.stack((255 - out.squeeze(1),) * 3, dim=1)
+    out = out.to(torch.uint8).permute(0, 2, 3, 1).detach().numpy()
+    if in_channels == 1:
+        out = 255 - out[..., 0]
+    return out
+
+
+def save_image(path, img8):
+    """`plt.imsave(path, img)` like the reference (sample.py:180) when matplotlib is installed -- for [H,W] arrays that
+    call applies matplotlib's default colour map, which is what the reference's EMNIST files contain; without
+    matplotlib the same array is written with OpenCV (RGB -> BGR, grey as is)."""
+    try:
+        import matplotlib.pyplot as plt
+    except ImportError:
+        plt = None
+    if plt is not None:
+        plt.imsave(path, img8)
+        return
+    import cv2
+    import numpy as np
+    cv2.imwrite(path, np.ascontiguousarray(img8 if img8.ndim == 2 else img8[..., ::-1]))

@@ -209,6 +209,83 @@ def main(only_unet=None):
     print('golden fixtures written to', OUT)
 
 
+def main_big(only=None):
+    """BASELINE-size trajectories (oracle/big_cases.py): the reference's step functions on the real ImageNet-64 /
+    EMNIST / ImageNet-128 networks with injected noise; oracle asserted bit-exact at every step; the oracle re-run with
+    fp16-rounded GEMM operands (free-running) is stored too -- it is the yardstick for the free-running bound of the
+    16-bit operand mode, and running it on the GPU box's host would take minutes."""
+    from oracle import CONFIGS
+    from oracle.big_cases import BIG_CASES, WEIGHT_SEED, big_case_inputs
+    from oracle.unet import unet_forward
+    from oracle.weights import random_state_dict
+    from oracle.sampler import Sampler
+
+    rm, rd = import_reference()
+    torch.set_num_threads(8)
+    dev = torch.device('cpu')
+    for name, (cname, dkw, B, start, n_steps) in BIG_CASES.items():
+        if only and name not in only:
+            continue
+        cfg = CONFIGS[cname]
+        sd = random_state_dict(cfg, seed=WEIGHT_SEED)
+        ref_model = rm.DiffusionModel(**cfg).eval()
+        ref_model.load_state_dict(sd, strict=True)
+        inp = big_case_inputs(name)
+        kwargs = {'y': inp['y']}
+        ref = rd.Diffusion(model=ref_model, loss_type='hybrid', device=dev, **dkw)
+
+        def model_fn(xx, tt, y=None, _cfg=cfg, _sd=sd):
+            return unet_forward(_cfg, _sd, xx, tt, y)
+
+        def model16(xx, tt, y=None, _cfg=cfg, _sd=sd):
+            return unet_forward(_cfg, _sd, xx, tt, y, operand_cast=lambda v: v.half().float())
+        ora, emu = Sampler(model_fn, **dkw), Sampler(model16, **dkw)
+        if start == 'noise':
+            x = inp['x_start'].clone()
+        else:
+            x = ref.diffuse(inp['x0_img'], steps_to_do=n_steps, noise=inp['q_noise'])
+            assert torch.equal(x, ora.diffuse(inp['x0_img'], n_steps, inp['q_noise']))
+        x_first = x.clone()
+        ref_step = ref.ddim_denoising_step if dkw.get('use_ddim') else ref.denoising_step
+        ora_step = ora.ddim_step if dkw.get('use_ddim') else ora.ddpm_step
+        emu_step = emu.ddim_step if dkw.get('use_ddim') else emu.ddpm_step
+        traj_x, traj_x0 = [], []
+        xe = x.clone()
+        real = torch.randn_like
+        for i in range(n_steps):
+            t = inp['t_first'] - i
+            ts = (t * torch.ones(B)).to(dev)
+            torch.randn_like = lambda ref_t, *a, _i=i, **k: inp['noises'][_i].clone()
+            try:
+                rx, rx0 = ref_step(x, t=ts, kwargs=kwargs)
+            finally:
+                torch.randn_like = real
+            ox, ox0 = ora_step(x, ts, kwargs, inp['noises'][i])
+            assert torch.equal(rx, ox) and torch.equal(rx0, ox0), (name, t)
+            xe, _ = emu_step(xe, ts, kwargs, inp['noises'][i])
+            traj_x.append(rx.clone()); traj_x0.append(rx0.clone())
+            x = rx
+            print('  ', name, 't', t, '|x|max', float(rx.abs().max()), 'emu16 err', float((xe - rx).abs().max()), flush=True)
+        if start == 'diffused':
+            # the public loop (diffusion.py:155-226) on the same inputs gives the same final image
+            it = iter(range(n_steps))
+            torch.randn_like = lambda ref_t, *a, **k: inp['noises'][next(it)].clone()
+            try:
+                loop = ref.denoise(x=x_first.clone(), kwargs=kwargs, batch_size=B, progress=False, steps_to_do=n_steps)
+            finally:
+                torch.randn_like = real
+            assert torch.equal(loop, x), name
+        save = dict(x_first=x_first.numpy(), final=x.numpy(), traj_x=np.stack([v.numpy() for v in traj_x]),
+                    emu16_final=xe.numpy())
+        if cname != 'in128':
+            save['traj_x0'] = np.stack([v.numpy() for v in traj_x0])
+        np.savez_compressed(os.path.join(OUT, 'bigtraj_{}.npz'.format(name)), **save)
+        print('big trajectory', name, 'bit-exact; emu16 final err', float((xe - x).abs().max()), flush=True)
+
+
 if __name__ == '__main__':
     import sys
-    main(only_unet=sys.argv[1].split(',') if len(sys.argv) > 1 else None)
+    if len(sys.argv) > 1 and sys.argv[1] == 'big':
+        main_big(only=sys.argv[2].split(',') if len(sys.argv) > 2 else None)
+    else:
+        main(only_unet=sys.argv[1].split(',') if len(sys.argv) > 1 else None)

@@ -19,7 +19,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nice_diffusion_b200.diffusion import Diffusion
 from nice_diffusion_b200.model import DiffusionModel
 from nice_diffusion_b200.sharding import global_indices, output_names, shard_range, world_info
-from nice_diffusion_b200.utils import get_dicts_from_args, make_argparser, randomize_zero_init_
+from nice_diffusion_b200.utils import (get_dicts_from_args, images_to_uint8, make_argparser, randomize_zero_init_,
+                                       save_image)
 
 
 def main():
@@ -31,9 +32,11 @@ def main():
                              "'philox' = in-kernel Philox keyed by global sample index (default under torchrun)")
     parser.add_argument('--random_weights', action='store_true', default=False,
                         help='use seeded random weights of the architecture instead of loading --model_path')
+    parser.add_argument('--dump_raw', type=str, default=None,
+                        help='also write the float [-1,1] sampler outputs of this rank to this .npy file (verification)')
     args = parser.parse_args()
-    noise_mode, random_weights = args.noise, args.random_weights
-    del args.noise, args.random_weights
+    noise_mode, random_weights, dump_raw = args.noise, args.random_weights, args.dump_raw
+    del args.noise, args.random_weights, args.dump_raw
     other, model_args, diff_args = get_dicts_from_args(args)
 
     rank, world, local_rank = world_info()
@@ -83,6 +86,7 @@ def main():
     gen = torch.Generator(device='cpu')
     gen.manual_seed(torch.initial_seed() if seed is None else seed)
     results = []   # (global ids, uint8 HWC images, labels)
+    raw = []
     all_labels = []
     lo, hi = shard_range(B, rank, world)
     with torch.no_grad():
@@ -113,10 +117,9 @@ def main():
             if wordy:
                 print('Denoising sample {}! :)'.format(i + 1))
             out = diffusion.denoise(x=data, kwargs={'y': labels}, batch_size=hi - lo, progress=wordy, steps_to_do=steps)
-            img8 = ((out + 1) * 127.5).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).cpu().numpy()
-            if model_args['in_channels'] == 1:
-                img8 = 255 - img8[..., 0]                        # grayscale is inverted (sample.py:98-100,170-171)
-            results.append((list(range(i * B + lo, i * B + hi)), img8))
+            # [-1,1] -> the uint8 HWC arrays the reference hands to plt.imsave (sample.py:94,98-100,165-171), one kernel
+            results.append((list(range(i * B + lo, i * B + hi)), images_to_uint8(out, model_args['in_channels'])))
+            raw.append(out.cpu().numpy())
 
     if other['upsample']:
         raise SystemExit('--upsample needs basicsr + RealESRGAN weights, which are outside this package (SURVEY.md section 2 #10)')
@@ -129,13 +132,13 @@ def main():
                 plt.title('Output Image' + ('' if all_labels[gid] is None else ', Label={}'.format(all_labels[gid])))
                 plt.waitforbuttonpress()
     else:
-        import cv2
         if wordy:
             print('Saving {} generated images to \'{}\'!'.format(n_batches * B, save_path))
         for ids, imgs in results:
             for gid, im in zip(ids, imgs):
-                bgr = im if im.ndim == 2 else im[..., ::-1]
-                cv2.imwrite(save_path + names[gid], np.ascontiguousarray(bgr))   # SAVE_PATH + filename, as the reference
+                save_image(save_path + names[gid], im)          # SAVE_PATH + filename, as the reference
+    if dump_raw is not None:
+        np.save(dump_raw, np.concatenate(raw, 0))
     if wordy:
         print('Done! have a nice day')
 

@@ -50,3 +50,37 @@ def test_sample_cli_files_determinism_and_start_img(cuda_dev, tmp_path):
     # no CPU implementation behind this CLI
     r = run_cli(['--cpu', '--save_path', str(c) + os.sep], str(tmp_path))
     assert r.returncode != 0 and 'no CPU implementation' in (r.stderr + r.stdout)
+
+
+def test_sample_cli_grayscale_bytes_follow_the_reference_formula(cuda_dev, tmp_path):
+    """One-channel models (EMNIST, BASELINE config 1): the reference inverts the float image, truncates to uint8 and inverts
+    again (scripts/sample.py:98-100,165-171 of the reference), so the stored byte is 255 - trunc(255 - v). The CLI's arrays
+    (one ndb_to_uint8 launch) must equal that formula evaluated with the reference's torch ops on the host, and the file
+    must hold exactly that array pushed through the same writer."""
+    import torch
+    from nice_diffusion_b200.utils import images_to_uint8, reference_image_formula, save_image
+    out_dir = tmp_path / 'g'
+    out_dir.mkdir()
+    raw = tmp_path / 'raw.npy'
+    gray = [a if a != '3' or CUSTOM[i - 1] != '--in_channels' else '1' for i, a in enumerate(CUSTOM)]
+    cmd = [sys.executable, os.path.join(ROOT, 'scripts', 'sample.py'), '--model_path', 'custom_random.pt', '--random_weights',
+           '--batch_size', '3', '--num_samples', '1', '--noise', 'philox', '--seed', '11', '--labels', '2',
+           '--save_path', str(out_dir) + os.sep, '--dump_raw', str(raw)] + gray
+    r = subprocess.run(cmd, cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    x = torch.from_numpy(np.load(raw))
+    assert x.shape == (3, 1, 16, 16)
+    want = reference_image_formula(x, 1)                               # host, the reference's own ops
+    got = images_to_uint8(x.to(cuda_dev), 1)                           # the kernel the CLI used
+    assert want.shape == (3, 16, 16) and want.dtype == np.uint8 and np.array_equal(got, want)
+    assert (want != (((x + 1) * 127.5).clamp(0, 255)).to(torch.uint8)[:, 0].numpy()).any()   # differs from a single truncation
+    for b in range(3):
+        ref_file = tmp_path / 'ref{}.jpg'.format(b)
+        save_image(str(ref_file), want[b])
+        assert (out_dir / '2_sample{}.jpg'.format(b)).read_bytes() == ref_file.read_bytes()
+    # colour path: same comparison on random data, edge values included
+    v = torch.rand(2, 3, 8, 8) * 2.4 - 1.2
+    v[0, 0, 0, :4] = torch.tensor([-1.0, 1.0, 0.0, 0.999999])
+    assert np.array_equal(images_to_uint8(v.to(cuda_dev), 3), reference_image_formula(v, 3))
+    g1 = torch.rand(4, 1, 8, 8) * 2.4 - 1.2
+    assert np.array_equal(images_to_uint8(g1.to(cuda_dev), 1), reference_image_formula(g1, 1))

@@ -507,3 +507,97 @@ def test_groupnorm_apply_channel_slices(cuda_dev, C0, C1):
     assert torch.equal(torch.cat([a, b], -1), full) and torch.equal(torch.cat([ra, rb], -1), raw)
     ref = F.silu(F.group_norm(torch.cat([x0, x1], -1).permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-5))
     assert rel_err(full.permute(0, 3, 1, 2), ref) < 1.5e-3
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# operand_format = 1 (bf16 operands, same tcgen05 kind::f16 path): every kernel template that takes the format
+# ----------------------------------------------------------------------------------------------------------------------
+def test_bf16_operand_format_kernels(cuda_dev):
+    ops, L = _ops()
+    BF = L.FMT_BF16
+    g = torch.Generator(device='cpu').manual_seed(77)
+    d = cuda_dev
+    # conv GEMM + residual + fused statistics + 16-bit output, bf16 operands
+    N, H, W, Cin, Cout = 3, 16, 16, 128, 192
+    x = torch.randn(N, Cin, H, W, generator=g).to(d)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)).to(d)
+    b = (0.1 * torch.randn(Cout, generator=g)).to(d)
+    r = torch.randn(N, Cout, H, W, generator=g).to(d)
+    x16 = nhwc(x).bfloat16()
+    wp = ops.pack_conv_weight(w, fmt=BF)
+    assert wp.dtype == torch.bfloat16
+    assert torch.equal(wp[4, :Cout].float(), w[:, :, 1, 1].bfloat16().float())
+    ref = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b, padding=1)
+    st = ops.conv_stats_alloc(N, H, W, Cout, d, Cin * 9)
+    out = ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, residual=nhwc(r), residual_mode=L.RES_SAME, fmt=BF, stats=st)
+    assert rel_err(out.permute(0, 3, 1, 2), ref + r) < 2e-5
+    o = out.double().flatten(1, 2)
+    assert torch.allclose(ops.stats_totals(st)[:, :, 0], o.sum(1), rtol=1e-5, atol=2e-3)
+    out16 = ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, out_kind=L.OUT_F16_NHWC, fmt=BF)
+    assert out16.dtype == torch.bfloat16 and rel_err(out16.permute(0, 3, 1, 2), ref) < 5e-3
+    # GroupNorm apply -> bf16 operand (+ raw copy)
+    C = 128
+    xa = nhwc(torch.randn(N, C, H, W, generator=g).to(d) * 1.5 + 0.3)
+    gamma = (1 + 0.1 * torch.randn(C, generator=g)).to(d)
+    beta = (0.1 * torch.randn(C, generator=g)).to(d)
+    stats = ops.gn_stats(xa)
+    y16, raw16 = ops.gn_apply(xa, stats, gamma, beta, silu=True, fmt=BF, want_raw16=True)
+    assert y16.dtype == torch.bfloat16 and raw16.dtype == torch.bfloat16
+    refn = F.silu(F.group_norm(xa.permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-5))
+    assert rel_err(y16.permute(0, 3, 1, 2), refn) < 6e-3            # bf16 rounding of the result (2^-9) + tanh.approx
+    assert torch.equal(raw16.float(), xa.bfloat16().float())
+    # 16-bit (bf16) source for the norm
+    y2 = ops.gn_apply(xa.bfloat16(), stats, gamma, beta, silu=True, fmt=BF)
+    refn2 = F.silu(F.group_norm(xa.bfloat16().float().permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-5))
+    assert rel_err(y2.permute(0, 3, 1, 2), refn2) < 2e-2
+    # attention, both channel orders, padded last key block
+    for (B, T, heads, dh, order) in [(2, 196, 2, 64, 0), (1, 256, 3, 32, 1)]:
+        Cc = heads * dh
+        qkv = torch.randn(B, T, 3 * Cc, generator=g).to(d).bfloat16()
+        o = ops.attention(qkv, B, T, heads, dh, order=order, fmt=BF)
+        f = qkv.float()
+        if order == 0:
+            q, k, v = f.reshape(B, T, 3, heads, dh).permute(2, 0, 3, 1, 4).unbind(0)
+        else:
+            q, k, v = f.reshape(B, T, heads, 3, dh).permute(3, 0, 2, 1, 4).unbind(0)
+        wgt = torch.softmax((q @ k.transpose(2, 3)) * dh ** -0.5, dim=-1)
+        refa = (wgt @ v).transpose(1, 2).reshape(B, T, Cc)
+        assert o.dtype == torch.bfloat16 and rel_err(o, refa) < 1.5e-2   # P and O rounded to bf16 (2^-9)
+    # embedding front end emits the bf16 activation
+    mc, E = 64, 256
+    t = torch.tensor([2., 998.])
+    w0 = torch.randn(E, mc, generator=g) / math.sqrt(mc); b0 = 0.1 * torch.randn(E, generator=g)
+    w2 = torch.randn(E, E, generator=g) / math.sqrt(E); b2 = 0.1 * torch.randn(E, generator=g)
+    freqs = torch.exp(torch.arange(mc // 2, dtype=torch.float32) * -(math.log(10000) / (mc // 2)))
+    emb, act = ops.embed(t.to(d), None, freqs.to(d), w0.to(d), b0.to(d), w2.to(d), b2.to(d), None, fmt=BF)
+    assert act.dtype == torch.bfloat16 and rel_err(act.float(), F.silu(emb)) < 6e-3
+    # cast / im2col helpers
+    assert torch.equal(ops.cast16(xa, fmt=BF).float(), xa.bfloat16().float())
+
+
+def test_bf16_operand_format_unet_forward(cuda_dev):
+    """Whole forward with bf16 operands (model.operand_format = 1): runs the same plan; bf16's 8-bit mantissa cannot
+    meet the 2e-3 bar (oracle/precision_study.py: 6.7e-3 on ImageNet-64), which is why fp16 is the default -- the
+    check here is against the oracle with bf16-rounded GEMM operands and a bf16-sized tolerance."""
+    from oracle import CONFIGS
+    from oracle.unet import unet_forward
+    from oracle.weights import random_state_dict
+    from nice_diffusion_b200 import _lib as L
+    from nice_diffusion_b200.model import DiffusionModel
+    cfg = CONFIGS['tiny']
+    sd = random_state_dict(cfg, seed=1234)
+    model = DiffusionModel(**cfg)
+    model.load_state_dict(sd, strict=True)
+    model.operand_format = L.FMT_BF16
+    model.to(cuda_dev).eval()
+    rs = np.random.RandomState(5)
+    x = torch.from_numpy(rs.standard_normal((3, 3, 16, 16)).astype(np.float32))
+    t = torch.tensor([998, 500, 2])
+    y = torch.tensor([1, 4, 9])
+    out = model(x.to(cuda_dev), t.to(cuda_dev), y.to(cuda_dev)).cpu()
+    ref = unet_forward(cfg, sd, x, t, y)
+    emu = unet_forward(cfg, sd, x, t, y, operand_cast=lambda v: v.bfloat16().float())
+    e_ref = float((out - ref).abs().max() / ref.abs().max())
+    e_emu = float((emu - ref).abs().max() / ref.abs().max())
+    print('bf16 forward err', e_ref, 'oracle-with-bf16-operands err', e_emu)
+    assert e_ref < max(2e-2, 2.5 * e_emu)

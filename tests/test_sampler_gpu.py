@@ -269,3 +269,166 @@ def test_full_size_chain_is_reproducible_in64(cuda_dev):
     diff.seed = 6
     c = diff.denoise(kwargs={'y': y}, batch_size=B, progress=False)
     assert not torch.equal(a, c)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# BASELINE-size trajectories (oracle/big_cases.py; fixtures tests/golden/bigtraj_*.npz from the reference itself)
+# ----------------------------------------------------------------------------------------------------------------------
+# Stated per-pixel tolerances (images / latents of O(1)..O(4), 16-bit operand mode):
+#   teacher-forced, every step from the reference's own x_t:       |x_{t-1} - ref| <= 1.5e-2
+#   free-running over the case's steps (errors compound):          |x_final - ref| <= max(1e-2, 2 x E16)
+# E16 = error of the ORACLE with fp16-rounded GEMM operands on the same chain, computed in the build container and
+# stored in the fixture (`emu16_final`): 1.5e-3 / 2.5e-4 (ImageNet-64 first / last 10 steps), 8.9e-3 (EMNIST, 25 steps,
+# CFG 0.8), 3.4e-2 (ImageNet-128 DDIM eta=0 + CFG, 10 noise-free steps).
+BIG_TF_TOL = 1.5e-2
+
+
+def _big(name, dev):
+    from oracle.big_cases import BIG_CASES, WEIGHT_SEED, big_case_inputs
+    from nice_diffusion_b200.diffusion import Diffusion
+    cname, dkw, B, start, n_steps = BIG_CASES[name]
+    cfg, sd, model = _build(cname, dev, seed=WEIGHT_SEED)
+    diff = Diffusion(model=model, loss_type='hybrid', device=dev, **dkw)
+    inp = big_case_inputs(name)
+    g = np.load(os.path.join(GOLD, 'bigtraj_{}.npz'.format(name)))
+    return diff, dkw, inp, g, B, start, n_steps
+
+
+@pytest.mark.parametrize('name', ['in64_ddpm_first10', 'in64_ddpm_last10', 'emnist_cfg_full', 'in128_ddim_cfg_first10'])
+def test_big_trajectory_matches_reference_golden(cuda_dev, name):
+    diff, dkw, inp, g, B, start, n_steps = _big(name, cuda_dev)
+    d = cuda_dev
+    kwargs = {'y': inp['y'].to(d)}
+    step = diff.ddim_denoising_step if dkw.get('use_ddim') else diff.denoising_step
+    if start == 'noise':
+        x_first = inp['x_start'].to(d)
+    else:
+        # q-sample is bit-exact (two products and an add): the product's diffuse() reproduces the fixture's start
+        x_first = diff.diffuse(inp['x0_img'].to(d), steps_to_do=n_steps, noise=inp['q_noise'].to(d))
+    assert torch.equal(x_first.cpu(), torch.from_numpy(g['x_first']))
+    noises = inp['noises'].to(d)
+    # (a) teacher-forced
+    worst = 0.0
+    for i in range(n_steps):
+        t = inp['t_first'] - i
+        x_in = x_first if i == 0 else torch.from_numpy(g['traj_x'][i - 1]).to(d)
+        xo, x0 = step(x_in.clone(), t=torch.full((B,), float(t), device=d), kwargs=kwargs, noise=noises[i])
+        e = float((xo.cpu() - torch.from_numpy(g['traj_x'][i])).abs().max())
+        assert e < BIG_TF_TOL, (name, t, e)
+        worst = max(worst, e)
+        if 'traj_x0' in g.files:
+            w_cfg = dkw.get('guidance_strength', 0.0) if dkw.get('guidance_method') == 'classifier_free' else 0.0
+            tol0 = max(1.5e-2, 6e-3 * (1 + 2 * w_cfg) * float(diff.sqrt_reciprocal_alphas_minus_one_cumprod[t]))
+            assert float((x0.cpu() - torch.from_numpy(g['traj_x0'][i])).abs().max()) < tol0, (name, t)
+    # (b) free-running through the public per-step API
+    x = x_first.clone()
+    for i in range(n_steps):
+        t = inp['t_first'] - i
+        x, _ = step(x, t=torch.full((B,), float(t), device=d), kwargs=kwargs, noise=noises[i])
+    final = torch.from_numpy(g['final'])
+    e16 = float((torch.from_numpy(g['emu16_final']) - final).abs().max())
+    bound = max(1e-2, 2.0 * e16)
+    err = float((x.cpu() - final).abs().max())
+    print(name, 'teacher-forced worst', worst, 'free-running', err, 'bound', bound, 'E16', e16)
+    assert err < bound
+    # (c) the loop itself (`denoise`, one CUDA graph per step) where the case is a whole `denoise` call: the full EMNIST
+    #     chain from x_T, and the PARTIAL chain steps_to_do < R of the --start_img path (reference diffusion.py:192-197)
+    if inp['t_first'] == n_steps - 1:
+        rows = torch.flip(noises, dims=[0])           # denoise(noise=...) is indexed by the step index t
+        out = diff.denoise(x=x_first.clone(), kwargs=kwargs, batch_size=B, progress=False, steps_to_do=n_steps, noise=rows)
+        assert torch.equal(out, x), 'graph loop and step-wise API disagree'
+
+
+@pytest.mark.parametrize('steps_to_do', [1, 4, 7])
+def test_partial_denoise_matches_oracle(cuda_dev, steps_to_do):
+    """f-3: `diffuse(x0, steps)` then `denoise(x, steps_to_do=steps)` (scripts/sample.py:77-78 of the reference) against
+    the oracle on the same start image, q-sample noise and per-step noise."""
+    from oracle.sampler import Sampler
+    from oracle.unet import unet_forward
+    from nice_diffusion_b200.diffusion import Diffusion
+    cfg, sd, model = _build('tiny', cuda_dev)
+    dkw = dict(original_num_steps=1000, rescaled_num_steps=10, beta_schedule='cosine',
+               sampling_var_type='learned_interpolation')
+    diff = Diffusion(model=model, loss_type='hybrid', device=cuda_dev, **dkw)
+    rs = np.random.RandomState(steps_to_do)
+    B = 3
+    x0 = torch.from_numpy(rs.uniform(-1, 1, (B, 3, 16, 16)).astype(np.float32))
+    qn = torch.from_numpy(rs.standard_normal((B, 3, 16, 16)).astype(np.float32))
+    noises = torch.from_numpy(rs.standard_normal((10, B, 3, 16, 16)).astype(np.float32))
+    y = torch.tensor([1, 5, 9])
+    ora = Sampler(lambda xx, tt, y=None: unet_forward(cfg, sd, xx, tt, y), **dkw)
+    xt_ref = ora.diffuse(x0, steps_to_do, qn)
+    want = ora.denoise(xt_ref.clone(), {'y': y}, lambda t: noises[t], steps_to_do=steps_to_do)
+    d = cuda_dev
+    xt = diff.diffuse(x0.to(d), steps_to_do=steps_to_do, noise=qn.to(d))
+    assert torch.equal(xt.cpu(), xt_ref)
+    got = diff.denoise(x=xt, kwargs={'y': y.to(d)}, batch_size=B, steps_to_do=steps_to_do, progress=False, noise=noises.to(d))
+    err = float((got.cpu() - want).abs().max())
+    print('partial denoise', steps_to_do, 'err', err)
+    assert err < 1e-2
+    # steps_to_do larger than the schedule is clamped like the reference; an out-of-range start raises like torch.gather
+    assert torch.equal(diff.diffuse(x0.to(d), steps_to_do=99, noise=qn.to(d)), diff.diffuse(x0.to(d), noise=qn.to(d)))
+    with pytest.raises(IndexError):
+        diff.diffuse(x0.to(d), steps_to_do=0, noise=qn.to(d))
+
+
+@pytest.mark.parametrize('var_type', ['learned_interpolation', 'learned', 'small', 'large'])
+def test_get_eps_and_log_var_matches_oracle(cuda_dev, var_type):
+    """a-12: the public method (reference diffusion.py:242-264), all four variance types."""
+    from oracle.sampler import Sampler
+    from oracle.unet import unet_forward
+    from nice_diffusion_b200.diffusion import Diffusion
+    cname = 'tiny' if var_type.startswith('learned') else 'tiny_legacy'
+    cfg, sd, model = _build(cname, cuda_dev)
+    dkw = dict(original_num_steps=1000, rescaled_num_steps=10, beta_schedule='cosine', sampling_var_type=var_type)
+    diff = Diffusion(model=model, loss_type='hybrid', device=cuda_dev, **dkw)
+    ora = Sampler(lambda xx, tt, y=None: unet_forward(cfg, sd, xx, tt, y), **dkw)
+    rs = np.random.RandomState(3)
+    B = 4
+    x = torch.from_numpy(rs.standard_normal((B, 3, 16, 16)).astype(np.float32))
+    t = torch.tensor([9.0, 5.0, 1.0, 0.0])
+    kwargs = {'y': torch.tensor([1, 2, 3, 4])} if cfg.get('num_classes') else {}
+    eps_ref, lv_ref = ora.eps_and_log_var(x, t, kwargs)
+    eps, lv = diff.get_eps_and_log_var(x.to(cuda_dev), t.to(cuda_dev), {k: v.to(cuda_dev) for k, v in kwargs.items()})
+    assert eps.shape == eps_ref.shape and lv.shape == lv_ref.shape
+    assert float((eps.cpu() - eps_ref).abs().max() / eps_ref.abs().max()) < 2e-3
+    if var_type in ('small', 'large'):
+        assert torch.equal(lv.cpu(), lv_ref.contiguous())            # a table row cast to fp32: bit-exact
+    else:
+        # log_var is (an affine function of) the model's second output half: same 2e-3 relative bar, scaled by the
+        # interpolation range for learned_interpolation
+        assert float((lv.cpu() - lv_ref).abs().max()) < 2e-3 * max(1.0, float(lv_ref.abs().max()))
+
+
+def test_graph_replays_follow_live_sampler_settings(cuda_dev):
+    """The per-step CUDA graph bakes guidance strength / eta / variance type in as kernel arguments; the reference
+    reads them live. Changing them between denoise() calls must change the result (and changing them back restores
+    it), and in-place parameter edits through `.data` are picked up by the next chain."""
+    from nice_diffusion_b200.diffusion import Diffusion
+    cfg, sd, model = _build('tiny', cuda_dev)
+    diff = Diffusion(model=model, original_num_steps=1000, rescaled_num_steps=6, beta_schedule='cosine',
+                     sampling_var_type='learned_interpolation', loss_type='hybrid', guidance_method='classifier_free',
+                     guidance_strength=0.8, device=cuda_dev)
+    diff.noise, diff.seed = 'philox', 3
+    y = torch.tensor([1, 2], device=cuda_dev)
+    a = diff.denoise(kwargs={'y': y}, batch_size=2, progress=False)
+    diff.strength = 2.5
+    b = diff.denoise(kwargs={'y': y}, batch_size=2, progress=False)
+    assert not torch.equal(a, b)
+    diff.strength = 0.8
+    assert torch.equal(diff.denoise(kwargs={'y': y}, batch_size=2, progress=False), a)
+    diff.sampling_var_type = 'learned'
+    c = diff.denoise(kwargs={'y': y}, batch_size=2, progress=False)
+    assert not torch.equal(a, c)
+    diff.sampling_var_type = 'learned_interpolation'
+    p = model.out[2].weight
+    saved = p.detach().clone()
+    p.data.mul_(0.5)                                  # invisible to autograd's version counter
+    e = diff.denoise(kwargs={'y': y}, batch_size=2, progress=False)
+    assert not torch.equal(a, e)
+    p.data.copy_(saved)
+    assert torch.equal(diff.denoise(kwargs={'y': y}, batch_size=2, progress=False), a)
+    # a model moved with a no-op .to() keeps its plans; the graphs belong to the engine
+    eng = model.engine_for(torch.empty((4, 0), device=cuda_dev))
+    model.to(cuda_dev)
+    assert model.engine_for(torch.empty((4, 0), device=cuda_dev)) is eng and len(eng.step_graphs) > 0
