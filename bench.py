@@ -104,9 +104,120 @@ class ClockSampler:
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
+def import_reference():
+    """The UNMODIFIED reference package, pip-installed into baseline/_ref (git-ignored; it travels to the GPU box with
+    the snapshot). nicediffusion/utils.py imports matplotlib at module top, which this image lacks: a stub module
+    satisfies the import (nothing on the sampling path touches it). Returns (model module, diffusion module) or None."""
+    import types
+    ref_dir = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref_dir, 'nicediffusion')):
+        return None
+    try:
+        import matplotlib  # noqa: F401
+    except ImportError:
+        for name in ('matplotlib', 'matplotlib.pyplot'):
+            sys.modules.setdefault(name, types.ModuleType(name))
+        sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    try:
+        import nicediffusion.model as rm
+        import nicediffusion.diffusion as rd
+        return rm, rd
+    except Exception as e:  # noqa: BLE001
+        print('bench.py: reference import failed: {}'.format(e), file=sys.stderr)
+        return None
+
+
+def host_cores():
+    # all host cores this process may use (torchrun pins OMP_NUM_THREADS=1 in its children; undo that for the CPU arm)
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_reference_arm(workload, steps, warmup, sample_batch=None):
-    """The reference's own --cpu path (Diffusion.denoise on the host, sample.py:27-28) as restated by the oracle
-    port: `steps` denoising steps on a bounded sample of the workload's batch."""
+    """The reference's own --cpu path: the real `nicediffusion.Diffusion.denoise(device=cpu)` from baseline/_ref
+    (kind 'reference') -- or, if that install is missing, the oracle port of it (kind 'port') -- for `steps` denoising
+    steps on a bounded sample of the workload's batch."""
+    ref = import_reference()
+    if ref is not None:
+        return real_reference_arm(ref, workload, steps, warmup, sample_batch)
+    return oracle_port_arm(workload, steps, warmup, sample_batch)
+
+
+def real_reference_arm(ref, workload, steps, warmup, sample_batch):
+    rm, rd = ref
+    from nice_diffusion_b200.utils import randomize_zero_init_
+    cname, dkw, _, per_image = WORKLOADS[workload]
+    cfg = model_config(workload)
+    if sample_batch is None:
+        sample_batch = {'in64': 2, 'emnist': 16, 'in128': 1}[workload]
+    torch.set_num_threads(max(1, host_cores()))
+    torch.manual_seed(0)
+    model = rm.DiffusionModel(**cfg)
+    randomize_zero_init_(model, seed=0)
+    cpu = torch.device('cpu')
+    diff = rd.Diffusion(model=model, device=cpu, **dkw)
+    x = torch.randn(sample_batch, cfg['in_channels'], cfg['resolution'], cfg['resolution'])
+    y = torch.randint(1, cfg['num_classes'], (sample_batch,))
+    # `denoise(x, steps_to_do=k)` runs the k steps t = k-1 .. 0 (diffusion.py:192-219); a step's cost does not depend on t
+    diff.denoise(x=x.clone(), kwargs={'y': y}, batch_size=sample_batch, progress=False, steps_to_do=max(1, warmup))
+    t0 = time.perf_counter()
+    diff.denoise(x=x.clone(), kwargs={'y': y}, batch_size=sample_batch, progress=False, steps_to_do=steps)
+    t_step = (time.perf_counter() - t0) / steps
+    return dict(value=sample_batch / (per_image * t_step), ms_per_step=1e3 * t_step, cores=torch.get_num_threads(),
+                kind='reference', batch=sample_batch,
+                sample='nicediffusion.Diffusion.denoise(device=cpu) from baseline/_ref (unmodified reference, fp32): {} '
+                       'denoising steps (+{} warm-up) of the {} chain at batch {}; images/sec = batch / ({} steps x time '
+                       'per step)'.format(steps, warmup, workload, sample_batch, per_image))
+
+
+def gpu_eager_reference(workload, B, dev, steps=3):
+    """Informational: the unmodified reference run eagerly on the SAME B200 -- torch's default
+    precision (cuDNN convs in TF32) and under bf16 autocast -- for a few denoising steps at this arm's batch."""
+    ref = import_reference()
+    if ref is None:
+        return None
+    rm, rd = ref
+    from nice_diffusion_b200.utils import randomize_zero_init_
+    cname, dkw, _, per_image = WORKLOADS[workload]
+    cfg = model_config(workload)
+    out = {'batch': B, 'steps_timed': steps, 'unit': 'images/sec',
+           'what': 'nicediffusion (baseline/_ref) Diffusion.denoise on cuda, eager PyTorch, same batch; extrapolated '
+                   'from {} steps like every other number here'.format(steps)}
+    try:
+        torch.manual_seed(0)
+        model = rm.DiffusionModel(**cfg)
+        randomize_zero_init_(model, seed=0)
+        diff = rd.Diffusion(model=model, device=dev, **dkw)
+        x = torch.randn(B, cfg['in_channels'], cfg['resolution'], cfg['resolution'], device=dev)
+        y = torch.randint(1, cfg['num_classes'], (B,), device=dev)
+        for key, ctx in (('tf32_default', None), ('bf16_autocast', torch.bfloat16)):
+            def run(k):
+                if ctx is None:
+                    return diff.denoise(x=x.clone(), kwargs={'y': y}, batch_size=B, progress=False, steps_to_do=k)
+                with torch.autocast('cuda', dtype=ctx):
+                    return diff.denoise(x=x.clone(), kwargs={'y': y}, batch_size=B, progress=False, steps_to_do=k)
+            run(2)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run(steps)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / steps
+            out[key] = {'ms_per_step': ms, 'value': B / (per_image * ms * 1e-3)}
+        del model, diff
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out['error'] = repr(e)[:200]
+    return out
+
+
+def oracle_port_arm(workload, steps, warmup, sample_batch=None):
+    """Fallback when baseline/_ref is absent: the oracle port of the reference's --cpu path."""
     from oracle import CONFIGS
     from oracle.sampler import Sampler
     from oracle.unet import unet_forward
@@ -118,12 +229,7 @@ def cpu_reference_arm(workload, steps, warmup, sample_batch=None):
         cfg = dict(cfg); cfg['num_classes'] = 1001
     if sample_batch is None:
         sample_batch = {'in64': 2, 'emnist': 16, 'in128': 1}[workload]
-    # all host cores this process may use (torchrun pins OMP_NUM_THREADS=1 in its children; undo that for this arm)
-    try:
-        ncores = len(os.sched_getaffinity(0))
-    except AttributeError:
-        ncores = os.cpu_count() or 1
-    torch.set_num_threads(max(1, ncores))
+    torch.set_num_threads(max(1, host_cores()))
     sd = random_state_dict(cfg, seed=0)
     okw = {k: v for k, v in dkw.items() if k != 'loss_type'}
 
@@ -146,6 +252,7 @@ def cpu_reference_arm(workload, steps, warmup, sample_batch=None):
         dt = time.perf_counter() - t0
     t_step = dt / steps
     return dict(value=sample_batch / (per_image * t_step), ms_per_step=1e3 * t_step, cores=torch.get_num_threads(),
+                kind='port',
                 sample='{} denoising steps (+{} warm-up) of the {} chain at batch {} on the host, oracle port of the '
                        'reference --cpu path; images/sec = batch / ({} steps x time per step)'.format(
                            steps, warmup, workload, sample_batch, per_image), batch=sample_batch)
@@ -183,6 +290,7 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--eager', action='store_true', help='launch kernels one by one instead of replaying CUDA graphs (profiling)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-gpu-reference', action='store_true', help='skip the informational eager-reference-on-GPU leg')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -210,10 +318,14 @@ def main():
         small = args.steps > 40
         r = cpu_reference_arm(args.config, args.steps, args.warmup,
                               sample_batch=({'in64': 1, 'emnist': 16, 'in128': 1}[args.config] if small else None))
+        # this arm's TRUE batch: a bounded sample of the workload on the host (one process, no GPUs)
+        config = dict(config, workload=config['workload'] + ' -- CPU arm: bounded sample at batch {} on {} host threads'.format(
+            r['batch'], r['cores']), per_gpu_batch=r['batch'], global_batch=r['batch'],
+            parallelism='one host process, {} threads'.format(r['cores']), operands='fp32 (PyTorch CPU kernels)', l2='n/a')
         line = {'impl': 'reference', 'metric': metric, 'value': r['value'], 'unit': 'images/sec', 'n_gpus': args.gpus,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
-                'cpu_baseline': {'value': r['value'], 'unit': 'images/sec', 'cores': r['cores'], 'kind': 'port',
+                'cpu_baseline': {'value': r['value'], 'unit': 'images/sec', 'cores': r['cores'], 'kind': r['kind'],
                                  'sample': r['sample']},
                 'e2e': {'value': r['value'], 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
         _emit(line)
@@ -317,20 +429,32 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (implicit-GEMM conv), measured live with CUDA events per launch ----
+    # ---- roofline: every launch of the step timed IN the step's graph (globaltimer stamps between kernels, warm caches,
+    #      no host launch latency: UNetEngine.timeline), aggregated per kernel ----
     pk = peaks()
     prof = runner.profile_kernels()
     conv = prof['conv_gemm']
     achieved = conv['flops'] / (conv['ms'] * 1e-3) / 1e12
     fwd_tflops = FLOPS_PER_FWD[args.config] * runner.model_batch / (ms_per_step * 1e-3) / 1e12
+    gn = prof.get('gn_apply', {'ms': 0.0, 'bytes': 0, 'launches': 0})
+    at = prof.get('attention', {'ms': 0.0, 'flops': 0, 'launches': 0})
     roofline = {'bound': 'tensor', 'kernel': 'conv_gemm_kernel (tcgen05 implicit GEMM, all conv / linear layers)',
                 'achieved': achieved, 'peak': pk['bf16_sustained'], 'unit': 'TFLOP/s', 'frac': achieved / pk['bf16_sustained'],
                 'peak_kind': pk['source'] + ' sustained dense bf16 (kernel timed inside a long step)',
                 'frac_of_burst_peak': achieved / pk['bf16'], 'traffic': None,
                 'launches_per_step': conv['launches'], 'ms_per_step_in_kernel': conv['ms'],
                 'share_of_step': conv['ms'] / prof['total_ms'],
-                'unet_forward': {'tflops': fwd_tflops, 'frac': fwd_tflops / pk['bf16_sustained'],
-                                 'what': 'algorithmic FLOPs of one UNet forward x batch / graph-replayed step time'},
+                # the whole UNet forward (the number the north-star target is written against): algorithmic FLOPs of one
+                # forward x batch / graph-replayed step time
+                'step_tflops': fwd_tflops, 'step_frac': fwd_tflops / pk['bf16_sustained'],
+                'step_frac_of_burst': fwd_tflops / pk['bf16'],
+                # HBM-bound norm kernel: algorithmic bytes (input once + every output once) / its time in the step
+                'gn_apply_gbs': gn['bytes'] / (gn['ms'] * 1e-3) / 1e9 if gn['ms'] > 0 else None,
+                'gn_apply_frac': gn['bytes'] / (gn['ms'] * 1e-3) / 1e9 / pk['hbm'] if gn['ms'] > 0 else None,
+                'gn_apply_ms': gn['ms'], 'gn_apply_launches': gn['launches'], 'hbm_peak_gbs': pk['hbm'],
+                'attention_tflops': at['flops'] / (at['ms'] * 1e-3) / 1e12 if at['ms'] > 0 else None,
+                'attention_ms': at['ms'], 'attention_launches': at['launches'],
+                'timing': 'per-kernel times: %globaltimer stamps between the launches inside one CUDA graph of the step',
                 'other_kernels_ms': {k: v['ms'] for k, v in prof.items() if isinstance(v, dict) and k != 'conv_gemm'}}
 
     # DRAM traffic of the dominant kernel: from the committed ncu pass of the same step (profiles/), not measured live
@@ -345,15 +469,23 @@ def main():
     except Exception:
         pass
 
+    gpu_ref = None
+    if not args.no_gpu_reference and world == 1:
+        del runner
+        model.release_engines()
+        torch.cuda.empty_cache()
+        gpu_ref = gpu_eager_reference(args.config, B, dev)
+
     cpu = None
     if not args.no_cpu_baseline:
-        r = cpu_reference_arm(args.config, 2, 1)
-        cpu = {'value': r['value'], 'unit': 'images/sec', 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']}
+        r = cpu_reference_arm(args.config, 3, 1)
+        cpu = {'value': r['value'], 'unit': 'images/sec', 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample']}
 
     line = {'metric': metric, 'value': value, 'unit': 'images/sec', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'fp16', 'data': 'synthetic', 'config': config, 'clocks': clk,
-            'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu}
+            'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
+            'gpu_eager_reference': gpu_ref}
     _emit(line)
     if dist is not None:
         dist.destroy_process_group()

@@ -134,33 +134,49 @@ struct GnApplyArgs {
     int x0_is16;     // x0 holds 16-bit values (operand_format) instead of fp32
     float* pool32;   // DOWN2 only: fp32 2x2 mean of the raw input (the x_resample operand of a down ResBlock)
     float eps;
-    int pix_per_block, threads_per_row, rows_per_block;
+    int pix_per_block;
+    int chunk_ch;    // channels per block (blockIdx.z selects the chunk): whole groups, a multiple of 8; C when not chunked
 };
 
-// Block = one sample n and a range of output pixels. Thread (r, v) owns the 8-channel vector v and pixels
-// p_begin + r, + rows_per_block, ...  Order of business, arranged so that the dependent-load chains overlap:
-//   0. request the first four pixels of this thread's data (independent of everything else);
-//   1. 8 lanes per group fold the statistics slots of the source tensor(s) into (mean, rstd) -> smem;
-//   2. all threads fold mean / rstd / gamma / beta / AdaGN (1+scale), shift / pre-add into one per-channel FMA
-//      (a_c, b_c) -> smem;
-//   3. stream: y = SiLU(a x + b) (+ resample) -> 16-bit operand, 16-byte stores, four pixels in flight per thread.
+// Block = one sample n (blockIdx.y), a range of output pixels (blockIdx.x) and a group-aligned range of channels
+// (blockIdx.z). Large feature maps split over pixels only; the low-resolution levels (8x8, 16x16: a few hundred KB per
+// sample) split over CHANNELS as well, so that the machine is filled with blocks whose statistics prologue covers only
+// their own 64..144 channels -- with pixel-only splitting every block folded the slots of all C channels, which read more
+// bytes than the tensor itself and made those launches pure latency (8 us for 9 MB).
+// Thread (r, v) owns the 8-channel vector v of the chunk and pixels p_begin + r, + rows_per_block, ...  Order of business,
+// arranged so that the dependent-load chains overlap:
+//   0. before griddepcontrol.wait: slot counts (static per plan);
+//   1. request the first four pixels of this thread's data and, one channel per thread, ALL statistics slots of that
+//      channel (independent loads, 8 in flight) -> per-channel fp64 (sum, sumsq) in shared memory;
+//   2. 8 lanes per group fold the channels of a group into (mean, rstd) -> smem;
+//   3. one channel per thread folds mean / rstd / gamma / beta / AdaGN (1+scale), shift / pre-add into one FMA (a_c, b_c);
+//   4. stream: y = SiLU(a x + b) (+ resample) -> 16-bit operand, 16-byte stores, four pixels in flight per thread.
+// The summation order (slots in order per channel; channels sub, sub+8, ... per lane; xor-shuffles) is fixed: results are
+// bit-reproducible and independent of the chunking.
 // IN16: x0 is a 16-bit tensor (the fp16 `h` between the two convs of a ResBlock) instead of fp32.
 template <int FMT, int RESAMPLE, bool SILU, bool RAW, bool IN16>
 __global__ void __launch_bounds__(kGnThreads, 3)
 gn_apply_kernel(const GnApplyArgs p) {
-    extern __shared__ float sm_ab[];   // a[C], b[C], pre[C]
+    extern __shared__ __align__(16) unsigned char sm_raw[];
     __shared__ float s_mean[kGroups], s_rstd[kGroups];
     const int C = p.C0 + p.C1;
-    const int V8 = C >> 3;
     const int n = blockIdx.y;
     const int cpg = p.cpg > 0 ? p.cpg : C / kGroups;
-    const int ngroups = C / cpg;          // <= 32
-    float* sa = sm_ab;
-    float* sb = sm_ab + C;
-    float* sp = sm_ab + 2 * C;
-    const int r = threadIdx.x / p.threads_per_row;
-    const int tv = threadIdx.x - r * p.threads_per_row;
-    const bool worker = (r < p.rows_per_block) && (tv < V8);
+    const int c_lo = blockIdx.z * p.chunk_ch;
+    const int Cb = (C - c_lo) < p.chunk_ch ? (C - c_lo) : p.chunk_ch;   // channels of this block (whole groups, % 8 == 0)
+    const int Vb = Cb >> 3;
+    const int ngroups = Cb / cpg;         // <= 32
+    // shared memory: [2][Cb] doubles during the statistics phase, then (aliased, after a barrier) a[Cb], b[Cb], pre[Cb]
+    double* dS = reinterpret_cast<double*>(sm_raw);
+    double* dSS = dS + Cb;
+    float* sa = reinterpret_cast<float*>(sm_raw);
+    float* sb = sa + Cb;
+    float* sp = sa + 2 * Cb;
+    const int threads_per_row = Vb < kGnThreads ? Vb : kGnThreads;
+    const int rows_per_block = kGnThreads / threads_per_row;
+    const int r = threadIdx.x / threads_per_row;
+    const int tv = threadIdx.x - r * threads_per_row;
+    const bool worker = (r < rows_per_block) && (tv < Vb);
     const int npix = p.Ho * p.Wo;
     const int p_begin = blockIdx.x * p.pix_per_block;
     int p_end = p_begin + p.pix_per_block;
@@ -207,51 +223,56 @@ gn_apply_kernel(const GnApplyArgs p) {
         return pu;
     };
 
+    // ---- 0. static data (written when the plan was built, never by a kernel of the step): legal before the wait ----
+    const int cnt0 = __ldg(p.counts0 + n);
+    const int cnt1 = p.parts1 ? __ldg(p.counts1 + n) : 0;
     pdl_launch_dependents();
     pdl_wait();
-    // ---- 0. first trip's data ----
+    // ---- 1a. first trip's data ----
     uint4 lo[U], hi[U];
     if (RESAMPLE != NDB_RESAMPLE_DOWN2 && worker) {
         const float* src; int ldc;
-        src_of(tv << 3, src, ldc);
+        src_of(c_lo + (tv << 3), src, ldc);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int pu = p_begin + r + u * p.rows_per_block;
+            const int pu = p_begin + r + u * rows_per_block;
             if (pu < p_end) load8(src, ldc, in_pixel(pu), lo[u], hi[u]);
         }
     }
-
-    // ---- 1. group statistics. With `pre_add` e_c (non-adaptive ResBlock: h += emb before the norm) the sums of
-    //         (x + e_c) follow analytically: S' = S + P e, SS' = SS + 2 e S + P e^2. ----
+    // ---- 1b. per-channel statistics: the slots of a channel are fetched eight at a time (independent loads) and added in
+    //          slot order. With `pre_add` e_c (non-adaptive ResBlock: h += emb before the norm) the sums of (x + e_c) follow
+    //          analytically: S' = S + P e, SS' = SS + 2 e S + P e^2. ----
+    const double P = (double)p.H * p.W;
+    for (int cl = threadIdx.x; cl < Cb; cl += kGnThreads) {
+        const int c = c_lo + cl;
+        const bool first = c < p.C0;
+        const float2* src = first ? p.parts0 + (size_t)n * p.smax0 * p.C0 + c
+                                  : p.parts1 + (size_t)n * p.smax1 * p.C1 + (c - p.C0);
+        const size_t ldp = first ? (size_t)p.C0 : (size_t)p.C1;
+        const int cnt = first ? cnt0 : cnt1;
+        double s1 = 0.0, s2 = 0.0;
+        for (int sl = 0; sl < cnt; sl += 8) {
+            float2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (sl + u < cnt) ? __ldg(src + (size_t)(sl + u) * ldp) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { s1 += (double)v[u].x; s2 += (double)v[u].y; }
+        }
+        if (p.pre_add != nullptr) {
+            const double e = (double)p.pre_add[(size_t)n * p.ld_pre + c];
+            s2 += 2.0 * e * s1 + P * e * e;
+            s1 += P * e;
+        }
+        dS[cl] = s1;
+        dSS[cl] = s2;
+    }
+    __syncthreads();
+    // ---- 2. groups ----
     {
         const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
-        const double P = (double)p.H * p.W;
         double S = 0.0, SS = 0.0;
-        const int cnt0 = p.counts0[n];
-        const int cnt1 = p.parts1 ? p.counts1[n] : 0;
-        for (int k = sub; g < ngroups && k < cpg; k += 8) {
-            const int c = g * cpg + k;
-            double s1 = 0.0, s2 = 0.0;
-            // the slot partials of a channel are fetched four at a time (independent loads; a one-load-per-iteration loop
-            // pays the full L2 latency per slot: ~4 us for the 12 slots of a 64x64 layer) and added in slot order
-            const bool first = c < p.C0;
-            const float2* src = first ? p.parts0 + (size_t)n * p.smax0 * p.C0 + c
-                                      : p.parts1 + (size_t)n * p.smax1 * p.C1 + (c - p.C0);
-            const size_t ldp = first ? (size_t)p.C0 : (size_t)p.C1;
-            const int cnt = first ? cnt0 : cnt1;
-            for (int sl = 0; sl < cnt; sl += 4) {
-                float2 v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = (sl + u < cnt) ? __ldg(src + (size_t)(sl + u) * ldp) : make_float2(0.f, 0.f);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { s1 += (double)v[u].x; s2 += (double)v[u].y; }
-            }
-            if (p.pre_add != nullptr) {
-                const double e = (double)p.pre_add[(size_t)n * p.ld_pre + c];
-                s2 += 2.0 * e * s1 + P * e * e;
-                s1 += P * e;
-            }
-            S += s1; SS += s2;
+        if (g < ngroups) {
+            for (int k = sub; k < cpg; k += 8) { S += dS[g * cpg + k]; SS += dSS[g * cpg + k]; }
         }
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) {
@@ -267,10 +288,11 @@ gn_apply_kernel(const GnApplyArgs p) {
             s_rstd[g] = rsqrtf((float)var + p.eps);
         }
     }
-    __syncthreads();
-    // ---- 2. per-channel affine ----
-    for (int c = threadIdx.x; c < C; c += kGnThreads) {
-        const int g = c / cpg;
+    __syncthreads();      // also: every read of dS / dSS is done, the region is re-used for a / b / pre below
+    // ---- 3. per-channel affine ----
+    for (int cl = threadIdx.x; cl < Cb; cl += kGnThreads) {
+        const int c = c_lo + cl;
+        const int g = cl / cpg;
         float ak = s_rstd[g] * __ldg(p.gamma + c);
         float bk = __ldg(p.beta + c) - s_mean[g] * ak;
         const float pr = p.pre_add ? __ldg(p.pre_add + (size_t)n * p.ld_pre + c) : 0.f;
@@ -281,24 +303,25 @@ gn_apply_kernel(const GnApplyArgs p) {
             bk = bk * s1 + __ldg(p.shift + (size_t)n * p.ld_ss + c);
         }
         if (SILU) { ak *= 0.5f; bk *= 0.5f; }   // SiLU is evaluated from v / 2 (silu_half)
-        sa[c] = ak; sb[c] = bk;
-        if (RAW) sp[c] = pr;
+        sa[cl] = ak; sb[cl] = bk;
+        if (RAW) sp[cl] = pr;
     }
     __syncthreads();
     if (!worker) return;
 
-    // ---- 3. stream ----
-    for (int v = tv; v < V8; v += p.threads_per_row) {
-        const int c = v << 3;
+    // ---- 4. stream ----
+    for (int v = tv; v < Vb; v += threads_per_row) {
+        const int cl = v << 3;
+        const int c = c_lo + cl;
         float a[8], b[8], pre[8];
         {
-            const float4 a0 = *reinterpret_cast<const float4*>(sa + c), a1 = *reinterpret_cast<const float4*>(sa + c + 4);
-            const float4 b0 = *reinterpret_cast<const float4*>(sb + c), b1 = *reinterpret_cast<const float4*>(sb + c + 4);
+            const float4 a0 = *reinterpret_cast<const float4*>(sa + cl), a1 = *reinterpret_cast<const float4*>(sa + cl + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(sb + cl), b1 = *reinterpret_cast<const float4*>(sb + cl + 4);
             a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
             b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
             if (RAW) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) pre[k] = sp[c + k];
+                for (int k = 0; k < 8; ++k) pre[k] = sp[cl + k];
             }
         }
         const float* src; int ldc;
@@ -307,7 +330,7 @@ gn_apply_kernel(const GnApplyArgs p) {
         uint16_t* __restrict__ outq = p.out + (size_t)n * npix * C + c;
         uint16_t* __restrict__ rawq = RAW ? p.raw16 + (size_t)n * npix * C + c : nullptr;
         if (RESAMPLE == NDB_RESAMPLE_DOWN2) {
-            for (int po = p_begin + r; po < p_end; po += p.rows_per_block) {
+            for (int po = p_begin + r; po < p_end; po += rows_per_block) {
                 float y[8], raw[8];
                 const int ho = po / p.Wo, wo = po - ho * p.Wo;
                 const float* px = srcp + ((size_t)(2 * ho) * p.W + 2 * wo) * ldc;
@@ -352,7 +375,7 @@ gn_apply_kernel(const GnApplyArgs p) {
         } else {
             // this thread's pixels: p_begin + r, + rows_per_block, ... ; element offsets advance by constant strides (no
             // per-pixel 64-bit index arithmetic in the loop)
-            const int rows = p.rows_per_block;
+            const int rows = rows_per_block;
             int cnt = (p_end - (p_begin + r) + rows - 1) / rows;           // > 0 for workers with a pixel
             const size_t esz = IN16 ? 2 : 4;
             const uint32_t out_stride = (uint32_t)rows * (uint32_t)C;       // elements between two of this thread's pixels
@@ -432,10 +455,19 @@ gn_apply_kernel(const GnApplyArgs p) {
     }
 }
 
+// shared memory of a block: max(2 doubles, 3 floats) per channel of its chunk
+static size_t gn_apply_smem(const GnApplyArgs& a) { return 16 * (size_t)a.chunk_ch; }
+
+template <typename K>
+static void launch_gn(K kernel, const GnApplyArgs& a, dim3 grid, cudaStream_t st) {
+    const size_t smem = gn_apply_smem(a);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // C > 3072, unchunked
+    launch_kernel(kernel, grid, dim3(kGnThreads), smem, st, 1, a);
+}
+
 template <int FMT, bool RAW>
 static void launch_gn_apply2(const GnApplyArgs& a, dim3 grid, cudaStream_t st) {
-    const size_t smem = 3 * (size_t)(a.C0 + a.C1) * sizeof(float);
-#define NDB_GN_CASE(RS, SL) launch_kernel(gn_apply_kernel<FMT, RS, SL, RAW, false>, grid, dim3(kGnThreads), smem, st, 1, a)
+#define NDB_GN_CASE(RS, SL) launch_gn(gn_apply_kernel<FMT, RS, SL, RAW, false>, a, grid, st)
     if (a.resample == NDB_RESAMPLE_NONE) { if (a.silu) NDB_GN_CASE(NDB_RESAMPLE_NONE, true); else NDB_GN_CASE(NDB_RESAMPLE_NONE, false); }
     else if (a.resample == NDB_RESAMPLE_UP2) { if (a.silu) NDB_GN_CASE(NDB_RESAMPLE_UP2, true); else NDB_GN_CASE(NDB_RESAMPLE_UP2, false); }
     else { if (a.silu) NDB_GN_CASE(NDB_RESAMPLE_DOWN2, true); else NDB_GN_CASE(NDB_RESAMPLE_DOWN2, false); }
@@ -446,9 +478,8 @@ template <int FMT>
 static void launch_gn_apply(const GnApplyArgs& a, dim3 grid, cudaStream_t st) {
     if (a.x0_is16) {
         // 16-bit source: the out_norm of a ResBlock (single source, no resampling, no raw copy)
-        const size_t smem = 3 * (size_t)(a.C0 + a.C1) * sizeof(float);
-        if (a.silu) launch_kernel(gn_apply_kernel<FMT, NDB_RESAMPLE_NONE, true, false, true>, grid, dim3(kGnThreads), smem, st, 1, a);
-        else launch_kernel(gn_apply_kernel<FMT, NDB_RESAMPLE_NONE, false, false, true>, grid, dim3(kGnThreads), smem, st, 1, a);
+        if (a.silu) launch_gn(gn_apply_kernel<FMT, NDB_RESAMPLE_NONE, true, false, true>, a, grid, st);
+        else launch_gn(gn_apply_kernel<FMT, NDB_RESAMPLE_NONE, false, false, true>, a, grid, st);
     } else if (a.raw16 != nullptr) launch_gn_apply2<FMT, true>(a, grid, st);
     else launch_gn_apply2<FMT, false>(a, grid, st);
 }
@@ -533,18 +564,45 @@ extern "C" int ndb_gn_apply(const ndb_gn_apply_params* q, void* stream) {
     if (q->x0_is16) NDB_CHECK_ARG(q->x1 == nullptr && q->resample == NDB_RESAMPLE_NONE && q->raw16 == nullptr);
     NDB_CHECK_ARG(q->pool32 == nullptr || q->resample == NDB_RESAMPLE_DOWN2);
     a.eps = q->eps;
-    const int V8 = C / 8;
-    a.threads_per_row = V8 < kGnThreads ? V8 : kGnThreads;
-    a.rows_per_block = kGnThreads / a.threads_per_row;
     const int npix = a.Ho * a.Wo;
-    // one full wave at the kernel's occupancy (3 blocks per SM): no tail wave, prologue amortised over more pixels
-    int blocks_per_sample = (3 * num_sms()) / q->N;
-    if (blocks_per_sample < 1) blocks_per_sample = 1;
-    int ppb = (npix + blocks_per_sample - 1) / blocks_per_sample;
-    const int min_pix = a.rows_per_block * 4;
-    if (ppb < min_pix) ppb = min_pix;
+    const int cpg = q->cpg > 0 ? q->cpg : C / kGroups;
+    // target: one full wave at the kernel's occupancy (3 blocks per SM): no tail wave, prologue amortised over more pixels
+    int target = (3 * num_sms()) / q->N;
+    if (target < 1) target = 1;
+    auto pixel_split = [&](int chunk_ch, int want_blocks, int& ppb) {
+        const int v8 = chunk_ch / 8;
+        const int rows = kGnThreads / (v8 < kGnThreads ? v8 : kGnThreads);
+        ppb = (npix + want_blocks - 1) / want_blocks;
+        if (ppb < rows * 4) ppb = rows * 4;
+        return (npix + ppb - 1) / ppb;
+    };
+    int ppb = 0;
+    int chunks = 1;
+    a.chunk_ch = C;
+    int pblocks = pixel_split(C, target, ppb);
+    static int no_chunk = -1;
+    if (no_chunk < 0) no_chunk = std::getenv("NDB_GN_NO_CHUNK") != nullptr ? 1 : 0;
+    if (pblocks < target && !no_chunk) {
+        // small feature map: split the channels too. A chunk is a whole number of groups and of 8-channel vectors
+        // (granule = lcm(cpg, 8) channels) and at least 64 channels wide (256-byte rows keep the accesses coalesced).
+        int gran = cpg;
+        while (gran % 8 != 0) gran += cpg;
+        int granules = C / gran;                               // C % gran == 0: C is a multiple of 32 * cpg ... and of 8
+        if (C % gran != 0) granules = 0;
+        int per = 1;                                           // granules per chunk
+        while (per * gran < 64 && per < granules) ++per;
+        if (granules > 0) {
+            int max_chunks = granules / per;
+            if (max_chunks < 1) max_chunks = 1;
+            int want = target < max_chunks ? target : max_chunks;
+            per = (granules + want - 1) / want;
+            a.chunk_ch = per * gran;
+            chunks = (C + a.chunk_ch - 1) / a.chunk_ch;
+            pblocks = pixel_split(a.chunk_ch, (target + chunks - 1) / chunks, ppb);
+        }
+    }
     a.pix_per_block = ppb;
-    dim3 grid((npix + ppb - 1) / ppb, q->N);
+    dim3 grid(pblocks, q->N, chunks);
     if (q->operand_format == 0)
         launch_gn_apply<0>(a, grid, (cudaStream_t)stream);
     else

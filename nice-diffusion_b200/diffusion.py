@@ -435,19 +435,46 @@ class _StepRunner:
         return self.eng.x_in[:self.B].clone()
 
     def profile_kernels(self):
-        """Eager pass of one step with CUDA events around every launch (bench.py roofline). Restores the state."""
-        d, eng, st = self.diff, self.eng, self.st
+        """Per-kernel time of one step, measured inside a CUDA graph with %globaltimer stamps between the launches
+        (UNetEngine.timeline) plus the two sampler kernels timed the same way. -> {name: {ms, launches, flops, bytes},
+        total_ms}. Restores the sampling state."""
+        d, eng, st, B = self.diff, self.eng, self.st, self.B
         saved = (eng.x_in.clone(), st['t_step'].clone(), eng.t_in.clone())
-        eng.serial = True                   # one stream: overlapping kernels would inflate each other's event times
-        try:
-            self._launch()                  # warm
-            torch.cuda.synchronize(d.device)
-            ops.PROFILE = []
-            self._launch()
-            torch.cuda.synchronize(d.device)
-            summary = ops.profile_summary(ops.PROFILE)
-        finally:
-            ops.PROFILE = None
-            eng.serial = False
+        rows, _stamp = eng.timeline()
+        # the fused step kernel + the step counter, bracketed the same way
+        buf = torch.zeros(4, dtype=torch.int64, device=d.device)
+
+        def tail():
+            ops.timestamp(buf, 0)
+            ops.timestamp(buf, 1)
+            ops.sampler_step(eng.x_in[:B], eng.out[:B], st['t_step'], self.tabs['tab'], d._var_code(), ddim=d.use_ddim,
+                             eta=d.ddim_eta if d.use_ddim else 0.0, null_out=eng.out[B:] if self.cfg else None,
+                             cfg_strength=d.strength if self.cfg else 0.0, clip_x0=True,
+                             noise=None if self.use_philox else st['noise'], seed=d.seed, sample_ids=st['ids'],
+                             x_prev=eng.x_in[:B], x_prev2=eng.x_in[B:] if self.cfg else None)
+            ops.timestamp(buf, 2)
+            ops.advance_step(st['t_step'], eng.t_in, self.tabs['tmap_f32'])
+            ops.timestamp(buf, 3)
+        tail()
+        torch.cuda.synchronize(d.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            tail()
+        g.replay()
+        torch.cuda.synchronize(d.device)
+        tb = buf.cpu().double()
+        cost = float(tb[1] - tb[0])
+        px = eng.x_in[:B].numel()
+        rows = list(rows) + [('sampler_step', '', max(float(tb[2] - tb[1]) - cost, 0.0) / 1e3, 0, 16 * px),
+                             ('advance_step', '', max(float(tb[3] - tb[2]) - cost, 0.0) / 1e3, 0, 0)]
         eng.x_in.copy_(saved[0]); st['t_step'].copy_(saved[1]); eng.t_in.copy_(saved[2])
-        return summary
+        out, total = {}, 0.0
+        for name, _desc, us, flops, nbytes in rows:
+            e = out.setdefault(name, {'ms': 0.0, 'launches': 0, 'flops': 0, 'bytes': 0})
+            e['ms'] += us / 1e3
+            e['launches'] += 1
+            e['flops'] += flops
+            e['bytes'] += nbytes
+            total += us / 1e3
+        out['total_ms'] = total
+        return out

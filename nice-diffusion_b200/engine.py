@@ -529,15 +529,15 @@ class UNetEngine:
     def timeline(self, replays=5):
         """In-graph, warm-cache duration of every launch of the plan: the launches are captured on ONE stream with a
         %globaltimer stamp (ndb_timestamp) between consecutive kernels, the graph is replayed and the stamp differences
-        averaged. Returns [(kernel name, description, microseconds)], with the stamp kernel's own cost (two stamps back
-        to back) subtracted. Unlike CUDA events around eager launches this does not include host launch latency, and
+        averaged. Returns ([(kernel name, description, microseconds, algorithmic flops, algorithmic bytes)], stamp cost),
+        with the stamp kernel's own cost (two stamps back to back) subtracted. Unlike CUDA events around eager launches this does not include host launch latency, and
         unlike an ncu pass the caches are as warm as in production."""
         dev = self.device
         launches = []                 # (callable, is_kernel)
         for i, f in enumerate(self.steps):
             if self.early and i == self.early_fork_idx:
-                launches += [(g, True) for g, _ev in self.early]
-            launches.append((f, True))
+                launches += [(g, ev) for g, ev in self.early]    # their consumers wait on these events
+            launches.append((f, None))
         n = len(launches)
         buf = torch.zeros(n + 3, dtype=torch.int64, device=dev)
         was_serial, self.serial = self.serial, True
@@ -546,12 +546,14 @@ class UNetEngine:
         def run(record):
             ops.timestamp(buf, 0)
             ops.timestamp(buf, 1)                      # calibration: stamp[1] - stamp[0] = cost of a stamp
-            for k, (f, _) in enumerate(launches):
+            for k, (f, ev) in enumerate(launches):
                 n0 = len(ops.PROFILE) if record else 0
                 f()
+                if ev is not None:
+                    ev.record(torch.cuda.current_stream(dev))
                 if record:
                     rec = ops.PROFILE[n0:]
-                    names.append((rec[0][0], rec[0][4]) if rec else ('wait', ''))
+                    names.append((rec[0][0], rec[0][4], rec[0][3], rec[0][5]) if rec else ('wait', '', 0, 0))
                 ops.timestamp(buf, 2 + k)
         try:
             ops.PROFILE = []
@@ -577,7 +579,8 @@ class UNetEngine:
         stamp_cost = float(acc[1] - acc[0])
         out = []
         for k in range(n):
-            out.append((names[k][0], names[k][1], max(float(acc[2 + k] - acc[1 + k]) - stamp_cost, 0.0) / 1e3))
+            out.append((names[k][0], names[k][1], max(float(acc[2 + k] - acc[1 + k]) - stamp_cost, 0.0) / 1e3,
+                        names[k][2], names[k][3]))
         return out, stamp_cost / 1e3
 
     @torch.no_grad()

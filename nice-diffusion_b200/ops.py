@@ -23,19 +23,19 @@ def _begin():
         _pending.record()
 
 
-def _count(name='kernel', flops=0, desc=''):
+def _count(name='kernel', flops=0, desc='', nbytes=0):
     global LAUNCHES
     LAUNCHES += 1
     if PROFILE is not None:
         end = torch.cuda.Event(enable_timing=True)
         end.record()
-        PROFILE.append((name, _pending, end, flops, desc))
+        PROFILE.append((name, _pending, end, flops, desc, nbytes))
 
 
 def profile_summary(records):
     """Aggregate PROFILE records (after a device synchronize) -> {name: {ms, launches, flops}, total_ms}."""
     out, total = {}, 0.0
-    for name, e0, e1, flops, _desc in records:
+    for name, e0, e1, flops, _desc, _nbytes in records:
         ms = e0.elapsed_time(e1)
         d = out.setdefault(name, {'ms': 0.0, 'launches': 0, 'flops': 0})
         d['ms'] += ms
@@ -222,7 +222,10 @@ def gn_apply(x0, stats0, gamma, beta, x1=None, stats1=None, scale=None, shift=No
     p.cpg = cpg
     _begin()
     L.check(L.load().ndb_gn_apply(C.byref(p), L.stream_ptr()), 'ndb_gn_apply')
-    _count('gn_apply', 0, 'N{} {}x{} C{} rs{} raw{}'.format(N, H, W, C0 + C1, resample, int(raw16 is not None)))
+    # algorithmic bytes: the input read once + every output written once
+    nbytes = N * H * W * (C0 * x0.element_size() + C1 * 4) + N * Ho * Wo * (C0 + C1) * (
+        2 + (2 if raw16 is not None else 0) + (4 if pool32 is not None else 0))
+    _count('gn_apply', 0, 'N{} {}x{} C{} rs{} raw{}'.format(N, H, W, C0 + C1, resample, int(raw16 is not None)), nbytes)
     return (out, raw16) if (want_raw16 or raw16 is not None) else out
 
 

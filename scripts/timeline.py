@@ -39,20 +39,22 @@ def main():
     total = sum(r[2] for r in rows)
     lines = ['in-graph timeline ({} B={}): {} launches, sum {:.1f} us, stamp cost {:.2f} us'.format(a.config, B, len(rows), total, stamp)]
     if a.raw:
-        for i, (name, desc, us) in enumerate(rows):
+        for i, (name, desc, us, _f, _b) in enumerate(rows):
             lines.append('{:4d} {:12s} {:46s} {:8.1f}'.format(i, name, desc, us))
     else:
         agg = collections.OrderedDict()
         by_kernel = collections.Counter()
-        for name, desc, us in rows:
-            d = agg.setdefault((name, desc), [0, 0.0])
+        for name, desc, us, fl, nb in rows:
+            d = agg.setdefault((name, desc), [0, 0.0, 0, 0])
             d[0] += 1
             d[1] += us
+            d[2] += fl
+            d[3] += nb
             by_kernel[name] += us
         lines.append(str({k: round(v / 1e3, 3) for k, v in by_kernel.items()}))
-        lines.append('{:12s} {:46s} {:>3s} {:>9s} {:>9s}'.format('kernel', 'shape', 'n', 'ms/step', 'us/launch'))
-        for (name, desc), (cnt, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-            lines.append('{:12s} {:46s} {:3d} {:9.3f} {:9.1f}'.format(name, desc, cnt, us / 1e3, us / cnt))
+        lines.append('{:12s} {:46s} {:>3s} {:>9s} {:>9s} {:>8s} {:>7s}'.format('kernel', 'shape', 'n', 'ms/step', 'us/launch', 'TFLOP/s', 'GB/s'))
+        for (name, desc), (cnt, us, fl, nb) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            lines.append('{:12s} {:46s} {:3d} {:9.3f} {:9.1f} {:8.1f} {:7.0f}'.format(name, desc, cnt, us / 1e3, us / cnt, fl / max(us, 1e-9) / 1e6, nb / max(us, 1e-9) / 1e3))
     text = '\n'.join(lines)
     print(text)
     if a.out:
