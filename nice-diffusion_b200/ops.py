@@ -177,8 +177,8 @@ def stats_totals(stats):
     """(parts, counts) -> float64 [N, C, 2] totals (test helper; the kernels never materialise this)."""
     parts, counts = stats
     N, smax = parts.shape[0], parts.shape[1]
-    mask = (torch.arange(smax, device=parts.device)[None, :] < counts[:, None]).to(torch.float64)
-    return (parts.double() * mask[:, :, None, None]).sum(1)
+    mask = torch.arange(smax, device=parts.device)[None, :] < counts[:, None]
+    return torch.where(mask[:, :, None, None], parts.double(), torch.zeros((), dtype=torch.float64, device=parts.device)).sum(1)
 
 
 def gn_apply(x0, stats0, gamma, beta, x1=None, stats1=None, scale=None, shift=None, pre_add=None, silu=True,
