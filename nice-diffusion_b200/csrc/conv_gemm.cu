@@ -47,6 +47,7 @@ struct TmapPack {
     CUtensorMap a[kMaxSeg];
     CUtensorMap b[kMaxSeg];
     CUtensorMap out;    // bulk epilogue: {32 channels, box_w, box_h, 1} boxes of the NHWC output
+    CUtensorMap res;    // bulk epilogue with a same-size residual: the same boxes of the fp32 NHWC residual tensor
 };
 
 struct ConvArgs {
@@ -149,6 +150,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             prefetch_tmap(&maps.b[s]);
         }
         if (p.epi_bulk) prefetch_tmap(&maps.out);
+        if (p.epi_bulk && p.res_mode == NDB_RES_SAME) prefetch_tmap(&maps.res);
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], k2 ? 2 : 1);   // pair mode: both CTAs' producers arrive on the leader's barrier
             mbar_init(&empty_bar[s], 1);
@@ -159,6 +161,9 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             mbar_init(&stat_full_bar[s], kEpiWarps);
             mbar_init(&stat_empty_bar[s], 1);
         }
+        if (p.epi_bulk)     // per epilogue warp: three "residual box has landed" barriers (inside its row-table slot)
+            for (int w = 0; w < kEpiWarps; ++w)
+                for (int b = 0; b < 3; ++b) mbar_init(reinterpret_cast<uint64_t*>(epi_rows + w * 128 + 64) + b, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -299,11 +304,20 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             // ------------------------------------------------------------------------------------------------
             // bulk path
             // ------------------------------------------------------------------------------------------------
-            uint8_t* sbuf0 = epi_base + (warp - 2) * 4096 * p.epi_bufs;
-            int sb = 0;
-            long long* row_tab = epi_rows + (warp - 2) * 128;     // [2 tile parities][32 rows]: residual element offsets
+            // Per warp and 32-column chunk: the accumulator rows come out of TMEM (thread = row), bias (stashed in shared
+            // memory once per tile, before the accumulator is waited for) and -- if there is one -- the residual are added in
+            // that same thread = row form, the result sits in a 4 KB SWIZZLE_128B staging tile and ONE TMA store writes the
+            // {32 ch, w, h} box. The RESIDUAL box arrives by TMA as well, straight into the staging tile it will be added in:
+            // three tiles per warp rotate through [loading chunk i+1 | being processed: chunk i | being stored: chunk i-1],
+            // so two boxes per warp are always in flight without holding a register (the per-row __ldg version kept 64
+            // registers busy, could only run one chunk ahead and capped the residual stream at ~3 TB/s: the proj GEMMs of the
+            // attention blocks took twice their HBM time).
             const bool has_res = p.res_mode == NDB_RES_SAME;
-            const bool transposed = has_res;     // in-place pass with lanes along channels (bias + residual)
+            const int nbuf = p.epi_bufs;        // residual: 3 (short K: the epilogue is the critical path) or 2 (long K: the
+                                                // staging space goes to the operand pipeline instead)
+            uint8_t* sbuf0 = epi_base + (warp - 2) * 4096 * nbuf;
+            float* bias_s = reinterpret_cast<float*>(epi_rows + (warp - 2) * 128);              // [<= 4 chunks][32]
+            uint64_t* res_bar = reinterpret_cast<uint64_t*>(epi_rows + (warp - 2) * 128 + 64);   // [3]
             // the box covered by this warp's 32 rows
             const int r0 = q * 32;
             const int btn = r0 / pix_per_img;
@@ -311,43 +325,37 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             const int bth = brem / p.TW;
             const int btw = brem - bth * p.TW;
             const bool box_on = btn < p.TN;
+            const bool use_res = has_res && box_on;
+            const bool any = tile_begin < tile_end && ch_begin < ch_end;
 
-            auto setup_tile = [&](int tile, int buf) -> unsigned {
+            // residual box of chunk `ch` of work item `tile` -> staging tile b (elected lane)
+            auto load_res = [&](int tile, int ch, int b) {
                 int m_tile = m_tile_of(tile);
                 const int tw_i = m_tile % p.tiles_w;
                 m_tile /= p.tiles_w;
                 const int th_i = m_tile % p.tiles_h;
                 const int tn_i = m_tile / p.tiles_h;
-                const int n = tn_i * p.TN + tn, h = th_i * p.TH + th, w = tw_i * p.TW + tw;
-                const bool valid = (tn < p.TN) && (n < p.N) && (h < p.H) && (w < p.W);
-                row_tab[buf * 32 + lane] = valid ? (((long long)n * p.H + h) * p.W + w) * p.cout : 0;
-                const unsigned m = __ballot_sync(0xffffffffu, valid);
-                __syncwarp();
-                return m;
+                mbar_arrive_expect_tx(&res_bar[b], 4096u);
+                tma_load_4d(sbuf0 + b * 4096, &maps.res, &res_bar[b], (tile % p.num_n_tiles) * p.block_n + ch * 32,
+                            tw_i * p.TW + btw, th_i * p.TH + bth, tn_i * p.TN + btn);
             };
-            auto issue_res = [&](float (&dst)[32], int buf, unsigned vmask, int col) {
-                const unsigned okmask = (col < p.cout) ? vmask : 0u;
-                const float* base = resp + col;
-                const long long* rt = row_tab + buf * 32;
-#pragma unroll
-                for (int r = 0; r < 32; ++r) {
-                    float v = 0.f;
-                    if ((okmask >> r) & 1u) v = __ldg(base + rt[r]);
-                    dst[r] = v;
+            // position of the chunk two ahead of (tile, ch) in this warp's sequence
+            auto advance = [&](int& tile, int& ch) {
+                if (++ch == ch_end) { ch = ch_begin; ++tile; }
+            };
+            if (use_res && any) {
+                if (elect_one()) {
+                    int t1 = tile_begin, c1 = ch_begin;
+                    load_res(t1, c1, 0);
+                    advance(t1, c1);
+                    if (t1 < tile_end) load_res(t1, c1, 1);
                 }
-            };
-
-            float resn[32];
-#pragma unroll
-            for (int r = 0; r < 32; ++r) resn[r] = 0.f;
-            unsigned vmask_next = 0;
-            if (tile_begin < tile_end && ch_begin < ch_end) {
-                vmask_next = setup_tile(tile_begin, 0);
-                if (has_res) issue_res(resn, 0, vmask_next, (tile_begin % p.num_n_tiles) * p.block_n + ch_begin * 32 + lane);
+                __syncwarp();
             }
+            int ci = 0;                 // chunks processed by this warp
+            uint32_t res_phase = 0;     // bit b: parity of the next completion of res_bar[b]
+            int sb = 0;
             for (int tile = tile_begin; tile < tile_end; ++tile) {
-                const int buf = (tile - tile_begin) & 1;
-                const unsigned vmask = vmask_next;
                 const int col0 = (tile % p.num_n_tiles) * p.block_n;
                 int m_tile = m_tile_of(tile);
                 const int tw_i = m_tile % p.tiles_w;
@@ -355,78 +363,84 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                 const int th_i = m_tile % p.tiles_h;
                 const int tn_i = m_tile / p.tiles_h;
                 const int bn = tn_i * p.TN + btn, bh = th_i * p.TH + bth, bw = tw_i * p.TW + btw;
+                unsigned vmask = 0;
+                if (kStats) {
+                    const int n = tn_i * p.TN + tn, h = th_i * p.TH + th, w = tw_i * p.TW + tw;
+                    vmask = __ballot_sync(0xffffffffu, (tn < p.TN) && (n < p.N) && (h < p.H) && (w < p.W));
+                }
+                // this tile's bias values for this warp's chunks -> shared memory, while the MMAs of the tile still run
+                for (int ch = ch_begin; ch < ch_end; ++ch) {
+                    const int col = col0 + ch * 32 + lane;
+                    bias_s[(ch - ch_begin) * 32 + lane] = (p.bias != nullptr && col < p.cout) ? __ldg(p.bias + col) : 0.f;
+                }
+                __syncwarp();
 
                 mbar_wait(&tmem_full_bar[acc], acc_phase);
                 tc_fence_after();
                 if (kStats) mbar_wait(&stat_empty_bar[stat_buf], stat_phase ^ 1);   // part_smem buffer free
                 const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * p.acc_stride;
-                for (int ch = ch_begin; ch < ch_end; ++ch) {
-                    float res[32];
-#pragma unroll
-                    for (int r = 0; r < 32; ++r) res[r] = resn[r];
-                    // next chunk's residual (possibly the next tile's first chunk) goes out before this chunk is touched
-                    if (ch + 1 < ch_end) {
-                        if (has_res) issue_res(resn, buf, vmask, col0 + (ch + 1) * 32 + lane);
-                    } else if (tile + 1 < tile_end) {
-                        vmask_next = setup_tile(tile + 1, buf ^ 1);
-                        if (has_res)
-                            issue_res(resn, buf ^ 1, vmask_next, ((tile + 1) % p.num_n_tiles) * p.block_n + ch_begin * 32 + lane);
-                    }
+                for (int ch = ch_begin; ch < ch_end; ++ch, ++ci) {
                     const int c0 = col0 + ch * 32;
-                    // thread = row form of the bias (statistic-free, residual-free GEMMs): loaded while TMEM is read
-                    float4 bias4[8];
-                    if (!transposed) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            bias4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (p.bias != nullptr && c0 + 4 * j < p.cout) bias4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * j));
-                        }
-                    }
                     uint32_t racc[32];
                     tmem_ld32(t_row + ch * 32, racc);
-                    tmem_ld_wait();
-                    // the TMA store that last used this staging tile must have drained it
-                    uint8_t* sbuf = sbuf0 + sb * 4096;
-                    float* sf = reinterpret_cast<float*>(sbuf);
-                    if (elect_one()) {
-                        if (p.epi_bufs == 2) bulk_wait_read_1(); else bulk_wait_read_all();
-                    }
-                    __syncwarp();
-                    if (p.epi_bufs == 2) sb ^= 1;
-                    if (NDB_DBG_BIT(p, 8)) {
-                    } else if (!transposed) {
-                        // bias in thread = row form, straight into the staging tile
-                        if (p.out_kind == NDB_OUT_F32_NHWC) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 b4 = bias4[j];
-                                *reinterpret_cast<float4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                                    make_float4(__uint_as_float(racc[4 * j]) + b4.x, __uint_as_float(racc[4 * j + 1]) + b4.y,
-                                                __uint_as_float(racc[4 * j + 2]) + b4.z, __uint_as_float(racc[4 * j + 3]) + b4.w);
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float4 b0 = bias4[2 * j], b1 = bias4[2 * j + 1];
-                                const float v0 = __uint_as_float(racc[8 * j]) + b0.x, v1 = __uint_as_float(racc[8 * j + 1]) + b0.y;
-                                const float v2 = __uint_as_float(racc[8 * j + 2]) + b0.z, v3 = __uint_as_float(racc[8 * j + 3]) + b0.w;
-                                const float v4 = __uint_as_float(racc[8 * j + 4]) + b1.x, v5 = __uint_as_float(racc[8 * j + 5]) + b1.y;
-                                const float v6 = __uint_as_float(racc[8 * j + 6]) + b1.z, v7 = __uint_as_float(racc[8 * j + 7]) + b1.w;
-                                uint4 w4;
-                                if (p.fmt == 0) w4 = make_uint4(pack2<0>(v0, v1), pack2<0>(v2, v3), pack2<0>(v4, v5), pack2<0>(v6, v7));
-                                else w4 = make_uint4(pack2<1>(v0, v1), pack2<1>(v2, v3), pack2<1>(v4, v5), pack2<1>(v6, v7));
-                                // 64-byte rows, SWIZZLE_64B: 16-byte chunk index ^ bits [1,2] of the row
-                                *reinterpret_cast<uint4*>(sbuf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = w4;
-                            }
+                    int b;
+                    if (has_res) {
+                        b = ci % nbuf;
+                        if (use_res) {
+                            mbar_wait(&res_bar[b], (res_phase >> b) & 1u);    // the residual box is in the staging tile
+                            res_phase ^= 1u << b;
                         }
-                        if (kStats) {
-                            // statistics without a residual: the staged values are final, the lanes-along-channels pass only
-                            // READS them for the column sums (no write-back: less shared-memory traffic next to the MMAs)
-                            __syncwarp();
-                            const int col = c0 + lane;
-                            const unsigned okmask = (col < p.cout) ? vmask : 0u;
+                    } else {
+                        b = sb;
+                        // the TMA store that last used this staging tile must have drained it
+                        if (elect_one()) {
+                            if (nbuf == 2) bulk_wait_read_1(); else bulk_wait_read_all();
+                        }
+                        __syncwarp();
+                        if (nbuf == 2) sb ^= 1;
+                    }
+                    tmem_ld_wait();
+                    uint8_t* sbuf = sbuf0 + b * 4096;
+                    float* sf = reinterpret_cast<float*>(sbuf);
+                    const float4* bias4 = reinterpret_cast<const float4*>(bias_s + (ch - ch_begin) * 32);
+                    if (NDB_DBG_BIT(p, 8)) {
+                    } else if (p.out_kind == NDB_OUT_F32_NHWC) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b4 = bias4[j];
+                            float4* dst = reinterpret_cast<float4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4));
+                            float4 v = make_float4(__uint_as_float(racc[4 * j]) + b4.x, __uint_as_float(racc[4 * j + 1]) + b4.y,
+                                                   __uint_as_float(racc[4 * j + 2]) + b4.z, __uint_as_float(racc[4 * j + 3]) + b4.w);
+                            if (use_res) {
+                                const float4 rv = *dst;
+                                v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+                            }
+                            *dst = v;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 b0 = bias4[2 * j], b1 = bias4[2 * j + 1];
+                            const float v0 = __uint_as_float(racc[8 * j]) + b0.x, v1 = __uint_as_float(racc[8 * j + 1]) + b0.y;
+                            const float v2 = __uint_as_float(racc[8 * j + 2]) + b0.z, v3 = __uint_as_float(racc[8 * j + 3]) + b0.w;
+                            const float v4 = __uint_as_float(racc[8 * j + 4]) + b1.x, v5 = __uint_as_float(racc[8 * j + 5]) + b1.y;
+                            const float v6 = __uint_as_float(racc[8 * j + 6]) + b1.z, v7 = __uint_as_float(racc[8 * j + 7]) + b1.w;
+                            uint4 w4;
+                            if (p.fmt == 0) w4 = make_uint4(pack2<0>(v0, v1), pack2<0>(v2, v3), pack2<0>(v4, v5), pack2<0>(v6, v7));
+                            else w4 = make_uint4(pack2<1>(v0, v1), pack2<1>(v2, v3), pack2<1>(v4, v5), pack2<1>(v6, v7));
+                            // 64-byte rows, SWIZZLE_64B: 16-byte chunk index ^ bits [1,2] of the row
+                            *reinterpret_cast<uint4*>(sbuf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = w4;
+                        }
+                    }
+                    if (kStats) {
+                        // the staged values are final: a lanes-along-channels pass READS them for the column sums (for a
+                        // 16-bit output these are the sums of the ROUNDED values -- exactly what the consuming norm will read)
+                        __syncwarp();
+                        const int col = c0 + lane;
+                        const unsigned okmask = (col < p.cout) ? vmask : 0u;
+                        float cs = 0.f, css = 0.f;
+                        if (p.out_kind == NDB_OUT_F32_NHWC) {
                             const int lswz = lane >> 2, lw = lane & 3;
-                            float cs = 0.f, css = 0.f;
 #pragma unroll
                             for (int r = 0; r < 32; ++r) {
                                 const float t = sf[r * 32 + (((lswz ^ (r & 7)) << 2) | lw)];
@@ -434,44 +448,39 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                                 cs += v;
                                 css += v * v;
                             }
-                            part_smem[(stat_buf * 4 + q) * p.block_n + ch * 32 + lane] = make_float2(cs, css);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                                make_uint4(racc[4 * j], racc[4 * j + 1], racc[4 * j + 2], racc[4 * j + 3]);
-                        __syncwarp();
-                        // lanes along channels: bias + residual in place, column sums on the way
-                        const int col = c0 + lane;
-                        const bool colok = col < p.cout;
-                        const float bias_v = (colok && p.bias != nullptr) ? __ldg(p.bias + col) : 0.f;
-                        const int lswz = lane >> 2, lw = lane & 3;
-#pragma unroll
-                        for (int r = 0; r < 32; ++r) {
-                            const int idx = r * 32 + (((lswz ^ (r & 7)) << 2) | lw);
-                            const float v = sf[idx] + bias_v + res[r];
-                            sf[idx] = v;
-                            res[r] = v;
-                        }
-                        if (kStats) {
-                            const unsigned okmask = colok ? vmask : 0u;
-                            float cs = 0.f, css = 0.f;
+                        } else {
+                            const uint16_t* sh = reinterpret_cast<const uint16_t*>(sbuf);
+                            const int lchunk = lane >> 3, lw = lane & 7;
 #pragma unroll
                             for (int r = 0; r < 32; ++r) {
-                                const float v = ((okmask >> r) & 1u) ? res[r] : 0.f;
+                                const uint16_t bits = sh[r * 32 + (((lchunk ^ ((r >> 1) & 3)) << 3) | lw)];
+                                float t;
+                                if (p.fmt == 0) t = __half2float(__ushort_as_half(bits));
+                                else t = __bfloat162float(__ushort_as_bfloat16(bits));
+                                const float v = ((okmask >> r) & 1u) ? t : 0.f;
                                 cs += v;
                                 css += v * v;
                             }
-                            part_smem[(stat_buf * 4 + q) * p.block_n + ch * 32 + lane] = make_float2(cs, css);
                         }
+                        part_smem[(stat_buf * 4 + q) * p.block_n + ch * 32 + lane] = make_float2(cs, css);
                     }
                     fence_proxy_async();      // generic-proxy writes -> visible to the TMA engine
                     __syncwarp();
-                    if (box_on && !NDB_DBG_BIT(p, 4)) {
-                        if (elect_one()) {
+                    if (elect_one()) {
+                        if (box_on && !NDB_DBG_BIT(p, 4)) {
                             tma_store_4d(&maps.out, sbuf, c0, bw, bh, bn);
                             bulk_commit();
+                        }
+                        if (use_res) {
+                            // chunk i+2 goes into the tile chunk i-1 was stored from: all but the store just committed
+                            // must have finished reading shared memory
+                            int t2 = tile, c2 = ch;
+                            advance(t2, c2);
+                            advance(t2, c2);
+                            if (t2 < tile_end) {
+                                if (nbuf == 3) bulk_wait_read_1(); else bulk_wait_read_all();
+                                load_res(t2, c2, (ci + 2) % nbuf);
+                            }
                         }
                     }
                     __syncwarp();
@@ -956,7 +965,8 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
         const int box_w = a.TW < 32 ? a.TW : 32, box_h = 32 / box_w;
         const bool geom_ok = (a.TW % 32 == 0 || (32 % a.TW == 0 && a.TH % box_h == 0)) && (a.TH * a.TW) % 32 == 0;
         const bool kind_ok = prm->out_kind == NDB_OUT_F32_NHWC ||
-                             (prm->out_kind == NDB_OUT_F16_NHWC && !stats && a.res_mode == NDB_RES_NONE);
+                             (prm->out_kind == NDB_OUT_F16_NHWC && a.res_mode == NDB_RES_NONE);
+        (void)stats;
         const int es = prm->out_kind == NDB_OUT_F32_NHWC ? 4 : 2;
         a.epi_bulk = (!off && geom_ok && kind_ok && (a.res_mode == NDB_RES_NONE || a.res_mode == NDB_RES_SAME) &&
                       a.block_n % 32 == 0 && (prm->cout * es) % 16 == 0 && (reinterpret_cast<uintptr_t>(prm->out) & 15) == 0)
@@ -968,20 +978,34 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
             uint32_t box[4] = {32u, (uint32_t)box_w, (uint32_t)box_h, 1u};
             int rc = encode_tmap(&maps.out, prm->out, es, es == 4 ? 128 : 64, 4, dims, strides, box);
             if (rc != NDB_OK) return rc;
+            if (a.res_mode == NDB_RES_SAME) {
+                if ((reinterpret_cast<uintptr_t>(prm->residual) & 15) != 0) a.epi_bulk = 0;     // TMA needs 16-byte alignment
+                else {
+                    rc = encode_tmap(&maps.res, prm->residual, 4, 128, 4, dims, strides, box);
+                    if (rc != NDB_OK) return rc;
+                }
+            }
         }
     }
 
     const int stage_bytes = kATileBytes + a.b_rows * 128;
-    a.epi_bufs = (a.epi_bulk && a.total_kblocks <= 24) ? 2 : 1;
-    a.epi_region = a.epi_bufs == 2 ? kEpiWarps * 2 * 4096 : kEpiWarps * kStageFloats * (int)sizeof(float);
-    const int epi_bytes = a.epi_region + kEpiWarps * 128 * (int)sizeof(long long) +
-                          2 * 4 * a.block_n * (int)sizeof(float2) +
-                          (prm->stat_parts ? a.TN * prm->cout * (int)sizeof(float2) : 0);
-    // NDB_GEMM_SMEM_KB (A/B switch): cap this kernel's shared memory so that blocks of the NEXT kernel (programmatic
-    // dependent launch) can become resident next to a draining GEMM CTA
-    static int smem_cap_kb = -1;
-    if (smem_cap_kb < 0) { const char* e = std::getenv("NDB_GEMM_SMEM_KB"); smem_cap_kb = e ? std::atoi(e) : 227; }
-    const int smem_budget = smem_cap_kb * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - epi_bytes;
+    // staging tiles per epilogue warp. Residual ring: 3 deep when the epilogue is the critical path (short K) or when the
+    // operand pipeline still gets 5 stages next to it, else 2 (the smem goes to the pipeline: the step time is flat from 5
+    // stages up and drops below)
+    auto epi_bytes_for = [&](int bufs) {
+        const int region = bufs >= 2 ? kEpiWarps * bufs * 4096 : kEpiWarps * kStageFloats * (int)sizeof(float);
+        return region + kEpiWarps * 128 * (int)sizeof(long long) + 2 * 4 * a.block_n * (int)sizeof(float2) +
+               (prm->stat_parts ? a.TN * prm->cout * (int)sizeof(float2) : 0);
+    };
+    if (a.epi_bulk && a.res_mode == NDB_RES_SAME) {
+        const int stages3 = (227 * 1024 - 1024 - 256 - epi_bytes_for(3)) / stage_bytes;
+        a.epi_bufs = (a.total_kblocks <= 24 || stages3 >= 5) ? 3 : 2;
+    } else {
+        a.epi_bufs = (a.epi_bulk && a.total_kblocks <= 24) ? 2 : 1;
+    }
+    a.epi_region = a.epi_bufs >= 2 ? kEpiWarps * a.epi_bufs * 4096 : kEpiWarps * kStageFloats * (int)sizeof(float);
+    const int epi_bytes = epi_bytes_for(a.epi_bufs);
+    const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - epi_bytes;
     int stages = smem_budget / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages > a.total_kblocks) stages = a.total_kblocks < 2 ? 2 : a.total_kblocks;

@@ -601,3 +601,30 @@ def test_bf16_operand_format_unet_forward(cuda_dev):
     e_emu = float((emu - ref).abs().max() / ref.abs().max())
     print('bf16 forward err', e_ref, 'oracle-with-bf16-operands err', e_emu)
     assert e_ref < max(2e-2, 2.5 * e_emu)
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout', [(4, 32, 32, 128, 192), (5, 8, 8, 64, 256), (2, 64, 64, 64, 64), (3, 28, 28, 64, 128)])
+def test_conv_16bit_output_with_fused_statistics(cuda_dev, N, H, W, Cin, Cout):
+    """The ResBlock-internal tensor h may be stored in 16 bits (model.h_fp16): the epilogue's statistics are then the sums
+    of the ROUNDED values, i.e. exactly the statistics of the tensor the out_norm reads."""
+    ops, L = _ops()
+    g = torch.Generator(device='cpu').manual_seed(N * H + Cout)
+    x = torch.randn(N, Cin, H, W, generator=g).to(cuda_dev)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)).to(cuda_dev)
+    b = (0.5 * torch.randn(Cout, generator=g)).to(cuda_dev)
+    x16, wp = nhwc(x).half(), ops.pack_conv_weight(w)
+    st = ops.conv_stats_alloc(N, H, W, Cout, cuda_dev, Cin * 9)
+    st[0].fill_(float('nan'))
+    out = ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, stats=st, out_kind=L.OUT_F16_NHWC)
+    ref = F.conv2d(x.half().float(), w.half().float(), b, padding=1)
+    assert out.dtype == torch.float16 and rel_err(out.permute(0, 3, 1, 2), ref) < 1e-3
+    o = out.double().flatten(1, 2)
+    tot = ops.stats_totals(st)
+    assert torch.allclose(tot[:, :, 0], o.sum(1), rtol=1e-6, atol=1e-3)
+    assert torch.allclose(tot[:, :, 1], (o * o).sum(1), rtol=1e-6, atol=1e-3)
+    # the norm fed by the 16-bit tensor + these statistics == torch's GroupNorm of that tensor
+    gamma = (1 + 0.1 * torch.randn(Cout, generator=g)).to(cuda_dev)
+    beta = (0.1 * torch.randn(Cout, generator=g)).to(cuda_dev)
+    y = ops.gn_apply(out, st, gamma, beta, silu=True)
+    refn = F.silu(F.group_norm(out.float().permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-5))
+    assert rel_err(y.permute(0, 3, 1, 2), refn) < 2e-3
