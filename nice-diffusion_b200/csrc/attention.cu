@@ -54,7 +54,9 @@ __device__ __forceinline__ uint32_t pack2a(float a, float b) {
 }
 
 template <int FMT>
-// Two CTAs per SM (shared memory: 2 x ~114 KB); keep the register count under 65536 / (2 * 288) = 113.
+// Two CTAs per SM (shared memory: 2 x ~114 KB). Registers are allocated for an even number of warps, so the budget is
+// 65536 / (2 * 10 * 32) = 102 -> 96 registers per thread: at 111 (measured) only one CTA is resident and T = 1024 takes 145 us
+// instead of 108.
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -130,10 +132,12 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
             load_tile(sQ, q_full, cq, q0);
             load_tile(sK, &k_full[0], ck, 0);
             load_tile(sV, &v_full[0], cv, 0);
+            const bool two = p.kv_stages == 2;
+            if (two && nkv > 1) load_tile(sK + dpc * kChunkBytes, &k_full[1], ck, kAttnBN);
             mbar_wait(q_full, 0);
             auto issue_S = [&](int j) {      // S = Q K_j^T into TMEM (K tile j must have been requested)
-                const int st = (p.kv_stages == 2) ? (j & 1) : 0;
-                const uint32_t use_parity = (p.kv_stages == 2) ? ((j >> 1) & 1) : (j & 1);
+                const int st = two ? (j & 1) : 0;
+                const uint32_t use_parity = two ? ((j >> 1) & 1) : (j & 1);
                 mbar_wait(&k_full[st], use_parity);
                 tc_fence_after();
                 const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + st * dpc * kChunkBytes);
@@ -147,18 +151,23 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
                 __syncwarp();
             };
             issue_S(0);
+            // Double-buffered K / V with SEPARATE schedules: a K stage is free as soon as the S MMA that read it has
+            // completed (one block earlier than its V stage, which PV reads last), so K_{j+2} is requested right after
+            // S_{j+1} is issued -- a block and a half before S_{j+2} needs it -- and the S MMA never waits on a TMA round trip;
+            // V_{j+1} is requested when PV_{j-1} has retired, a full block before PV_{j+1}.
             for (int j = 0; j < nkv; ++j) {
-                const int st = (p.kv_stages == 2) ? (j & 1) : 0;
-                const uint32_t use_parity = (p.kv_stages == 2) ? ((j >> 1) & 1) : (j & 1);
-                if (j + 1 < nkv && p.kv_stages == 2) {
-                    // ---- prefetch K/V for block j+1 (its stage was last read by block j-1) ----
-                    const int st2 = (j + 1) & 1;
-                    if (j >= 1) mbar_wait(pv_done, (j - 1) & 1);
-                    load_tile(sK + st2 * dpc * kChunkBytes, &k_full[st2], ck, (j + 1) * kAttnBN);
-                    load_tile(sV + st2 * dpc * kChunkBytes, &v_full[st2], cv, (j + 1) * kAttnBN);
-                    // ---- S_{j+1} as soon as the softmax warps hold S_j in registers: it runs under their exp phase ----
+                const int st = two ? (j & 1) : 0;
+                const uint32_t use_parity = two ? ((j >> 1) & 1) : (j & 1);
+                if (two && j + 1 < nkv) {
+                    if (j >= 1) mbar_wait(pv_done, (j - 1) & 1);          // V stage (j+1)&1 was last read by PV_{j-1}
+                    load_tile(sV + ((j + 1) & 1) * dpc * kChunkBytes, &v_full[(j + 1) & 1], cv, (j + 1) * kAttnBN);
+                    // S_{j+1} as soon as the softmax threads hold S_j in registers: it runs under their exp phase
                     mbar_wait(s_free, j & 1);
                     issue_S(j + 1);
+                    if (j + 2 < nkv) {
+                        // K stage j&1 was read by S_j, complete since before s_free(j)
+                        load_tile(sK + (j & 1) * dpc * kChunkBytes, &k_full[j & 1], ck, (j + 2) * kAttnBN);
+                    }
                 }
                 // ---- O += P_j V_j ----
                 mbar_wait(p_full, j & 1);
@@ -177,7 +186,7 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
                     }
                     __syncwarp();
                 }
-                if (j + 1 < nkv && p.kv_stages == 1) {
+                if (j + 1 < nkv && !two) {
                     // single-buffered K/V (large head dims): reload only after both MMAs of block j retired
                     mbar_wait(pv_done, j & 1);
                     load_tile(sK, &k_full[0], ck, (j + 1) * kAttnBN);
@@ -202,26 +211,33 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
             else if (q == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
             else asm volatile("bar.sync 4, 64;" ::: "memory");
         };
+        // Lazy rescaling: the running shift m_run of a row only moves when the block maximum exceeds it by more than
+        // kLazy in the exp2 domain; until then p = exp2(s - m_run) may reach 2^kLazy (exact in fp32, representable in both
+        // 16-bit formats) and O / l keep accumulating against the same shift. The O correction (a TMEM round trip) then
+        // happens on the first block and almost never again, instead of on nearly every block of every warp.
+        constexpr float kLazy = 8.f;
+        const float lazy_raw = kLazy / p.scale_log2e;       // threshold in raw score units
         for (int j = 0; j < nkv; ++j) {
             mbar_wait(s_full, j & 1);
             tc_fence_after();
             const int kv_valid = p.T - j * kAttnBN - key0;  // this thread's keys >= kv_valid are padding
             const bool full = kv_valid >= 64;
             // pass 1: maximum over this thread's 64 keys (two 32-column TMEM reads; the scores are read again in pass 2 --
-            // holding all 64 in registers raises the register count past what two resident CTAs allow)
+            // holding all 64 in registers across the exchange / correction raises the register count past what two
+            // resident CTAs allow)
             float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
             for (int c0 = 0; c0 < 64; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem_S + lane_addr + key0 + c0, r);
+                uint32_t r1[32];
+                tmem_ld32(tmem_S + lane_addr + key0 + c0, r1);
                 tmem_ld_wait();
                 if (full) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[i]));
+                    for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r1[i]));
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        if (c0 + i < kv_valid) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[i]));
+                        if (c0 + i < kv_valid) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r1[i]));
                 }
             }
             // Both warps of a row must use the SAME block maximum. They exchange 16-bit values (the two-CTAs-per-SM shared
@@ -232,23 +248,25 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
             xchg[hf * 128 + row] = (uint16_t)(mu >> 16);
             pair_sync();
             const float m_blk = fmaxf(__uint_as_float(mu), __uint_as_float((uint32_t)xchg[(hf ^ 1) * 128 + row] << 16));
-            const float m_new = fmaxf(m_run, m_blk);
-            const float alpha = ex2_fast((m_run - m_new) * p.scale_log2e);  // 0 when m_run = -inf
-            const bool need_fix = (j > 0) && (m_new > m_run);
+            const bool move = m_blk > m_run + lazy_raw;        // always true on the first block (m_run = -inf)
+            const float m_new = move ? m_blk : m_run;
+            const float alpha = move ? ex2_fast((m_run - m_new) * p.scale_log2e) : 1.f;   // 0 when m_run = -inf
+            const bool need_fix = (j > 0) && move;
             // previous block's P V must have retired before P (smem) and O (TMEM) are touched
             if (j > 0) {
                 mbar_wait(pv_done, (j - 1) & 1);
                 tc_fence_after();
             }
             if (__any_sync(0xffffffffu, need_fix)) {
+                // rare: eight columns at a time, so that the 64 live scores are not spilled around it
 #pragma unroll 1
-                for (int c0 = hf * oc_half; c0 < (hf + 1) * oc_half; c0 += 32) {
-                    uint32_t o[32];
-                    tmem_ld32(tmem_O + lane_addr + c0, o);
+                for (int c0 = hf * oc_half; c0 < (hf + 1) * oc_half; c0 += 8) {
+                    uint32_t o[8];
+                    tmem_ld8(tmem_O + lane_addr + c0, o);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                    tmem_st32(tmem_O + lane_addr + c0, o);
+                    for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    tmem_st8(tmem_O + lane_addr + c0, o);
                 }
                 tmem_st_wait();
             }
@@ -260,14 +278,14 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
             float ls[4] = {0.f, 0.f, 0.f, 0.f};
             uint8_t* line = sP + hf * kChunkBytes + row * 128;
             // pass 2 pulls all 64 scores into registers and releases S at once, so the S_{j+1} MMA overlaps the exp phase.
-            // (Two copies of the exp loop: with the padding test folded in as predication every element pays three extra
-            //  issue slots even when the block is full -- the kernel is issue-bound.)
             uint32_t r[64];
             tmem_ld32(tmem_S + lane_addr + key0, r);
             tmem_ld32(tmem_S + lane_addr + key0 + 32, r + 32);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(s_free);
+            // (Two copies of the exp loop: with the padding test folded in as predication every element pays three extra
+            //  issue slots even when the block is full -- the kernel is issue-bound.)
             if (full) {
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
