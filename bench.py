@@ -289,6 +289,9 @@ def main():
     ap.add_argument('--batch', type=int, default=None, help='per-GPU batch (default: the BASELINE value)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--eager', action='store_true', help='launch kernels one by one instead of replaying CUDA graphs (profiling)')
+    ap.add_argument('--operands', type=str, default='fp16', choices=['fp16', 'fp32x'],
+                    help="tensor-core operand mode: fp16 (default, 2e-3 class) or fp32x = fp32-class (three fp16 products per "
+                         "multiply, chunked accumulation; 1e-5 class)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-gpu-reference', action='store_true', help='skip the informational eager-reference-on-GPU leg')
     args = ap.parse_args()
@@ -350,6 +353,11 @@ def main():
     model = DiffusionModel(**model_config(args.config))
     randomize_zero_init_(model, seed=0)
     model = model.to(dev).eval()
+    if args.operands == 'fp32x':
+        from nice_diffusion_b200 import _lib as _L
+        model.operand_format = _L.FMT_FP32X
+        config['operands'] = 'fp32-class: fp16 (hi, lo) operand pairs, three tensor-core products per multiply, K accumulated ' \
+                             'in 128-element chunks added in fp32 round-to-nearest, fp32 residual stream'
     model.use_cuda_graph = not args.eager
     diff = Diffusion(model=model, device=dev, **dkw)
     diff.noise, diff.seed = 'philox', 1234
@@ -483,7 +491,8 @@ def main():
 
     line = {'metric': metric, 'value': value, 'unit': 'images/sec', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'fp16', 'data': 'synthetic', 'config': config, 'clocks': clk,
+            'vs_baseline': None, 'dtype': 'fp16' if args.operands == 'fp16' else 'fp32x', 'data': 'synthetic', 'config': config,
+            'clocks': clk,
             'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
             'gpu_eager_reference': gpu_ref}
     _emit(line)

@@ -83,17 +83,27 @@ typedef struct {
                                 consumer (ndb_gn_apply) adds the slots in order: deterministic, no atomics, no fences,
                                 no extra pass over the tensor. NULL = off. */
     int32_t stat_smax;       /* slots per image, must equal ndb_conv_stats_layout(...) */
+    float out_scale;         /* the accumulators are multiplied by this before bias / residual; 0 = 1. The fp32-class mode packs
+                                its weights times 2^8 (so that the low halves stay normal fp16 numbers) and passes 2^-8 here;
+                                powers of two are exact */
+    int32_t acc_chunk_kblocks; /* 0 = one accumulation over the whole K range. > 0 (fp32-class mode): the tensor core's fp32
+                                accumulation truncates (measured: -5e-9 relative per element of K), so K is accumulated in chunks
+                                of this many 64-element blocks, each from a zeroed TMEM accumulator, and the chunks are added with
+                                round-to-nearest adds in the epilogue warps' registers. Limits BLOCK_N to 192. */
 } ndb_conv_params;
 
 int ndb_conv_gemm(const ndb_conv_params* p, void* stream);
 /* Returns stat_smax for this geometry and fills counts[N] (HOST pointer) with the slots written per image. */
-int ndb_conv_stats_layout(int N, int H, int W, int cout_pad, int block_n, int k_total, int32_t* counts);
+int ndb_conv_stats_layout(int N, int H, int W, int cout_pad, int block_n, int k_total, int acc_chunk_kblocks,
+                          int32_t* counts);
 int ndb_conv_stats_supported(int N, int H, int W);   /* 1 if stat_parts is available for this geometry */
 
 /* OIHW fp32 (nn.Conv2d / Conv1d / Linear weight, kernel 1 or 3) -> [taps][cout_pad][cin] 16-bit, rows >= cout zero.
- * `cin_off`/`cin_len` select an input-channel range (used to split a weight over concat segments). */
+ * `cin_off`/`cin_len` select an input-channel range (used to split a weight over concat segments).
+ * The stored value is the 16-bit rounding of w * scale (scale 0 = 1; part 0), or -- part 1, fp16 only -- the fp16 rounding of
+ * the remainder w * scale - part0: the (hi, lo) weight pair of the fp32-class mode. */
 int ndb_pack_conv_weight(const float* w_oihw, void* dst, int cout, int cin_total, int ksize, int cout_pad,
-                         int cin_off, int cin_len, int operand_format, void* stream);
+                         int cin_off, int cin_len, int operand_format, float scale, int part, void* stream);
 
 /* ---- GroupNorm(32) statistics + apply ------------------------------------------------------------------
  * Replaces nn.GroupNorm(32, C, eps=1e-5) + SiLU + AdaGN scale/shift + h_resample + torch.cat
@@ -140,6 +150,9 @@ typedef struct {
                                           epilogue as a plain residual */
     int32_t operand_format;
     float eps;
+    void* out_lo; void* raw_lo;        /* fp32-class mode (operand_format 0, fp32 input): when out_lo != NULL every result v is
+                                          stored as the fp16 pair out = fp16(v), out_lo = fp16(v - out) (same for raw16 /
+                                          raw_lo), and SiLU is evaluated with an accurate exponential and a true division */
     int32_t cpg;                       /* channels per group; 0 = (C0 + C1) / 32. Non-zero: this call normalises a channel SLICE
                                           of a wider GroupNorm(32) input (the skip half of a concatenated tensor) whose groups
                                           do not straddle the slice: (C0 + C1) / cpg <= 32 groups, gamma / beta already offset */
@@ -153,6 +166,10 @@ int ndb_gn_apply(const ndb_gn_apply_params* p, void* stream);
  * order 0: channels laid out [3][heads][d] (split_qkv_first=True); order 1: [heads][3][d] (legacy). */
 int ndb_attention(const void* qkv, void* out, int B, int T, int heads, int d, int order, int operand_format,
                   void* stream);
+/* fp32-class variant (head dim <= 64): q, k, v as fp16 (hi, lo) pairs in two tensors of that layout (ndb_split16 of the fp32
+ * qkv GEMM output), every product evaluated as hi*hi + lo*hi + hi*lo, probabilities split the same way; out: fp32 [B][T][C]. */
+int ndb_attention_split(const void* qkv_hi, const void* qkv_lo, float* out, int B, int T, int heads, int d, int order,
+                        void* stream);
 
 /* ---- timestep / class embedding front end ------------------------------------------------------------------
  * Replaces timestep_embedding + step_embed MLP + class_embedding add + the SiLU in front of every
@@ -181,6 +198,9 @@ int ndb_stem_im2col(const float* x_nchw, void* out, int N, int Cin, int H, int W
 /* generic fp32 NHWC resample (standalone Upsample / Downsample without conv, model.py:77,111) and layout casts */
 int ndb_resample_f32(const float* x, float* out, int N, int H, int W, int C, int mode, void* stream);
 int ndb_cast_nhwc16(const float* x, void* out, int64_t numel, int operand_format, void* stream);
+/* fp32 -> fp16 pair (hi, lo), hi + lo == x to ~2^-22 relative: the activation operands of the fp32-class mode. silu != 0
+ * applies SiLU (accurate expf) first (the step-embedding activation, model.py:197). numel % 4 == 0. */
+int ndb_split16(const float* x, void* hi, void* lo, int64_t numel, int silu, void* stream);
 /* strided conv3x3 s2 p1 input gather for Downsample(with_conv) (model.py:103-105): builds the 9-tap
  * tap-major operand [9][N,Ho,Wo,C] (Ho=(H-1)/2+1) so the GEMM runs it as nine 1x1 K-segments. */
 int ndb_im2col_s2(const float* x, void* out, int N, int H, int W, int C, int operand_format, void* stream);

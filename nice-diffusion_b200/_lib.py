@@ -22,6 +22,11 @@ VAR_FIXED, VAR_LEARNED, VAR_LEARNED_INTERP = 0, 1, 2
  TAB_LOGVAR_MAX, TAB_ABAR, TAB_ABAR_PREV, TAB_SQRT_1M_ABAR, TAB_COUNT) = range(10)
 
 FMT_FP16, FMT_BF16 = 0, 1
+# fp32-class mode of the model (DiffusionModel.operand_format): every tensor-core operand is an fp16 (hi, lo) pair and every
+# product is evaluated as hi*hi + lo*hi + hi*lo; the kernels themselves run in FMT_FP16
+FMT_FP32X = 2
+SPLIT_ACC_CHUNK = 2           # K blocks per tensor-core accumulation chunk in the fp32-class mode (8 MMA steps)
+SPLIT_WEIGHT_SCALE = 256.0   # weights are packed times 2^8 so that their low halves stay normal fp16 numbers
 
 
 class ConvSegment(C.Structure):
@@ -36,7 +41,7 @@ class ConvParams(C.Structure):
                 ('residual_mode', C.c_int32), ('out_kind', C.c_int32),
                 ('out', C.c_void_p),
                 ('operand_format', C.c_int32), ('block_n', C.c_int32),
-                ('stat_parts', C.c_void_p), ('stat_smax', C.c_int32)]
+                ('stat_parts', C.c_void_p), ('stat_smax', C.c_int32), ('out_scale', C.c_float), ('acc_chunk_kblocks', C.c_int32)]
 
 
 class GnApplyParams(C.Structure):
@@ -50,7 +55,8 @@ class GnApplyParams(C.Structure):
                 ('pre_add', C.c_void_p), ('ld_pre', C.c_int32),
                 ('silu', C.c_int32), ('resample', C.c_int32),
                 ('out', C.c_void_p), ('raw16', C.c_void_p), ('x0_is16', C.c_int32), ('pool32', C.c_void_p),
-                ('operand_format', C.c_int32), ('eps', C.c_float), ('cpg', C.c_int32)]
+                ('operand_format', C.c_int32), ('eps', C.c_float), ('out_lo', C.c_void_p), ('raw_lo', C.c_void_p),
+                ('cpg', C.c_int32)]
 
 
 class StepParams(C.Structure):
@@ -72,13 +78,15 @@ SIGNATURES = {
     'ndb_device_supported': (_I, []),
     'ndb_last_error': (C.c_char_p, []),
     'ndb_conv_gemm': (_I, [C.POINTER(ConvParams), _P]),
-    'ndb_conv_stats_layout': (_I, [_I, _I, _I, _I, _I, _I, _P]),
+    'ndb_conv_stats_layout': (_I, [_I, _I, _I, _I, _I, _I, _I, _P]),
     'ndb_conv_stats_supported': (_I, [_I, _I, _I]),
-    'ndb_pack_conv_weight': (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'ndb_pack_conv_weight': (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, C.c_float, _I, _P]),
+    'ndb_split16': (_I, [_P, _P, _P, _I64, _I, _P]),
     'ndb_gn_stats': (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P, _P]),
     'ndb_gn_stats_workspace_bytes': (_I64, [_I, _I, _I]),
     'ndb_gn_apply': (_I, [C.POINTER(GnApplyParams), _P]),
     'ndb_attention': (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    'ndb_attention_split': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     'ndb_embed': (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     'ndb_stem_conv': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     'ndb_resample_f32': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),

@@ -53,12 +53,15 @@ __device__ __forceinline__ uint32_t pack2a(float a, float b) {
     }
 }
 
-template <int FMT>
+// SPLIT (fp32-class mode, head dim <= 64): q, k, v arrive as fp16 (hi, lo) pairs in two tensors of the same layout and every
+// product runs as three MMAs (hi hi + lo hi + hi lo); P is written as a (hi, lo) pair too; the output is fp32. One CTA per
+// SM (160 KB of operand tiles), single-buffered K / V.
+template <int FMT, bool SPLIT>
 // Two CTAs per SM (shared memory: 2 x ~114 KB). Registers are allocated for an even number of warps, so the budget is
 // 65536 / (2 * 10 * 32) = 102 -> 96 registers per thread: at 111 (measured) only one CTA is resident and T = 1024 takes 145 us
 // instead of 108.
-__global__ void __launch_bounds__(kAttnThreads, 2)
-attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) {
+__global__ void __launch_bounds__(kAttnThreads, SPLIT ? 1 : 2)
+attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__ CUtensorMap qkv_lo_map, const AttnArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0u) __trap();
 
@@ -70,11 +73,13 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
     const int Dp = dpc * 64;
 
     // smem carve-up
-    uint8_t* sQ = smem;                                   // dpc chunks
-    uint8_t* sK = sQ + dpc * kChunkBytes;                 // kv_stages * dpc chunks
-    uint8_t* sV = sK + p.kv_stages * dpc * kChunkBytes;   // kv_stages * dpc chunks
-    uint8_t* sP = sV + p.kv_stages * dpc * kChunkBytes;   // 2 chunks (128 keys)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kChunkBytes);
+    // SPLIT: every tile is followed by its "lo" twin (kv_stages == 1)
+    constexpr int kTw = SPLIT ? 2 : 1;
+    uint8_t* sQ = smem;                                         // dpc chunks (x kTw)
+    uint8_t* sK = sQ + kTw * dpc * kChunkBytes;                 // kv_stages * dpc chunks (x kTw)
+    uint8_t* sV = sK + kTw * p.kv_stages * dpc * kChunkBytes;   // kv_stages * dpc chunks (x kTw)
+    uint8_t* sP = sV + kTw * p.kv_stages * dpc * kChunkBytes;   // 2 chunks (128 keys) (x kTw)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kTw * 2 * kChunkBytes);
     uint64_t* q_full = bars + 0;
     uint64_t* k_full = bars + 1;   // [2]
     uint64_t* v_full = bars + 3;   // [2]
@@ -87,6 +92,7 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
 
     if (threadIdx.x == 256) {
         prefetch_tmap(&qkv_map);
+        if (SPLIT) prefetch_tmap(&qkv_lo_map);
         mbar_init(q_full, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&k_full[i], 1);
@@ -121,11 +127,14 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
         // descriptor operands stay in uniform registers (no per-instruction R2UR waterfall).
         {
             const uint32_t tile_bytes = (uint32_t)dpc * kChunkBytes;
+            const uint32_t lo_off = (uint32_t)dpc * kChunkBytes;      // SPLIT: the lo twin sits right behind its hi tile
             auto load_tile = [&](uint8_t* dst, uint64_t* bar, int colblk, int row0) {
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(bar, tile_bytes);
-                    for (int c = 0; c < dpc; ++c)
+                    mbar_arrive_expect_tx(bar, kTw * tile_bytes);
+                    for (int c = 0; c < dpc; ++c) {
                         tma_load_4d(dst + c * kChunkBytes, &qkv_map, bar, c * 64, colblk, row0, b);
+                        if (SPLIT) tma_load_4d(dst + lo_off + c * kChunkBytes, &qkv_lo_map, bar, c * 64, colblk, row0, b);
+                    }
                 }
                 __syncwarp();
             };
@@ -133,18 +142,23 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
             load_tile(sK, &k_full[0], ck, 0);
             load_tile(sV, &v_full[0], cv, 0);
             const bool two = p.kv_stages == 2;
-            if (two && nkv > 1) load_tile(sK + dpc * kChunkBytes, &k_full[1], ck, kAttnBN);
+            if (two && nkv > 1) load_tile(sK + kTw * dpc * kChunkBytes, &k_full[1], ck, kAttnBN);
             mbar_wait(q_full, 0);
             auto issue_S = [&](int j) {      // S = Q K_j^T into TMEM (K tile j must have been requested)
                 const int st = two ? (j & 1) : 0;
                 const uint32_t use_parity = two ? ((j >> 1) & 1) : (j & 1);
                 mbar_wait(&k_full[st], use_parity);
                 tc_fence_after();
-                const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + st * dpc * kChunkBytes);
+                const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + kTw * st * dpc * kChunkBytes);
                 if (elect_one()) {
-                    for (int i = 0; i < Dp / 16; ++i) {
-                        const uint32_t off = (i >> 2) * kChunkBytes + (i & 3) * 32;
-                        umma_f16(tmem_S, make_desc_k_sw128(qa + off), make_desc_k_sw128(ka + off), p.idesc_qk, i ? 1u : 0u);
+                    // SPLIT: q_hi k_hi + q_lo k_hi + q_hi k_lo
+                    for (int pass = 0; pass < (SPLIT ? 3 : 1); ++pass) {
+                        const uint32_t qo = (pass == 1) ? lo_off : 0u, ko = (pass == 2) ? lo_off : 0u;
+                        for (int i = 0; i < Dp / 16; ++i) {
+                            const uint32_t off = (i >> 2) * kChunkBytes + (i & 3) * 32;
+                            umma_f16(tmem_S, make_desc_k_sw128(qa + qo + off), make_desc_k_sw128(ka + ko + off), p.idesc_qk,
+                                     (pass | i) ? 1u : 0u);
+                        }
                     }
                     umma_commit(s_full);
                 }
@@ -160,13 +174,13 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
                 const uint32_t use_parity = two ? ((j >> 1) & 1) : (j & 1);
                 if (two && j + 1 < nkv) {
                     if (j >= 1) mbar_wait(pv_done, (j - 1) & 1);          // V stage (j+1)&1 was last read by PV_{j-1}
-                    load_tile(sV + ((j + 1) & 1) * dpc * kChunkBytes, &v_full[(j + 1) & 1], cv, (j + 1) * kAttnBN);
+                    load_tile(sV + kTw * ((j + 1) & 1) * dpc * kChunkBytes, &v_full[(j + 1) & 1], cv, (j + 1) * kAttnBN);
                     // S_{j+1} as soon as the softmax threads hold S_j in registers: it runs under their exp phase
                     mbar_wait(s_free, j & 1);
                     issue_S(j + 1);
                     if (j + 2 < nkv) {
                         // K stage j&1 was read by S_j, complete since before s_free(j)
-                        load_tile(sK + (j & 1) * dpc * kChunkBytes, &k_full[j & 1], ck, (j + 2) * kAttnBN);
+                        load_tile(sK + kTw * (j & 1) * dpc * kChunkBytes, &k_full[j & 1], ck, (j + 2) * kAttnBN);
                     }
                 }
                 // ---- O += P_j V_j ----
@@ -174,13 +188,17 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
                 mbar_wait(&v_full[st], use_parity);
                 tc_fence_after();
                 {
-                    const uint32_t pa = smem_u32(sP), va = smem_u32(sV + st * dpc * kChunkBytes);
+                    const uint32_t pa = smem_u32(sP), va = smem_u32(sV + kTw * st * dpc * kChunkBytes);
                     if (elect_one()) {
-                        for (int i = 0; i < kAttnBN / 16; ++i) {
-                            const uint64_t adesc = make_desc_k_sw128(pa + (i >> 2) * kChunkBytes + (i & 3) * 32);
-                            // V tile: rows = keys (K dim), 64 d-elements contiguous per row (MN-major), 16 keys = 2048 B
-                            const uint64_t bdesc = make_desc_mn_sw128(va + i * 2048, kChunkBytes);
-                            umma_f16(tmem_O, adesc, bdesc, p.idesc_pv, (j | i) ? 1u : 0u);
+                        // SPLIT: p_hi v_hi + p_lo v_hi + p_hi v_lo
+                        for (int pass = 0; pass < (SPLIT ? 3 : 1); ++pass) {
+                            const uint32_t po = (pass == 1) ? 2u * kChunkBytes : 0u, vo = (pass == 2) ? lo_off : 0u;
+                            for (int i = 0; i < kAttnBN / 16; ++i) {
+                                const uint64_t adesc = make_desc_k_sw128(pa + po + (i >> 2) * kChunkBytes + (i & 3) * 32);
+                                // V tile: rows = keys (K dim), 64 d-elements contiguous per row (MN-major), 16 keys = 2048 B
+                                const uint64_t bdesc = make_desc_mn_sw128(va + vo + i * 2048, kChunkBytes);
+                                umma_f16(tmem_O, adesc, bdesc, p.idesc_pv, (j | pass | i) ? 1u : 0u);
+                            }
                         }
                         umma_commit(pv_done);
                     }
@@ -289,7 +307,7 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
             if (full) {
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    uint32_t pk[4];
+                    uint32_t pk[4], pl[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int i = c * 8 + 2 * k;
@@ -297,13 +315,19 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
                         const float p1 = ex2_fast(fmaf(__uint_as_float(r[i + 1]), p.scale_log2e, -mb));
                         ls[k] += p0 + p1;
                         pk[k] = pack2a<FMT>(p0, p1);
+                        if (SPLIT) {
+                            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&pk[k]));
+                            pl[k] = pack2a<0>(p0 - hf.x, p1 - hf.y);
+                        }
                     }
                     *reinterpret_cast<uint4*>(line + ((c ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    if (SPLIT)
+                        *reinterpret_cast<uint4*>(line + 2 * kChunkBytes + ((c ^ (row & 7)) << 4)) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                 }
             } else {
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    uint32_t pk[4];
+                    uint32_t pk[4], pl[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int i = c * 8 + 2 * k;
@@ -313,8 +337,14 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
                         if (i + 1 >= kv_valid) p1 = 0.f;
                         ls[k] += p0 + p1;
                         pk[k] = pack2a<FMT>(p0, p1);
+                        if (SPLIT) {
+                            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&pk[k]));
+                            pl[k] = pack2a<0>(p0 - hf.x, p1 - hf.y);
+                        }
                     }
                     *reinterpret_cast<uint4*>(line + ((c ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    if (SPLIT)
+                        *reinterpret_cast<uint4*>(line + 2 * kChunkBytes + ((c ^ (row & 7)) << 4)) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                 }
             }
             l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
@@ -331,12 +361,22 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
         const float inv_l = 1.f / (lx[row] + lx[128 + row]);
         const int qrow = q0 + row;
         uint16_t* orow = p.out + ((size_t)b * p.T + qrow) * p.C + (size_t)h * p.d;
+        float* orow32 = reinterpret_cast<float*>(p.out) + ((size_t)b * p.T + qrow) * p.C + (size_t)h * p.d;   // SPLIT: fp32 output
 #pragma unroll 1
         for (int c0 = hf * oc_half; c0 < (hf + 1) * oc_half; c0 += 32) {
             uint32_t o[32];
             tmem_ld32(tmem_O + lane_addr + c0, o);
             tmem_ld_wait();
-            if (qrow < p.T) {
+            if (SPLIT) {
+                if (qrow < p.T) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        if (c0 + i + 4 <= p.d)
+                            *reinterpret_cast<float4*>(orow32 + c0 + i) =
+                                make_float4(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l,
+                                            __uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+                }
+            } else if (qrow < p.T) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 8) {
                     if (c0 + i + 8 <= p.d) {
@@ -363,23 +403,32 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const AttnArgs p) 
 
 using namespace ndb;
 
-extern "C" int ndb_attention(const void* qkv, void* out, int B, int T, int heads, int d, int order, int operand_format,
-                             void* stream) {
+static int launch_attention(const void* qkv, const void* qkv_lo, void* out, int B, int T, int heads, int d, int order,
+                            int operand_format, void* stream) {
     NDB_CHECK_ARG(qkv && out && B > 0 && T > 0 && heads > 0);
     NDB_CHECK_ARG(d % 8 == 0 && d >= 8 && d <= 256);
     NDB_CHECK_ARG(order == 0 || order == 1);
     NDB_CHECK_ARG(operand_format == 0 || operand_format == 1);
+    const bool split = qkv_lo != nullptr;
+    if (split) {
+        NDB_CHECK_ARG(operand_format == 0);
+        if (d > 64) {
+            std::fprintf(stderr, "[ndb200] fp32-class attention supports head dims up to 64 (got %d)\n", d);
+            return NDB_ERR_UNSUPPORTED;
+        }
+    }
     const int C = heads * d;
     AttnArgs a{};
     a.B = B; a.T = T; a.heads = heads; a.d = d; a.order = order;
     a.dp_chunks = (d + 63) / 64;
     const int Dp = a.dp_chunks * 64;
-    a.kv_stages = (a.dp_chunks <= 2) ? 2 : 1;
-    // smem: Q + kv_stages*(K+V) + P(2 chunks) + barriers
-    size_t smem = (size_t)(a.dp_chunks * (1 + 2 * a.kv_stages) + 2) * kChunkBytes + 640;
+    const int tw = split ? 2 : 1;
+    a.kv_stages = (a.dp_chunks <= 2 && !split) ? 2 : 1;
+    // smem: Q + kv_stages*(K+V) + P(2 chunks) (all doubled in split mode) + barriers
+    size_t smem = (size_t)tw * (a.dp_chunks * (1 + 2 * a.kv_stages) + 2) * kChunkBytes + 640;
     if (smem > 227 * 1024) {
         a.kv_stages = 1;
-        smem = (size_t)(a.dp_chunks * 3 + 2) * kChunkBytes + 640;
+        smem = (size_t)tw * (a.dp_chunks * 3 + 2) * kChunkBytes + 640;
     }
     NDB_CHECK_ARG(smem <= 227 * 1024);
     a.fmt = operand_format;
@@ -391,7 +440,7 @@ extern "C" int ndb_attention(const void* qkv, void* out, int B, int T, int heads
     a.out = (uint16_t*)out;
     a.C = C;
 
-    CUtensorMap map;
+    CUtensorMap map, map_lo;
     {
         // view [B][T][3*heads][d]
         uint64_t dims[4] = {(uint64_t)d, (uint64_t)(3 * heads), (uint64_t)T, (uint64_t)B};
@@ -399,17 +448,33 @@ extern "C" int ndb_attention(const void* qkv, void* out, int B, int T, int heads
         uint32_t box[4] = {64u, 1u, (uint32_t)kAttnBM, 1u};
         int rc = encode_tmap_16bit(&map, qkv, 4, dims, strides, box);
         if (rc != NDB_OK) return rc;
+        rc = encode_tmap_16bit(&map_lo, split ? qkv_lo : qkv, 4, dims, strides, box);
+        if (rc != NDB_OK) return rc;
     }
     static PerDeviceOnce attr_once;
     if (attr_once.pending()) {
-        cudaFuncSetAttribute(attention_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attention_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attention_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attention_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_once.done();
     }
     dim3 grid((T + kAttnBM - 1) / kAttnBM, heads, B);
-    if (operand_format == 0)
-        launch_kernel(attention_kernel<0>, grid, dim3(kAttnThreads), smem, (cudaStream_t)stream, 1, map, a);
+    if (split)
+        launch_kernel(attention_kernel<0, true>, grid, dim3(kAttnThreads), smem, (cudaStream_t)stream, 1, map, map_lo, a);
+    else if (operand_format == 0)
+        launch_kernel(attention_kernel<0, false>, grid, dim3(kAttnThreads), smem, (cudaStream_t)stream, 1, map, map_lo, a);
     else
-        launch_kernel(attention_kernel<1>, grid, dim3(kAttnThreads), smem, (cudaStream_t)stream, 1, map, a);
+        launch_kernel(attention_kernel<1, false>, grid, dim3(kAttnThreads), smem, (cudaStream_t)stream, 1, map, map_lo, a);
     return launch_status("ndb_attention");
+}
+
+extern "C" int ndb_attention(const void* qkv, void* out, int B, int T, int heads, int d, int order, int operand_format,
+                             void* stream) {
+    return launch_attention(qkv, nullptr, out, B, T, heads, d, order, operand_format, stream);
+}
+
+extern "C" int ndb_attention_split(const void* qkv_hi, const void* qkv_lo, float* out, int B, int T, int heads, int d, int order,
+                                   void* stream) {
+    NDB_CHECK_ARG(qkv_lo != nullptr);
+    return launch_attention(qkv_hi, qkv_lo, out, B, T, heads, d, order, 0, stream);
 }

@@ -72,6 +72,8 @@ struct ConvArgs {
     int out_kind;
     void* out;
     int fmt;
+    float out_scale;           // accumulators are multiplied by this (a power of two: exact) before bias / residual
+    int acc_chunk;             // kChunk kernels: K blocks per accumulation chunk
     // fused GroupNorm statistics: per (image, CTA slot, channel) partial (sum, sum of squares) of the stored output
     float2* stat_parts;        // [N][stat_smax][cout] or nullptr
     int stat_smax;             // partial slots per image
@@ -110,7 +112,11 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // 256 x BLOCK_N tcgen05.mma issued by the leader; each CTA stages its own A tile and only HALF of the weight tile, which
 // halves the B traffic per SM (L2 -> smem writes and smem -> tensor-core reads) -- the single-CTA kernel is shared-memory
 // bandwidth bound at ~55 % tensor utilisation.
-template <bool kStats, bool k2>
+// kChunk (fp32-class mode): the tensor core accumulates in fp32 with TRUNCATION -- measured on B200: the result shrinks by
+// 5.05e-9 per element of K, -7e-5 relative at K = 13824 -- so the K range is cut into chunks of p.acc_chunk K blocks; every
+// chunk starts from a zeroed accumulator (the two TMEM stages alternate) and the epilogue warps add the finished chunks into
+// registers with ordinary round-to-nearest adds while the next chunk is being multiplied. BLOCK_N <= 192 (3 x 32 registers).
+template <bool kStats, bool k2, bool kChunk = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -241,13 +247,16 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             constexpr uint64_t kDescHi = (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61) | (uint64_t(1) << 16);
             const uint32_t desc_lo0 = (smem_u32(smem) & 0x3FFFF) >> 4;
             const uint32_t desc_step = (uint32_t)stage_bytes >> 4;
-            for (int tile = tile_begin; tile < tile_end; ++tile) {
+            const int chunk_kb = kChunk ? p.acc_chunk : p.total_kblocks;
+            for (int tile = tile_begin; tile < tile_end; ++tile)
+            for (int kb0 = 0; kb0 < p.total_kblocks; kb0 += chunk_kb) {
+                const int kb1 = (kb0 + chunk_kb < p.total_kblocks) ? kb0 + chunk_kb : p.total_kblocks;
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
                 // The issue loop is the critical path for narrow N tiles (4 MMAs of 48..96 cycles per K block): the operand
                 // descriptors advance by one multiply-add per stage.
-                for (int kb = 0; kb < p.total_kblocks; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t a_lo = desc_lo0 + (uint32_t)stage * desc_step;
@@ -258,8 +267,8 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                         for (int k = 0; k < kBlockK / 16; ++k) {
                             if (NDB_DBG_BIT(p, 2)) break;
                             // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
-                            if (k2) umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
-                            else umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) ? 1u : 0u);
+                            if (k2) umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, ((kb - kb0) | k) ? 1u : 0u);
+                            else umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, ((kb - kb0) | k) ? 1u : 0u);
                         }
                         // frees the smem slot (in both CTAs of a pair) once these MMAs retire
                         if (k2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
@@ -300,6 +309,51 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
         const int rem = row - tn * pix_per_img;
         const int th = rem / p.TW;
         const int tw = rem - th * p.TW;
+        // kChunk: running sums of this warp's (<= 3) column chunks; all chunks of a tile but the last are drained here
+        float csum[kChunk ? 3 : 1][32];
+        const int n_acc_chunks = kChunk ? (p.total_kblocks + p.acc_chunk - 1) / p.acc_chunk : 1;
+        auto drain_chunks = [&]() {
+            if (!kChunk) return;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) csum[c][i] = 0.f;
+            for (int cc = 0; cc + 1 < n_acc_chunks; ++cc) {
+                mbar_wait(&tmem_full_bar[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * p.acc_stride;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    if (ch_begin + c < ch_end) {
+                        uint32_t v[32];
+                        tmem_ld32(t_row + (ch_begin + c) * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) csum[c][i] += __uint_as_float(v[i]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (k2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
+                    else mbar_arrive(&tmem_empty_bar[acc]);
+                }
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        };
+        // adds the running sum of column chunk `ch` to the last chunk's accumulator values
+        auto add_csum = [&](uint32_t (&racc)[32], int ch) {
+            if (!kChunk) return;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                if (ch - ch_begin == c) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) racc[i] = __float_as_uint(__uint_as_float(racc[i]) + csum[c][i]);
+                }
+        };
         if (p.epi_bulk) {
             // ------------------------------------------------------------------------------------------------
             // bulk path
@@ -313,6 +367,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             // registers busy, could only run one chunk ahead and capped the residual stream at ~3 TB/s: the proj GEMMs of the
             // attention blocks took twice their HBM time).
             const bool has_res = p.res_mode == NDB_RES_SAME;
+            const float osc = p.out_scale;
             const int nbuf = p.epi_bufs;        // residual: 3 (short K: the epilogue is the critical path) or 2 (long K: the
                                                 // staging space goes to the operand pipeline instead)
             uint8_t* sbuf0 = epi_base + (warp - 2) * 4096 * nbuf;
@@ -375,6 +430,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                 }
                 __syncwarp();
 
+                drain_chunks();
                 mbar_wait(&tmem_full_bar[acc], acc_phase);
                 tc_fence_after();
                 if (kStats) mbar_wait(&stat_empty_bar[stat_buf], stat_phase ^ 1);   // part_smem buffer free
@@ -400,6 +456,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                         if (nbuf == 2) sb ^= 1;
                     }
                     tmem_ld_wait();
+                    add_csum(racc, ch);
                     uint8_t* sbuf = sbuf0 + b * 4096;
                     float* sf = reinterpret_cast<float*>(sbuf);
                     const float4* bias4 = reinterpret_cast<const float4*>(bias_s + (ch - ch_begin) * 32);
@@ -409,8 +466,9 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                         for (int j = 0; j < 8; ++j) {
                             const float4 b4 = bias4[j];
                             float4* dst = reinterpret_cast<float4*>(sbuf + lane * 128 + ((j ^ (lane & 7)) << 4));
-                            float4 v = make_float4(__uint_as_float(racc[4 * j]) + b4.x, __uint_as_float(racc[4 * j + 1]) + b4.y,
-                                                   __uint_as_float(racc[4 * j + 2]) + b4.z, __uint_as_float(racc[4 * j + 3]) + b4.w);
+                            // acc * 2^k is exact, so the fma rounds exactly like the plain add it replaces (out_scale = 1)
+                            float4 v = make_float4(fmaf(__uint_as_float(racc[4 * j]), osc, b4.x), fmaf(__uint_as_float(racc[4 * j + 1]), osc, b4.y),
+                                                   fmaf(__uint_as_float(racc[4 * j + 2]), osc, b4.z), fmaf(__uint_as_float(racc[4 * j + 3]), osc, b4.w));
                             if (use_res) {
                                 const float4 rv = *dst;
                                 v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
@@ -421,10 +479,10 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float4 b0 = bias4[2 * j], b1 = bias4[2 * j + 1];
-                            const float v0 = __uint_as_float(racc[8 * j]) + b0.x, v1 = __uint_as_float(racc[8 * j + 1]) + b0.y;
-                            const float v2 = __uint_as_float(racc[8 * j + 2]) + b0.z, v3 = __uint_as_float(racc[8 * j + 3]) + b0.w;
-                            const float v4 = __uint_as_float(racc[8 * j + 4]) + b1.x, v5 = __uint_as_float(racc[8 * j + 5]) + b1.y;
-                            const float v6 = __uint_as_float(racc[8 * j + 6]) + b1.z, v7 = __uint_as_float(racc[8 * j + 7]) + b1.w;
+                            const float v0 = fmaf(__uint_as_float(racc[8 * j]), osc, b0.x), v1 = fmaf(__uint_as_float(racc[8 * j + 1]), osc, b0.y);
+                            const float v2 = fmaf(__uint_as_float(racc[8 * j + 2]), osc, b0.z), v3 = fmaf(__uint_as_float(racc[8 * j + 3]), osc, b0.w);
+                            const float v4 = fmaf(__uint_as_float(racc[8 * j + 4]), osc, b1.x), v5 = fmaf(__uint_as_float(racc[8 * j + 5]), osc, b1.y);
+                            const float v6 = fmaf(__uint_as_float(racc[8 * j + 6]), osc, b1.z), v7 = fmaf(__uint_as_float(racc[8 * j + 7]), osc, b1.w);
                             uint4 w4;
                             if (p.fmt == 0) w4 = make_uint4(pack2<0>(v0, v1), pack2<0>(v2, v3), pack2<0>(v4, v5), pack2<0>(v6, v7));
                             else w4 = make_uint4(pack2<1>(v0, v1), pack2<1>(v2, v3), pack2<1>(v4, v5), pack2<1>(v6, v7));
@@ -540,6 +598,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             row_res[lane] = res_off;
             __syncwarp();
 
+            drain_chunks();
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
             if (kStats) mbar_wait(&stat_empty_bar[stat_buf], stat_phase ^ 1);   // part_smem buffer free
@@ -579,6 +638,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                 uint32_t racc[32];
                 tmem_ld32(t_row + ch * 32, racc);
                 tmem_ld_wait();
+                add_csum(racc, ch);
                 // (3) transpose through the padded per-warp tile
 #pragma unroll
                 for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __uint_as_float(racc[i]);
@@ -586,7 +646,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                 const float bias_v = (colok && p.bias != nullptr) ? __ldg(p.bias + col) : 0.f;
                 // (4) bias + residual, then store with lanes along channels
 #pragma unroll
-                for (int r = 0; r < 32; ++r) res[r] = stg[r * 33 + lane] + bias_v + res[r];
+                for (int r = 0; r < 32; ++r) res[r] = fmaf(stg[r * 33 + lane], p.out_scale, bias_v) + res[r];
                 if (p.out_kind == NDB_OUT_F32_NHWC) {
                     float* ob = reinterpret_cast<float*>(p.out) + col;
 #pragma unroll
@@ -710,8 +770,9 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
 // ------------------------------------------------------------------------------------------------------
 // weight packing: OIHW fp32 -> [tap][cout_pad][cin_len] 16-bit
 // ------------------------------------------------------------------------------------------------------
+// part 0: the 16-bit rounding of w * scale; part 1 (fp32-class mode): the fp16 rounding of what part 0 lost
 __global__ void pack_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ dst, int cout, int cin_total,
-                                   int taps, int cout_pad, int cin_off, int cin_len, int fmt) {
+                                   int taps, int cout_pad, int cin_off, int cin_len, int fmt, float scale, int part) {
     const long long total = (long long)taps * cout_pad * cin_len;
     pdl_launch_dependents();
     pdl_wait();
@@ -722,7 +783,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, uint16_t* __rest
         const int co = (int)(r % cout_pad);
         const int tap = (int)(r / cout_pad);
         float v = 0.f;
-        if (co < cout) v = w[((long long)co * cin_total + cin_off + ci) * taps + tap];
+        if (co < cout) v = w[((long long)co * cin_total + cin_off + ci) * taps + tap] * scale;
+        if (part == 1) v -= __half2float(__float2half_rn(v));
         uint16_t bits;
         if (fmt == 0) {
             __half h = __float2half_rn(v);
@@ -840,14 +902,14 @@ static WorkGeom work_geom(const ConvGeom& g, int num_n_tiles, int block_n, bool 
 // BLOCK_N by a small cost model: rounds of tiles per worker x tile cost. Narrow tiles run the tensor pipe at a lower rate
 // (shared-memory operand bandwidth per MMA grows relative to its work; rates measured with scripts/blockn_probe.py), but
 // they fill the machine when a layer has few tiles (the 8x8 levels: 16 M tiles).
-static int pick_block_n(int cout_pad, const ConvGeom& g, bool want_stats, int kblocks) {
+static int pick_block_n(int cout_pad, const ConvGeom& g, bool want_stats, int kblocks, int max_bn = 256) {
     static const int cand[5] = {256, 192, 128, 96, 64};
     static const double rate[5] = {1.0, 1.0, 0.78, 0.61, 0.5};
     int best = 0;
     double best_cost = 0.0;
     for (int i = 0; i < 5; ++i) {
         const int bn = cand[i];
-        if (cout_pad % bn != 0) continue;
+        if (cout_pad % bn != 0 || bn > max_bn) continue;
         const WorkGeom w = work_geom(g, cout_pad / bn, bn, want_stats, kblocks);
         const int rounds = (w.items + w.workers - 1) / w.workers;
         double cost = rounds * (double)bn / rate[i];
@@ -855,7 +917,7 @@ static int pick_block_n(int cout_pad, const ConvGeom& g, bool want_stats, int kb
         if (best == 0 || cost < best_cost) { best = bn; best_cost = cost; }
     }
     if (best) return best;
-    for (int bn = 256; bn >= 16; bn -= 16)
+    for (int bn = max_bn; bn >= 16; bn -= 16)
         if (cout_pad % bn == 0) return bn;
     return 0;
 }
@@ -865,8 +927,10 @@ static int pick_block_n(int cout_pad, const ConvGeom& g, bool want_stats, int kb
 using namespace ndb;
 
 extern "C" int ndb_pack_conv_weight(const float* w_oihw, void* dst, int cout, int cin_total, int ksize, int cout_pad,
-                                    int cin_off, int cin_len, int operand_format, void* stream) {
+                                    int cin_off, int cin_len, int operand_format, float scale, int part, void* stream) {
     NDB_CHECK_ARG(w_oihw && dst);
+    NDB_CHECK_ARG(part == 0 || (part == 1 && operand_format == 0));
+    if (scale == 0.f) scale = 1.f;
     NDB_CHECK_ARG(ksize == 1 || ksize == 3);
     NDB_CHECK_ARG(cout_pad >= cout && cin_off >= 0 && cin_off + cin_len <= cin_total);
     const int taps = ksize * ksize;
@@ -874,7 +938,7 @@ extern "C" int ndb_pack_conv_weight(const float* w_oihw, void* dst, int cout, in
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     launch_kernel(pack_weight_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, 1, w_oihw, (uint16_t*)dst, cout,
-                  cin_total, taps, cout_pad, cin_off, cin_len, operand_format);
+                  cin_total, taps, cout_pad, cin_off, cin_len, operand_format, scale, part);
     return launch_status("ndb_pack_conv_weight");
 }
 
@@ -896,7 +960,8 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     int kblocks_total = 0;
     for (int s = 0; s < prm->num_segments; ++s) kblocks_total += prm->seg[s].taps * (prm->seg[s].C / kBlockK);
     a.block_n = prm->block_n > 0 ? prm->block_n
-                                 : pick_block_n(prm->cout_pad, cg, prm->stat_parts != nullptr, kblocks_total);
+                                 : pick_block_n(prm->cout_pad, cg, prm->stat_parts != nullptr, kblocks_total,
+                                                prm->acc_chunk_kblocks > 0 ? 192 : 256);
     NDB_CHECK_ARG(a.block_n >= 16 && a.block_n <= 256 && a.block_n % 16 == 0 && prm->cout_pad % a.block_n == 0);
     a.num_n_tiles = prm->cout_pad / a.block_n;
     a.cout = prm->cout;
@@ -912,6 +977,9 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     a.out_kind = prm->out_kind;
     a.out = prm->out;
     a.fmt = prm->operand_format;
+    a.out_scale = prm->out_scale == 0.f ? 1.f : prm->out_scale;
+    a.acc_chunk = prm->acc_chunk_kblocks;
+    NDB_CHECK_ARG(a.acc_chunk >= 0);
     a.stat_parts = reinterpret_cast<float2*>(prm->stat_parts);
     a.tiles_per_group = a.tiles_w * a.tiles_h * a.num_n_tiles;
     const WorkGeom wg = work_geom(cg, a.num_n_tiles, a.block_n, prm->stat_parts != nullptr, kblocks_total);
@@ -1024,7 +1092,23 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     }
     const bool stats = a.stat_parts != nullptr;
     cudaError_t le;
-    if (!wg.pair)
+    if (a.acc_chunk > 0) {
+        NDB_CHECK_ARG(a.block_n <= 192);      // three 32-column running-sum chunks per epilogue warp
+        static PerDeviceOnce chunk_attr;
+        if (chunk_attr.pending()) {
+            cudaFuncSetAttribute(conv_gemm_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            cudaFuncSetAttribute(conv_gemm_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            cudaFuncSetAttribute(conv_gemm_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            cudaFuncSetAttribute(conv_gemm_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            chunk_attr.done();
+        }
+        if (!wg.pair)
+            le = stats ? launch_kernel(conv_gemm_kernel<true, false, true>, dim3(wg.grid), dim3(kThreads), smem_bytes, (cudaStream_t)stream, 1, maps, a)
+                       : launch_kernel(conv_gemm_kernel<false, false, true>, dim3(wg.grid), dim3(kThreads), smem_bytes, (cudaStream_t)stream, 1, maps, a);
+        else
+            le = stats ? launch_kernel(conv_gemm_kernel<true, true, true>, dim3(wg.grid), dim3(kThreads), smem_bytes, (cudaStream_t)stream, 2, maps, a)
+                       : launch_kernel(conv_gemm_kernel<false, true, true>, dim3(wg.grid), dim3(kThreads), smem_bytes, (cudaStream_t)stream, 2, maps, a);
+    } else if (!wg.pair)
         le = stats ? launch_kernel(conv_gemm_kernel<true, false>, dim3(wg.grid), dim3(kThreads), smem_bytes, (cudaStream_t)stream, 1, maps, a)
                    : launch_kernel(conv_gemm_kernel<false, false>, dim3(wg.grid), dim3(kThreads), smem_bytes, (cudaStream_t)stream, 1, maps, a);
     else
@@ -1041,11 +1125,12 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
 // segments of taps * C; it decides between the CTA-pair and the single-CTA kernel): returns the number of partial slots per image
 // (stat_smax) and fills counts[N] (host memory) with the slots actually written for each image; <0 on error.
 // stat_parts must hold N * stat_smax * cout float2.
-extern "C" int ndb_conv_stats_layout(int N, int H, int W, int cout_pad, int block_n, int k_total, int32_t* counts) {
+extern "C" int ndb_conv_stats_layout(int N, int H, int W, int cout_pad, int block_n, int k_total, int acc_chunk_kblocks,
+                                     int32_t* counts) {
     if (N <= 0 || H <= 0 || W <= 0 || cout_pad <= 0 || k_total <= 0 || k_total % kBlockK != 0) return NDB_ERR_INVALID;
     const int kblocks = k_total / kBlockK;
     const ConvGeom g = conv_geom(N, H, W);
-    const int bn = block_n > 0 ? block_n : pick_block_n(cout_pad, g, true, kblocks);
+    const int bn = block_n > 0 ? block_n : pick_block_n(cout_pad, g, true, kblocks, acc_chunk_kblocks > 0 ? 192 : 256);
     if (bn <= 0 || cout_pad % bn != 0) return NDB_ERR_INVALID;
     const int n_tiles = cout_pad / bn;
     const WorkGeom w = work_geom(g, n_tiles, bn, true, kblocks);

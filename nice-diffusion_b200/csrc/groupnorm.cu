@@ -130,6 +130,7 @@ struct GnApplyArgs {
     const float* pre_add; int ld_pre;
     int silu, resample;
     uint16_t* out; uint16_t* raw16;
+    uint16_t* out_lo; uint16_t* raw_lo;   // fp32-class mode: the fp16 remainders (SPLIT kernels)
     int cpg;         // channels per group; 0 = (C0 + C1) / 32. A slice of a wider normalised tensor passes the parent's value
     int x0_is16;     // x0 holds 16-bit values (operand_format) instead of fp32
     float* pool32;   // DOWN2 only: fp32 2x2 mean of the raw input (the x_resample operand of a down ResBlock)
@@ -154,7 +155,18 @@ struct GnApplyArgs {
 // The summation order (slots in order per channel; channels sub, sub+8, ... per lane; xor-shuffles) is fixed: results are
 // bit-reproducible and independent of the chunking.
 // IN16: x0 is a 16-bit tensor (the fp16 `h` between the two convs of a ResBlock) instead of fp32.
-template <int FMT, int RESAMPLE, bool SILU, bool RAW, bool IN16>
+// SPLIT (fp32-class mode): SiLU is evaluated with an accurate exponential and a true division, and every output value v is
+// stored as the fp16 pair (hi = fp16(v), lo = fp16(v - hi)) in two tensors of the same layout.
+__device__ __forceinline__ float silu_exact(float v) { return v / (1.f + expf(-v)); }
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+template <int FMT, int RESAMPLE, bool SILU, bool RAW, bool IN16, bool SPLIT = false>
 __global__ void __launch_bounds__(kGnThreads, 3)
 gn_apply_kernel(const GnApplyArgs p) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -222,6 +234,21 @@ gn_apply_kernel(const GnApplyArgs p) {
         }
         return pu;
     };
+
+    // eight results -> one 16-byte store (two in SPLIT mode)
+    auto store8 = [&](uint16_t* dst, uint16_t* dst_lo, const float* y) {
+        if (SPLIT) {
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) split2(y[2 * k], y[2 * k + 1], h[k], l[k]);
+            *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(dst_lo) = make_uint4(l[0], l[1], l[2], l[3]);
+        } else {
+            *reinterpret_cast<uint4*>(dst) =
+                make_uint4(pack2h<FMT>(y[0], y[1]), pack2h<FMT>(y[2], y[3]), pack2h<FMT>(y[4], y[5]), pack2h<FMT>(y[6], y[7]));
+        }
+    };
+    auto act = [&](float t) { return !SILU ? t : (SPLIT ? silu_exact(t) : silu_half(t)); };
 
     // ---- 0. static data (written when the plan was built, never by a kernel of the step): legal before the wait ----
     const int cnt0 = __ldg(p.counts0 + n);
@@ -302,7 +329,7 @@ gn_apply_kernel(const GnApplyArgs p) {
             ak *= s1;
             bk = bk * s1 + __ldg(p.shift + (size_t)n * p.ld_ss + c);
         }
-        if (SILU) { ak *= 0.5f; bk *= 0.5f; }   // SiLU is evaluated from v / 2 (silu_half)
+        if (SILU && !SPLIT) { ak *= 0.5f; bk *= 0.5f; }   // SiLU is evaluated from v / 2 (silu_half)
         sa[cl] = ak; sb[cl] = bk;
         if (RAW) sp[cl] = pr;
     }
@@ -329,6 +356,8 @@ gn_apply_kernel(const GnApplyArgs p) {
         const float* __restrict__ srcp = src;
         uint16_t* __restrict__ outq = p.out + (size_t)n * npix * C + c;
         uint16_t* __restrict__ rawq = RAW ? p.raw16 + (size_t)n * npix * C + c : nullptr;
+        uint16_t* __restrict__ outq_lo = SPLIT ? p.out_lo + (size_t)n * npix * C + c : nullptr;
+        uint16_t* __restrict__ rawq_lo = (SPLIT && RAW) ? p.raw_lo + (size_t)n * npix * C + c : nullptr;
         if (RESAMPLE == NDB_RESAMPLE_DOWN2) {
             for (int po = p_begin + r; po < p_end; po += rows_per_block) {
                 float y[8], raw[8];
@@ -349,7 +378,7 @@ gn_apply_kernel(const GnApplyArgs p) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         float t = a[k] * xv[q][k] + b[k];
-                        if (SILU) t = silu_half(t);
+                        t = act(t);
                         acc += t;
                         if (RAW) racc += xv[q][k] + pre[k];
                     }
@@ -357,11 +386,8 @@ gn_apply_kernel(const GnApplyArgs p) {
                     raw[k] = racc * 0.25f;
                 }
                 const size_t o = (size_t)po * C;
-                *reinterpret_cast<uint4*>(outq + o) =
-                    make_uint4(pack2h<FMT>(y[0], y[1]), pack2h<FMT>(y[2], y[3]), pack2h<FMT>(y[4], y[5]), pack2h<FMT>(y[6], y[7]));
-                if (RAW)
-                    *reinterpret_cast<uint4*>(rawq + o) = make_uint4(pack2h<FMT>(raw[0], raw[1]), pack2h<FMT>(raw[2], raw[3]),
-                                                                     pack2h<FMT>(raw[4], raw[5]), pack2h<FMT>(raw[6], raw[7]));
+                store8(outq + o, SPLIT ? outq_lo + o : nullptr, y);
+                if (RAW) store8(rawq + o, SPLIT ? rawq_lo + o : nullptr, raw);
                 if (p.pool32 != nullptr) {
                     // same association as F.avg_pool2d: sum of the four taps, then * 0.25 (pre_add is not part of x)
                     float pl[8];
@@ -381,6 +407,8 @@ gn_apply_kernel(const GnApplyArgs p) {
             const uint32_t out_stride = (uint32_t)rows * (uint32_t)C;       // elements between two of this thread's pixels
             uint16_t* op = outq + (size_t)(p_begin + r) * C;
             uint16_t* rp = RAW ? rawq + (size_t)(p_begin + r) * C : nullptr;
+            const ptrdiff_t lo_off = SPLIT ? (p.out_lo - p.out) : 0;            // hi -> lo tensor, in elements
+            const ptrdiff_t raw_lo_off = (SPLIT && RAW) ? (p.raw_lo - p.raw16) : 0;
             bool first = (v == tv);                                        // the very first trip was requested before the prologue
             if (RESAMPLE == NDB_RESAMPLE_NONE) {
                 const uint32_t in_stride = (uint32_t)rows * (uint32_t)ldc * (uint32_t)esz;   // bytes
@@ -404,16 +432,14 @@ gn_apply_kernel(const GnApplyArgs p) {
                             unpack8(lo[u], hi[u], xv);
                             float y[8];
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                const float t = fmaf(a[k], xv[k], b[k]);
-                                y[k] = SILU ? silu_half(t) : t;
+                            for (int k = 0; k < 8; ++k) y[k] = act(fmaf(a[k], xv[k], b[k]));
+                            store8(op + u * out_stride, op + u * out_stride + lo_off, y);
+                            if (RAW) {
+                                float rw[8];
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) rw[k] = xv[k] + pre[k];
+                                store8(rp + u * out_stride, rp + u * out_stride + raw_lo_off, rw);
                             }
-                            *reinterpret_cast<uint4*>(op + u * out_stride) = make_uint4(pack2h<FMT>(y[0], y[1]), pack2h<FMT>(y[2], y[3]),
-                                                                                        pack2h<FMT>(y[4], y[5]), pack2h<FMT>(y[6], y[7]));
-                            if (RAW)
-                                *reinterpret_cast<uint4*>(rp + u * out_stride) =
-                                    make_uint4(pack2h<FMT>(xv[0] + pre[0], xv[1] + pre[1]), pack2h<FMT>(xv[2] + pre[2], xv[3] + pre[3]),
-                                               pack2h<FMT>(xv[4] + pre[4], xv[5] + pre[5]), pack2h<FMT>(xv[6] + pre[6], xv[7] + pre[7]));
                         }
                     }
                 }
@@ -436,17 +462,15 @@ gn_apply_kernel(const GnApplyArgs p) {
                             unpack8(lo[u], hi[u], xv);
                             float y[8];
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                const float t = fmaf(a[k], xv[k], b[k]);
-                                y[k] = SILU ? silu_half(t) : t;
-                            }
+                            for (int k = 0; k < 8; ++k) y[k] = act(fmaf(a[k], xv[k], b[k]));
                             const size_t o = (size_t)pu * C;
-                            *reinterpret_cast<uint4*>(outq + o) = make_uint4(pack2h<FMT>(y[0], y[1]), pack2h<FMT>(y[2], y[3]),
-                                                                             pack2h<FMT>(y[4], y[5]), pack2h<FMT>(y[6], y[7]));
-                            if (RAW)
-                                *reinterpret_cast<uint4*>(rawq + o) =
-                                    make_uint4(pack2h<FMT>(xv[0] + pre[0], xv[1] + pre[1]), pack2h<FMT>(xv[2] + pre[2], xv[3] + pre[3]),
-                                               pack2h<FMT>(xv[4] + pre[4], xv[5] + pre[5]), pack2h<FMT>(xv[6] + pre[6], xv[7] + pre[7]));
+                            store8(outq + o, SPLIT ? outq_lo + o : nullptr, y);
+                            if (RAW) {
+                                float rw[8];
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) rw[k] = xv[k] + pre[k];
+                                store8(rawq + o, SPLIT ? rawq_lo + o : nullptr, rw);
+                            }
                         }
                     }
                 }
@@ -474,9 +498,21 @@ static void launch_gn_apply2(const GnApplyArgs& a, dim3 grid, cudaStream_t st) {
 #undef NDB_GN_CASE
 }
 
+template <bool RAW>
+static void launch_gn_apply_split(const GnApplyArgs& a, dim3 grid, cudaStream_t st) {
+#define NDB_GN_SCASE(RS, SL) launch_gn(gn_apply_kernel<0, RS, SL, RAW, false, true>, a, grid, st)
+    if (a.resample == NDB_RESAMPLE_NONE) { if (a.silu) NDB_GN_SCASE(NDB_RESAMPLE_NONE, true); else NDB_GN_SCASE(NDB_RESAMPLE_NONE, false); }
+    else if (a.resample == NDB_RESAMPLE_UP2) { if (a.silu) NDB_GN_SCASE(NDB_RESAMPLE_UP2, true); else NDB_GN_SCASE(NDB_RESAMPLE_UP2, false); }
+    else { if (a.silu) NDB_GN_SCASE(NDB_RESAMPLE_DOWN2, true); else NDB_GN_SCASE(NDB_RESAMPLE_DOWN2, false); }
+#undef NDB_GN_SCASE
+}
+
 template <int FMT>
 static void launch_gn_apply(const GnApplyArgs& a, dim3 grid, cudaStream_t st) {
-    if (a.x0_is16) {
+    if (a.out_lo != nullptr) {
+        if (a.raw16 != nullptr) launch_gn_apply_split<true>(a, grid, st);
+        else launch_gn_apply_split<false>(a, grid, st);
+    } else if (a.x0_is16) {
         // 16-bit source: the out_norm of a ResBlock (single source, no resampling, no raw copy)
         if (a.silu) launch_gn(gn_apply_kernel<FMT, NDB_RESAMPLE_NONE, true, false, true>, a, grid, st);
         else launch_gn(gn_apply_kernel<FMT, NDB_RESAMPLE_NONE, false, false, true>, a, grid, st);
@@ -557,6 +593,11 @@ extern "C" int ndb_gn_apply(const ndb_gn_apply_params* q, void* stream) {
     a.pre_add = q->pre_add; a.ld_pre = q->ld_pre;
     a.silu = q->silu; a.resample = q->resample;
     a.out = (uint16_t*)q->out; a.raw16 = (uint16_t*)q->raw16;
+    a.out_lo = (uint16_t*)q->out_lo; a.raw_lo = (uint16_t*)q->raw_lo;
+    if (q->out_lo != nullptr) {
+        NDB_CHECK_ARG(q->operand_format == 0 && !q->x0_is16);
+        NDB_CHECK_ARG((q->raw16 == nullptr) == (q->raw_lo == nullptr));
+    }
     a.pool32 = q->pool32;
     a.x0_is16 = q->x0_is16;
     a.cpg = q->cpg;

@@ -261,6 +261,28 @@ __global__ void cast16_kernel(const float* __restrict__ x, uint16_t* __restrict_
     }
 }
 
+// fp32 -> (hi, lo) fp16 pair with hi + lo == x to ~2^-22 relative (the operands of the fp32-class mode: three tensor-core
+// products a_hi w_hi + a_lo w_hi + a_hi w_lo stand in for one fp32 product). silu: apply SiLU (accurate expf) first.
+__global__ void split16_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, long long numel,
+                               int silu) {
+    const long long n4 = numel >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x) + i);
+        float v[4] = {a.x, a.y, a.z, a.w};
+        uint16_t h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (silu) v[k] = v[k] / (1.f + expf(-v[k]));
+            const __half hh = __float2half_rn(v[k]);
+            h[k] = __half_as_ushort(hh);
+            l[k] = __half_as_ushort(__float2half_rn(v[k] - __half2float(hh)));
+        }
+        reinterpret_cast<uint2*>(hi)[i] = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+        reinterpret_cast<uint2*>(lo)[i] = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+    }
+}
+
 // Stem conv as a GEMM: out[n][h][w][tap*CIN + c] = x[n][c][h+ky-1][w+kx-1] (zero outside the image), tap = ky*3+kx, the
 // 9*CIN <= 64 gathered values of a pixel zero-padded to ONE 64-element K block. x is NCHW fp32 (the model input); thread =
 // pixel, consecutive threads read consecutive w (coalesced per (c, ky, kx)), each writes its 128-byte row as 8 x 16 bytes.
@@ -447,6 +469,12 @@ extern "C" int ndb_to_uint8(const float* x_nchw, uint8_t* out_nhwc, int B, int C
     to_uint8_kernel<<<grid_for((long long)B * C * H * W, 256), 256, 0, (cudaStream_t)stream>>>(x_nchw, out_nhwc, B, C, H, W,
                                                                                                gray_invert);
     return launch_status("ndb_to_uint8");
+}
+
+extern "C" int ndb_split16(const float* x, void* hi, void* lo, int64_t numel, int silu, void* stream) {
+    NDB_CHECK_ARG(x && hi && lo && numel > 0 && numel % 4 == 0);
+    split16_kernel<<<grid_for(numel / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (uint16_t*)hi, (uint16_t*)lo, numel, silu);
+    return launch_status("ndb_split16");
 }
 
 extern "C" int ndb_timestamp(uint64_t* dst, void* stream) {

@@ -58,7 +58,11 @@ class UNetEngine:
         self.model = model
         self.B = batch
         self.device = device
-        self.fmt = model.operand_format
+        # fp32-class mode: kernels run with fp16 operands, every operand is a (hi, lo) pair and every GEMM has three K segments
+        # per logical segment (hi hi + lo hi + hi lo); a "16-bit operand" below is then a tuple of two tensors
+        self.split = model.operand_format == L.FMT_FP32X
+        self.fmt = L.FMT_FP16 if self.split else model.operand_format
+        self.wscale = L.SPLIT_WEIGHT_SCALE if self.split else 1.0
         self.dt16 = ops.dtype16(self.fmt)
         self.steps = []          # list of zero-arg callables, one kernel launch each
         self.n_embed_steps = 0   # leading steps (embedding front end) that run on a side stream ...
@@ -96,10 +100,46 @@ class UNetEngine:
         k = p.shape[2] if p.dim() >= 3 else 1
         cp = ops.pad16(cout) if cout_pad is None else cout_pad
         cl = p.shape[1] - cin_off if cin_len is None else cin_len
-        buf = torch.empty((k * k, cp, cl), dtype=self.dt16, device=self.device)
-        self.packers.append(lambda: ops.pack_conv_weight(getattr(mod, name).detach().to(self.device), cout_pad=cp,
-                                                         cin_off=cin_off, cin_len=cl, fmt=self.fmt, out=buf))
-        return buf
+        bufs = [torch.empty((k * k, cp, cl), dtype=self.dt16, device=self.device) for _ in range(2 if self.split else 1)]
+
+        def pack():
+            w = getattr(mod, name).detach().to(self.device)
+            for part, buf in enumerate(bufs):
+                ops.pack_conv_weight(w, cout_pad=cp, cin_off=cin_off, cin_len=cl, fmt=self.fmt, out=buf, scale=self.wscale,
+                                     part=part)
+        self.packers.append(pack)
+        return tuple(bufs) if self.split else bufs[0]
+
+    # ---- 16-bit operands: one tensor, or a (hi, lo) pair in the fp32-class mode --------------------------------------
+    def _new16(self, shape, pooled=True):
+        mk = (lambda: self.pool.get(shape, self.dt16)) if pooled else \
+            (lambda: torch.empty(shape, dtype=self.dt16, device=self.device))
+        return (mk(), mk()) if self.split else mk()
+
+    def _free16(self, t):
+        if t is None:
+            return
+        for x in (t if isinstance(t, tuple) else (t,)):
+            self.pool.put(x)
+
+    def _expand(self, segs):
+        """Logical K segments -> kernel segments (+ the accumulator scale that undoes the weight scale)."""
+        if not self.split:
+            return list(segs), 1.0
+        out = []
+        for a, w in segs:
+            out += [(a[0], w[0]), (a[1], w[0]), (a[0], w[1])]
+        if len(out) > L.MAX_SEGMENTS:
+            raise L.NdbError('fp32-class mode: this layer needs {} K segments (max {})'.format(len(out), L.MAX_SEGMENTS))
+        return out, 1.0 / self.wscale
+
+    def _gn(self, x0, stats0, gamma, beta, out, raw16=None, **kw):
+        """ops.gn_apply with the output operand(s) given as tensors or (hi, lo) pairs."""
+        if self.split:
+            return ops.gn_apply(x0, stats0, gamma, beta, out=out[0], out_lo=out[1],
+                                raw16=raw16[0] if raw16 is not None else None,
+                                raw_lo=raw16[1] if raw16 is not None else None, fmt=self.fmt, **kw)
+        return ops.gn_apply(x0, stats0, gamma, beta, out=out, raw16=raw16, fmt=self.fmt, **kw)
 
     def _bias_sum(self, m1, m2):
         buf = torch.empty(m1.bias.shape, dtype=torch.float32, device=self.device)
@@ -142,7 +182,8 @@ class UNetEngine:
         if key not in self._layouts:
             import ctypes
             counts = (ctypes.c_int32 * self.B)()
-            smax = int(L.load().ndb_conv_stats_layout(self.B, H, W, ops.pad16(cout), 0, k_total, counts))
+            smax = int(L.load().ndb_conv_stats_layout(self.B, H, W, ops.pad16(cout), 0, k_total,
+                                                      L.SPLIT_ACC_CHUNK if self.split else 0, counts))
             if smax < 1:
                 raise L.NdbError('ndb_conv_stats_layout failed')
             self._layouts[key] = (smax, torch.tensor(list(counts), dtype=torch.int32, device=self.device))
@@ -152,6 +193,10 @@ class UNetEngine:
         """Emit one implicit-GEMM launch. With want_stats the epilogue also produces the output's per-channel
         statistics (or, for geometries it does not cover, a standalone statistics launch follows)."""
         B, fmt = self.B, self.fmt
+        segs, osc = self._expand(segs)
+        if self.split:
+            kw['out_scale'] = osc
+            kw['acc_chunk'] = L.SPLIT_ACC_CHUNK
         if out is None:
             out = self.pool.get((B, H, W, cout), torch.float32)
         stats = None
@@ -198,7 +243,7 @@ class UNetEngine:
         resblocks = [mod for mod in m.modules() if isinstance(mod, ResidualBlock)]
         total = sum(rb.step_embedding.out_features for rb in resblocks)
         assert total % 16 == 0
-        w_all = torch.empty((1, total, E), dtype=self.dt16, device=dev)
+        w_parts = [torch.empty((1, total, E), dtype=self.dt16, device=dev) for _ in range(2 if self.split else 1)]
         b_all = torch.empty((total,), dtype=torch.float32, device=dev)
         self.emb_all = torch.empty((B, total), dtype=torch.float32, device=dev)
         self.emb_off = {}
@@ -206,14 +251,28 @@ class UNetEngine:
         for rb in resblocks:
             n = rb.step_embedding.out_features
             self.emb_off[id(rb)] = off
-            wv, bv, lin = w_all[:, off:off + n, :], b_all[off:off + n], rb.step_embedding
-            self.packers.append(lambda wv=wv, lin=lin, n=n: wv.copy_(
-                lin.weight.detach().to(self.dt16).view(1, n, E)))
+            bv, lin = b_all[off:off + n], rb.step_embedding
+
+            def pack_lin(lin=lin, n=n, off=off):
+                w = lin.weight.detach().float() * self.wscale
+                hi = w.to(self.dt16)
+                w_parts[0][:, off:off + n, :].copy_(hi.view(1, n, E))
+                if self.split:
+                    w_parts[1][:, off:off + n, :].copy_((w - hi.float()).to(self.dt16).view(1, n, E))
+            self.packers.append(pack_lin)
             self.packers.append(lambda bv=bv, lin=lin: bv.copy_(lin.bias.detach()))
             off += n
-        a_view = act16.view(1, 1, B, E)
-        self.steps.append(lambda: ops.conv_gemm([(a_view, w_all)], 1, 1, B, total, bias=b_all,
-                                                out=self.emb_all, fmt=fmt, cout_pad=total))
+        if self.split:
+            # SiLU(emb) as an fp16 (hi, lo) pair, from the fp32 embedding
+            a_hi = torch.empty((B, E), dtype=self.dt16, device=dev)
+            a_lo = torch.empty((B, E), dtype=self.dt16, device=dev)
+            self.steps.append(lambda: ops.split16(self.emb, a_hi, a_lo, silu=True))
+            a_view, w_all = (a_hi.view(1, 1, B, E), a_lo.view(1, 1, B, E)), tuple(w_parts)
+        else:
+            a_view, w_all = act16.view(1, 1, B, E), w_parts[0]
+        esegs, eosc = self._expand([(a_view, w_all)])
+        self.steps.append(lambda: ops.conv_gemm(esegs, 1, 1, B, total, bias=b_all, out=self.emb_all, fmt=fmt, cout_pad=total,
+                                                out_scale=eosc, acc_chunk=L.SPLIT_ACC_CHUNK if self.split else 0))
         self.n_embed_steps = len(self.steps)
 
         # ---- workspace of the standalone statistics kernel (stem output, uncovered geometries) ----
@@ -227,7 +286,7 @@ class UNetEngine:
         # ---- trunk ----
         stem = m.downsampling[0][0]
         C0 = stem.weight.shape[0]
-        if 9 * m.in_channels <= 64 and ops.conv_stats_supported(B, R, R) and os.environ.get('NDB_STEM_GEMM'):
+        if 9 * m.in_channels <= 64 and ops.conv_stats_supported(B, R, R) and os.environ.get('NDB_STEM_GEMM') and not self.split:
             # stem conv on the tensor cores: the 3x3 neighbourhood of a pixel (9 * Cin <= 64 values) is ONE K block, so the
             # conv is a 1x1 GEMM that is purely output-bandwidth bound and gets the fused bias / TMA-store epilogue /
             # GroupNorm statistics of every other conv. OPT-IN (NDB_STEM_GEMM=1): measured 0.05 ms (0.5 %) per step faster
@@ -265,12 +324,13 @@ class UNetEngine:
         # head: GroupNorm -> SiLU -> conv3x3 to out_channels (model.py:446-449), NCHW fp32 out
         gn, conv = m.out[0], m.out[2]
         g = self._copy_param(gn, 'weight'); bt = self._copy_param(gn, 'bias')
-        a = self.pool.get(tuple(cur.t.shape), self.dt16)
+        a = self._new16(tuple(cur.t.shape))
         wp = self._packed(conv, 'weight'); bp = self._copy_param(conv, 'bias')
         H = cur.t.shape[1]
-        self.steps.append(lambda: ops.gn_apply(cur.t, cur.stats, g, bt, silu=True, out=a, fmt=fmt, eps=gn.eps))
-        self.steps.append(lambda: ops.conv_gemm([(a, wp)], B, H, H, m.out_channels, bias=bp,
-                                                out_kind=L.OUT_F32_NCHW, out=self.out, fmt=fmt))
+        self.steps.append(lambda: self._gn(cur.t, cur.stats, g, bt, a, silu=True, eps=gn.eps))
+        hsegs, hosc = self._expand([(a, wp)])
+        self.steps.append(lambda: ops.conv_gemm(hsegs, B, H, H, m.out_channels, bias=bp, out_kind=L.OUT_F32_NCHW, out=self.out,
+                                                fmt=fmt, out_scale=hosc, acc_chunk=L.SPLIT_ACC_CHUNK if self.split else 0))
         self.num_kernels = len(self.steps) - self.n_aux_steps + len(self.early) + 1   # the embedding front end is two launches
 
     def _all_channels(self):
@@ -349,34 +409,32 @@ class UNetEngine:
             pre = self.emb_all[:, off:off + Cout]
 
         eps1, eps2 = rb.in_norm.eps, rb.out_norm.eps
-        a2 = pool.get((B, Ho, Wo, Cout), self.dt16)
+        a2 = self._new16((B, Ho, Wo, Cout))
         pooled = None
         if split:
-            a1 = pool.get((B, H, W, C0), self.dt16)
-            raw = pool.get((B, H, W, C0), self.dt16)
-            a1b = torch.empty((B, H, W, C1), dtype=self.dt16, device=self.device)     # live from the fork to this block
-            rawb = torch.empty((B, H, W, C1), dtype=self.dt16, device=self.device)
+            a1 = self._new16((B, H, W, C0))
+            raw = self._new16((B, H, W, C0))
+            a1b = self._new16((B, H, W, C1), pooled=False)     # live from the fork to this block
+            rawb = self._new16((B, H, W, C1), pooled=False)
             g1a, b1a, g1b, b1b = g1[:C0], b1[:C0], g1[C0:], b1[C0:]
             sk = skip
             ev = torch.cuda.Event()
-            self.early.append((lambda: ops.gn_apply(sk.t, sk.stats, g1b, b1b, silu=True, out=a1b, raw16=rawb, fmt=fmt,
-                                                    eps=eps1, cpg=cpg), ev))
-            self.steps.append(lambda: ops.gn_apply(x.t, x.stats, g1a, b1a, silu=True, out=a1, raw16=raw, fmt=fmt, eps=eps1,
-                                                   cpg=cpg))
+            self.early.append((lambda: self._gn(sk.t, sk.stats, g1b, b1b, a1b, raw16=rawb, silu=True, eps=eps1, cpg=cpg), ev))
+            self.steps.append(lambda: self._gn(x.t, x.stats, g1a, b1a, a1, raw16=raw, silu=True, eps=eps1, cpg=cpg))
             self.steps.append(lambda: torch.cuda.current_stream(self.device).wait_event(ev))
             self.n_aux_steps += 1
             h = self._conv([(a1, w_in_a), (a1b, w_in_b)], Ho, Wo, Cout, want_stats=True, bias=bias_in)
         else:
-            a1 = pool.get((B, Ho, Wo, Cin), self.dt16)
-            raw = pool.get((B, Ho, Wo, Cin), self.dt16) if conv_skip else None
+            a1 = self._new16((B, Ho, Wo, Cin))
+            raw = self._new16((B, Ho, Wo, Cin)) if conv_skip else None
             x1 = skip.t if skip is not None else None
             s1 = skip.stats if skip is not None else None
             # down blocks with an identity skip: the apply kernel (which reads x anyway) also leaves avg_pool2d(x) in fp32,
             # so the out_conv epilogue adds it as a plain residual instead of gathering four taps per element
             pooled = pool.get((B, Ho, Wo, Cin), torch.float32) if (rb.mode == 'down' and not conv_skip) else None
-            self.steps.append(lambda: ops.gn_apply(x.t, x.stats, g1, b1, x1=x1, stats1=s1, silu=True, resample=mode,
-                                                   out=a1, raw16=raw, fmt=fmt, eps=eps1, pool32=pooled))
-            if self.model.h_fp16 and ops.conv_stats_supported(B, Ho, Wo):
+            self.steps.append(lambda: self._gn(x.t, x.stats, g1, b1, a1, raw16=raw, x1=x1, stats1=s1, silu=True, resample=mode,
+                                               eps=eps1, pool32=pooled))
+            if self.model.h_fp16 and not self.split and ops.conv_stats_supported(B, Ho, Wo):
                 # `h` only feeds the out_norm: 16-bit storage halves its write + read (statistics still come from the fp32
                 # accumulators in the epilogue)
                 h = self._conv([(a1, w_in)], Ho, Wo, Cout, want_stats=True, bias=bias_in, out_kind=L.OUT_F16_NHWC,
@@ -385,8 +443,8 @@ class UNetEngine:
                 h = self._conv([(a1, w_in)], Ho, Wo, Cout, want_stats=True, bias=bias_in)
         if self.join_idx is None:
             self.join_idx = len(self.steps)     # first consumer of the step embedding
-        self.steps.append(lambda: ops.gn_apply(h.t, h.stats, g2, b2, scale=scale, shift=shift, pre_add=pre, silu=True,
-                                               out=a2, fmt=fmt, eps=eps2))
+        self.steps.append(lambda: self._gn(h.t, h.stats, g2, b2, a2, scale=scale, shift=shift, pre_add=pre, silu=True,
+                                           eps=eps2))
         if split:
             out = self._conv([(a2, w_out), (raw, w_skip_a), (rawb, w_skip_b)], Ho, Wo, Cout, want_stats=True, bias=bias_out)
         elif conv_skip:
@@ -396,9 +454,10 @@ class UNetEngine:
             rmode = {'same': L.RES_SAME, 'up': L.RES_UP2, 'down': L.RES_SAME}[rb.mode]
             out = self._conv([(a2, w_out)], Ho, Wo, Cout, want_stats=True, bias=bias_out,
                              residual=pooled if pooled is not None else x.t, residual_mode=rmode)
-        for t in (a1, raw, a2, pooled):
-            if t is not None:
-                pool.put(t)
+        for t in (a1, raw, a2):
+            self._free16(t)
+        if pooled is not None:
+            pool.put(pooled)
         self._release(h)
         return out
 
@@ -411,19 +470,31 @@ class UNetEngine:
         g = self._copy_param(ab.norm, 'weight'); bt = self._copy_param(ab.norm, 'bias')
         w_qkv = self._packed(ab.qkv_nin, 'weight'); b_qkv = self._copy_param(ab.qkv_nin, 'bias')
         w_proj = self._packed(ab.proj_out, 'weight'); b_proj = self._copy_param(ab.proj_out, 'bias')
-        n16 = pool.get((B, H, W, C), self.dt16)
-        qkv = pool.get((B, H, W, 3 * C), self.dt16)
-        o16 = pool.get((B, H, W, C), self.dt16)
+        n16 = self._new16((B, H, W, C))
+        o16 = self._new16((B, H, W, C))
         order = 0 if ab.split_qkv_first else 1
         eps = ab.norm.eps
-        self.steps.append(lambda: ops.gn_apply(x.t, x.stats, g, bt, silu=False, out=n16, fmt=fmt, eps=eps))
-        self._conv([(n16, w_qkv)], H, W, 3 * C, want_stats=False, out=qkv, bias=b_qkv, out_kind=L.OUT_F16_NHWC)
-        self.steps.append(lambda: ops.attention(qkv.view(B, T, 3 * C), B, T, heads, d, order=order,
-                                                out=o16.view(B, T, C), fmt=fmt))
+        self.steps.append(lambda: self._gn(x.t, x.stats, g, bt, n16, silu=False, eps=eps))
+        if self.split:
+            # fp32-class: qkv in fp32 -> (hi, lo) pairs -> three-product attention -> fp32 -> (hi, lo) pairs for proj
+            qkv32 = pool.get((B, H, W, 3 * C), torch.float32)
+            qkv = self._new16((B, H, W, 3 * C))
+            o32 = pool.get((B, H, W, C), torch.float32)
+            self._conv([(n16, w_qkv)], H, W, 3 * C, want_stats=False, out=qkv32, bias=b_qkv)
+            self.steps.append(lambda: ops.split16(qkv32, qkv[0], qkv[1]))
+            self.steps.append(lambda: ops.attention_split(qkv[0].view(B, T, 3 * C), qkv[1].view(B, T, 3 * C), B, T, heads, d,
+                                                          order=order, out=o32.view(B, T, C)))
+            self.steps.append(lambda: ops.split16(o32, o16[0], o16[1]))
+            pool.put(qkv32); pool.put(o32)
+        else:
+            qkv = pool.get((B, H, W, 3 * C), self.dt16)
+            self._conv([(n16, w_qkv)], H, W, 3 * C, want_stats=False, out=qkv, bias=b_qkv, out_kind=L.OUT_F16_NHWC)
+            self.steps.append(lambda: ops.attention(qkv.view(B, T, 3 * C), B, T, heads, d, order=order,
+                                                    out=o16.view(B, T, C), fmt=fmt))
         out = self._conv([(o16, w_proj)], H, W, C, want_stats=True, bias=b_proj, residual=x.t,
                          residual_mode=L.RES_SAME)
         for t in (n16, qkv, o16):
-            pool.put(t)
+            self._free16(t)
         return out
 
     def _upsample(self, layer, x):
@@ -437,11 +508,14 @@ class UNetEngine:
             self._emit_stats_kernel(up, act.stats)
             return act
         Cout = layer.conv.weight.shape[0]
-        a = pool.get((B, 2 * H, 2 * W, C), self.dt16)
+        a = self._new16((B, 2 * H, 2 * W, C))
         wp = self._packed(layer.conv, 'weight'); bp = self._copy_param(layer.conv, 'bias')
-        self.steps.append(lambda: ops.cast16(up, out=a, fmt=fmt))
+        if self.split:
+            self.steps.append(lambda: ops.split16(up, a[0], a[1]))
+        else:
+            self.steps.append(lambda: ops.cast16(up, out=a, fmt=fmt))
         out = self._conv([(a, wp)], 2 * H, 2 * W, Cout, want_stats=True, bias=bp)
-        pool.put(up); pool.put(a)
+        pool.put(up); self._free16(a)
         return out
 
     def _downsample(self, layer, x):
@@ -454,6 +528,9 @@ class UNetEngine:
             act = _Act(out, self._stats_buf(C))
             self._emit_stats_kernel(out, act.stats)
             return act
+        if self.split:
+            raise L.NdbError('fp32-class mode: the strided Downsample conv (nine K segments, 27 with split operands) is not '
+                             'supported; use resblock_updown=True or conv_resample=False')
         Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
         Cout = layer.conv.weight.shape[0]
         cols = pool.get((9, B, Ho, Wo, C), self.dt16)

@@ -54,9 +54,9 @@ def pad16(n):
     return (n + 15) // 16 * 16
 
 
-def pack_conv_weight(w, cout_pad=None, cin_off=0, cin_len=None, fmt=L.FMT_FP16, out=None):
+def pack_conv_weight(w, cout_pad=None, cin_off=0, cin_len=None, fmt=L.FMT_FP16, out=None, scale=1.0, part=0):
     """nn.Conv2d / Conv1d / Linear weight (fp32, [cout, cin, k, k] | [cout, cin, 1] | [cout, cin]) ->
-    [taps][cout_pad][cin_len] 16-bit."""
+    [taps][cout_pad][cin_len] 16-bit rounding of w * scale (part 0) or the fp16 remainder of that rounding (part 1)."""
     L.require_device(w, 'pack_conv_weight')
     w = w.detach().contiguous().float()
     cout, cin = w.shape[0], w.shape[1]
@@ -69,15 +69,16 @@ def pack_conv_weight(w, cout_pad=None, cin_off=0, cin_len=None, fmt=L.FMT_FP16, 
         out = torch.empty((k * k, cout_pad, cin_len), dtype=dtype16(fmt), device=w.device)
     _begin()
     L.check(L.load().ndb_pack_conv_weight(L.ptr(w), L.ptr(out), cout, cin, k, cout_pad, cin_off, cin_len, fmt,
-                                          L.stream_ptr()), 'ndb_pack_conv_weight')
+                                          float(scale), int(part), L.stream_ptr()), 'ndb_pack_conv_weight')
     _count('pack_conv_weight')
     return out
 
 
 def conv_gemm(segments, N, H, W, cout, bias=None, residual=None, residual_mode=L.RES_NONE,
               out_kind=L.OUT_F32_NHWC, out=None, fmt=L.FMT_FP16, block_n=0, cout_pad=None,
-              stats=None):
-    """segments: list of (act16 [N,H,W,C], packed_weight [taps,cout_pad,C]).  Returns `out`."""
+              stats=None, out_scale=1.0, acc_chunk=0):
+    """segments: list of (act16 [N,H,W,C], packed_weight [taps,cout_pad,C]).  Returns `out`.
+    out_scale: power of two applied to the accumulators before bias / residual (fp32-class mode: 1 / SPLIT_WEIGHT_SCALE)."""
     p = L.ConvParams()
     p.N, p.H, p.W = N, H, W
     p.cout = cout
@@ -108,6 +109,8 @@ def conv_gemm(segments, N, H, W, cout, bias=None, residual=None, residual_mode=L
     p.out = out.data_ptr()
     p.operand_format = fmt
     p.block_n = block_n
+    p.out_scale = float(out_scale)
+    p.acc_chunk_kblocks = int(acc_chunk)
     if stats is not None:
         parts = stats[0]   # float32 [N, smax, cout, 2]
         assert parts.dtype == torch.float32 and parts.shape[0] == N and parts.shape[2] == cout and parts.shape[3] == 2
@@ -125,14 +128,14 @@ def conv_stats_supported(N, H, W):
     return bool(L.load().ndb_conv_stats_supported(N, H, W))
 
 
-def conv_stats_alloc(N, H, W, cout, device, k_total, cout_pad=None, block_n=0):
+def conv_stats_alloc(N, H, W, cout, device, k_total, cout_pad=None, block_n=0, acc_chunk=0):
     """Buffers for the statistics a conv epilogue writes for its output: (parts float32 [N, smax, cout, 2],
     counts int32 [N]) -- see ndb_conv_stats_layout. k_total = reduction length of the GEMM that will write them
     (sum over its segments of taps * C): it selects the kernel variant and with it the slot layout."""
     import ctypes
     cp = pad16(cout) if cout_pad is None else cout_pad
     counts = (ctypes.c_int32 * N)()
-    smax = int(L.load().ndb_conv_stats_layout(N, H, W, cp, block_n, int(k_total), counts))
+    smax = int(L.load().ndb_conv_stats_layout(N, H, W, cp, block_n, int(k_total), int(acc_chunk), counts))
     if smax < 1:
         raise L.NdbError('ndb_conv_stats_layout failed ({})'.format(smax))
     parts = torch.zeros((N, smax, cout, 2), dtype=torch.float32, device=device)
@@ -182,7 +185,9 @@ def stats_totals(stats):
 
 
 def gn_apply(x0, stats0, gamma, beta, x1=None, stats1=None, scale=None, shift=None, pre_add=None, silu=True,
-             resample=L.RESAMPLE_NONE, out=None, raw16=None, want_raw16=False, fmt=L.FMT_FP16, eps=1e-5, pool32=None, cpg=0):
+             resample=L.RESAMPLE_NONE, out=None, raw16=None, want_raw16=False, fmt=L.FMT_FP16, eps=1e-5, pool32=None, cpg=0,
+             out_lo=None, raw_lo=None):
+    """out_lo / raw_lo (fp32-class mode): tensors like out / raw16 that receive the fp16 remainders."""
     L.require_device(x0, 'gn_apply')
     N, H, W, C0 = x0.shape
     C1 = x1.shape[-1] if x1 is not None else 0
@@ -216,6 +221,8 @@ def gn_apply(x0, stats0, gamma, beta, x1=None, stats1=None, scale=None, shift=No
     p.resample = resample
     p.out = out.data_ptr()
     p.raw16 = raw16.data_ptr() if raw16 is not None else None
+    p.out_lo = out_lo.data_ptr() if out_lo is not None else None
+    p.raw_lo = raw_lo.data_ptr() if raw_lo is not None else None
     p.pool32 = pool32.data_ptr() if pool32 is not None else None
     p.operand_format = fmt
     p.eps = eps
@@ -239,6 +246,19 @@ def attention(qkv16, B, T, heads, d, order=0, out=None, fmt=L.FMT_FP16):
     L.check(L.load().ndb_attention(L.ptr(qkv16), L.ptr(out), B, T, heads, d, order, fmt, L.stream_ptr()),
             'ndb_attention')
     _count('attention', 4 * B * heads * T * T * d, 'B{} T{} h{} d{}'.format(B, T, heads, d))
+    return out
+
+
+def attention_split(qkv_hi, qkv_lo, B, T, heads, d, order=0, out=None):
+    """fp32-class attention: qkv as fp16 (hi, lo) pairs [B,T,3C] -> fp32 [B,T,C]."""
+    L.require_device(qkv_hi, 'attention_split')
+    assert qkv_hi.is_contiguous() and qkv_lo.is_contiguous() and qkv_hi.dtype == torch.float16 and qkv_lo.dtype == torch.float16
+    if out is None:
+        out = torch.empty((B, T, heads * d), dtype=torch.float32, device=qkv_hi.device)
+    _begin()
+    L.check(L.load().ndb_attention_split(L.ptr(qkv_hi), L.ptr(qkv_lo), L.ptr(out), B, T, heads, d, order, L.stream_ptr()),
+            'ndb_attention_split')
+    _count('attention', 3 * 4 * B * heads * T * T * d, 'B{} T{} h{} d{} split'.format(B, T, heads, d))
     return out
 
 
@@ -330,6 +350,20 @@ def cast16(x, out=None, fmt=L.FMT_FP16):
     L.check(L.load().ndb_cast_nhwc16(L.ptr(x), L.ptr(out), x.numel(), fmt, L.stream_ptr()), 'ndb_cast_nhwc16')
     _count('cast_nhwc16')
     return out
+
+
+def split16(x, hi=None, lo=None, silu=False):
+    """fp32 -> fp16 pair (hi, lo) with hi + lo == x to ~2^-22 relative (fp32-class mode operands)."""
+    L.require_device(x, 'split16')
+    x = x.contiguous()
+    if hi is None:
+        hi = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    if lo is None:
+        lo = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    _begin()
+    L.check(L.load().ndb_split16(L.ptr(x), L.ptr(hi), L.ptr(lo), x.numel(), 1 if silu else 0, L.stream_ptr()), 'ndb_split16')
+    _count('split16')
+    return hi, lo
 
 
 def im2col_s2(x, out=None, fmt=L.FMT_FP16):

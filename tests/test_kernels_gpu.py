@@ -628,3 +628,93 @@ def test_conv_16bit_output_with_fused_statistics(cuda_dev, N, H, W, Cin, Cout):
     y = ops.gn_apply(out, st, gamma, beta, silu=True)
     refn = F.silu(F.group_norm(out.float().permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-5))
     assert rel_err(y.permute(0, 3, 1, 2), refn) < 2e-3
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# fp32-class mode building blocks: (hi, lo) fp16 operand pairs, three products per GEMM
+# ----------------------------------------------------------------------------------------------------------------------
+def test_fp32_class_kernels(cuda_dev):
+    ops, L = _ops()
+    d = cuda_dev
+    g = torch.Generator(device='cpu').manual_seed(2024)
+    S = L.SPLIT_WEIGHT_SCALE
+    # split16: hi + lo reproduces x to ~2^-22 relative for O(1) values (and to the fp16 subnormal floor 2^-25 absolutely)
+    x = (torch.randn(4096, generator=g) * 3).to(d)
+    hi, lo = ops.split16(x)
+    rec = hi.float() + lo.float()
+    # 2^-22 relative, down to the fp16 subnormal spacing (2^-24) for values whose low half underflows
+    assert bool(((rec - x).abs() <= torch.maximum(x.abs() * 2.0 ** -21, torch.full_like(x, 2.0 ** -24))).all())
+    hs, ls = ops.split16(x, silu=True)
+    assert rel_err(hs.float() + ls.float(), F.silu(x)) < 5e-7
+    # conv as three K segments vs the fp32 convolution (TF32 off): fp32-class agreement
+    N, H, W, Cin, Cout = 3, 16, 16, 128, 192
+    xc = torch.randn(N, Cin, H, W, generator=g).to(d)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)).to(d)
+    b = (0.1 * torch.randn(Cout, generator=g)).to(d)
+    r = torch.randn(N, Cout, H, W, generator=g).to(d)
+    a_hi, a_lo = ops.split16(nhwc(xc))
+    w_hi = ops.pack_conv_weight(w, scale=S, part=0)
+    w_lo = ops.pack_conv_weight(w, scale=S, part=1)
+    assert float((w_hi.float() + w_lo.float())[4, :Cout].sub(w[:, :, 1, 1] * S).abs().max()) < 1e-4 * S * 1e-2
+    st = ops.conv_stats_alloc(N, H, W, Cout, d, 3 * Cin * 9, acc_chunk=L.SPLIT_ACC_CHUNK)
+    out = ops.conv_gemm([(a_hi, w_hi), (a_lo, w_hi), (a_hi, w_lo)], N, H, W, Cout, bias=b, residual=nhwc(r),
+                        residual_mode=L.RES_SAME, stats=st, out_scale=1.0 / S, acc_chunk=L.SPLIT_ACC_CHUNK)
+    o = out.double().flatten(1, 2)
+    assert torch.allclose(ops.stats_totals(st)[:, :, 0], o.sum(1), rtol=1e-5, atol=2e-3)
+    ref = (F.conv2d(xc.cpu().double(), w.cpu().double(), b.cpu().double(), padding=1) + r.cpu().double()).float().to(d)
+    e = rel_err(out.permute(0, 3, 1, 2), ref)
+    e_f32 = rel_err(F.conv2d(xc, w, b, padding=1) + r, ref)
+    e_cpu = rel_err((F.conv2d(xc.cpu(), w.cpu(), b.cpu(), padding=1) + r.cpu()).to(d), ref)
+    print('split conv err', e, '(torch fp32 conv vs fp64: cuda', e_f32, 'cpu', e_cpu, ')')
+    # error vs reduction length (tensor-core fp32 accumulation), 1x1 convs on 8x8 images
+    for K in (256, 1024, 4096, 16384):
+        xa_ = torch.randn(2, K, 8, 8, generator=g).to(d)
+        wa_ = (torch.randn(64, K, 1, 1, generator=g) / math.sqrt(K)).to(d)
+        ah, al = ops.split16(nhwc(xa_))
+        o_ = ops.conv_gemm([(ah, ops.pack_conv_weight(wa_, scale=S, part=0)), (al, ops.pack_conv_weight(wa_, scale=S, part=0)),
+                            (ah, ops.pack_conv_weight(wa_, scale=S, part=1))], 2, 8, 8, 64, out_scale=1.0 / S,
+                           acc_chunk=L.SPLIT_ACC_CHUNK)
+        o1 = ops.conv_gemm([(ah, ops.pack_conv_weight(wa_, scale=S, part=0)), (al, ops.pack_conv_weight(wa_, scale=S, part=0)),
+                            (ah, ops.pack_conv_weight(wa_, scale=S, part=1))], 2, 8, 8, 64, out_scale=1.0 / S, out_kind=L.OUT_F32_NCHW,
+                           acc_chunk=L.SPLIT_ACC_CHUNK)
+        assert torch.equal(o1, o_.permute(0, 3, 1, 2))                  # the per-row-store epilogue adds the same chunks
+        r64 = F.conv2d(xa_.cpu().double(), wa_.cpu().double()).float().to(d)
+        print('  K', K, 'split err', rel_err(o_.permute(0, 3, 1, 2), r64), 'torch fp32 err', rel_err(F.conv2d(xa_, wa_), r64),
+              'mean signed rel', float(((o_.permute(0, 3, 1, 2) - r64) * r64.sign()).mean() / r64.abs().mean()))
+    assert e < 2e-6
+    # GroupNorm + exact SiLU -> (hi, lo)
+    C = 128
+    xa = nhwc(torch.randn(N, C, H, W, generator=g).to(d) * 1.5 + 0.3)
+    gamma = (1 + 0.1 * torch.randn(C, generator=g)).to(d)
+    beta = (0.1 * torch.randn(C, generator=g)).to(d)
+    stats = ops.gn_stats(xa)
+    y_hi = torch.empty(N, H, W, C, dtype=torch.float16, device=d); y_lo = torch.empty_like(y_hi)
+    r_hi = torch.empty_like(y_hi); r_lo = torch.empty_like(y_hi)
+    ops.gn_apply(xa, stats, gamma, beta, silu=True, out=y_hi, out_lo=y_lo, raw16=r_hi, raw_lo=r_lo)
+    refn = F.silu(F.group_norm(xa.permute(0, 3, 1, 2).double(), 32, gamma.double(), beta.double(), eps=1e-5)).float()
+    e = rel_err((y_hi.float() + y_lo.float()).permute(0, 3, 1, 2), refn)
+    print('split groupnorm err', e)
+    assert e < 2e-6
+    assert rel_err(r_hi.float() + r_lo.float(), xa) < 5e-7
+    for rs in (L.RESAMPLE_UP2, L.RESAMPLE_DOWN2):
+        Ho = 2 * H if rs == L.RESAMPLE_UP2 else H // 2
+        u_hi = torch.empty(N, Ho, Ho, C, dtype=torch.float16, device=d); u_lo = torch.empty_like(u_hi)
+        ops.gn_apply(xa, stats, gamma, beta, silu=True, resample=rs, out=u_hi, out_lo=u_lo)
+        want = F.interpolate(refn, scale_factor=2.0, mode='nearest') if rs == L.RESAMPLE_UP2 else F.avg_pool2d(refn, 2)
+        assert rel_err((u_hi.float() + u_lo.float()).permute(0, 3, 1, 2), want) < 2e-6
+    # attention with split operands vs fp64 softmax attention
+    for (B, T, heads, dh, order) in [(2, 196, 2, 64, 0), (1, 320, 3, 32, 1), (2, 64, 4, 64, 0)]:
+        Cc = heads * dh
+        qkv = torch.randn(B, T, 3 * Cc, generator=g).to(d)
+        q_hi, q_lo = ops.split16(qkv)
+        o = ops.attention_split(q_hi, q_lo, B, T, heads, dh, order=order)
+        f = qkv.double()
+        if order == 0:
+            q, k, v = f.reshape(B, T, 3, heads, dh).permute(2, 0, 3, 1, 4).unbind(0)
+        else:
+            q, k, v = f.reshape(B, T, heads, 3, dh).permute(3, 0, 2, 1, 4).unbind(0)
+        wgt = torch.softmax((q @ k.transpose(2, 3)) * dh ** -0.5, dim=-1)
+        refa = (wgt @ v).transpose(1, 2).reshape(B, T, Cc).float()
+        e = rel_err(o, refa)
+        print('split attention err', (B, T, heads, dh, order), e)
+        assert o.dtype == torch.float32 and e < 3e-6

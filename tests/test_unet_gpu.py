@@ -135,3 +135,37 @@ def test_full_size_batch_properties_in64(cuda_dev):
         assert norm_err(full[pos:pos + n].cpu(), ref) < TOL
     assert norm_err(full[5:7].cpu(), pair.cpu()) < 1.5e-3
     assert torch.isfinite(full).all()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# fp32-class mode (BASELINE north_star: "1e-5 in fp32 mode")
+# ----------------------------------------------------------------------------------------------------------------------
+TOL32 = 1e-5
+
+
+@pytest.mark.parametrize('name', ['tiny', 'tiny_pool', 'emnist', 'in64'])
+def test_forward_fp32_class_matches_reference_golden(cuda_dev, name):
+    """model.operand_format = FMT_FP32X: every tensor-core product as three fp16 MMAs (hi hi + lo hi + hi lo), accurate
+    SiLU / softmax exponentials, fp32 everywhere else. Bar: max|out - ref| / max|ref| <= 1e-5 against the reference's own fp32
+    output (the reference differs from an fp64 evaluation of itself by 5e-7..9e-7)."""
+    from nice_diffusion_b200 import _lib as L
+    cfg, sd, model = build(name, 1234, cuda_dev)
+    model.operand_format = L.FMT_FP32X
+    g = np.load(os.path.join(GOLD, 'unet_{}.npz'.format(name)))
+    x = torch.from_numpy(g['x']).to(cuda_dev)
+    t = torch.from_numpy(g['t']).to(cuda_dev)
+    y = torch.from_numpy(g['y']).to(cuda_dev) if 'y' in g.files else None
+    with torch.no_grad():
+        out = model(x, t, y) if y is not None else model(x, t)
+    ref = torch.from_numpy(g['out'])
+    err = norm_err(out.cpu(), ref)
+    print(name, 'fp32-class max|d|/max|ref| =', err)
+    assert err < TOL32
+    h = ref.shape[1] // 2
+    assert norm_err(out.cpu()[:, :h], ref[:, :h]) < TOL32 and norm_err(out.cpu()[:, h:], ref[:, h:]) < TOL32
+    # switching back restores the 16-bit plan (and its error level)
+    model.operand_format = L.FMT_FP16
+    with torch.no_grad():
+        out16 = model(x, t, y) if y is not None else model(x, t)
+    e16 = norm_err(out16.cpu(), ref)
+    assert TOL32 < e16 < TOL
