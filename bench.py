@@ -258,6 +258,126 @@ def oracle_port_arm(workload, steps, warmup, sample_batch=None):
                            steps, warmup, workload, sample_batch, per_image), batch=sample_batch)
 
 
+TRAIN_WORKLOADS = {
+    # BASELINE config 5: hybrid-loss training step, synthetic batches, data-parallel gradient all-reduce over NCCL
+    # name: (model preset, per-GPU batch); T = R = 1000 (the setting the reference's trainer needs)
+    'train_emnist': ('emnist', 468),      # batch size of the reference's scripts/train.py:25
+    'train_in64': ('in64', 32),
+}
+
+
+def train_arm(args, rank, world, local_rank):
+    """One training step = q-sample + differentiable forward + fused loss kernel + backward (bucketed NCCL all-reduce
+    overlapped with it) + AdamW + EMA, through nice_diffusion_b200.trainer.Trainer on synthetic host batches."""
+    import numpy as np
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    from nice_diffusion_b200 import ops
+    from nice_diffusion_b200.model import DiffusionModel
+    from nice_diffusion_b200.train_forward import count_flops
+    from nice_diffusion_b200.trainer import Trainer
+    from nice_diffusion_b200.utils import randomize_zero_init_
+    preset, B = TRAIN_WORKLOADS[args.config]
+    if args.batch:
+        B = args.batch
+    cfg = model_config(preset)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = randomize_zero_init_(DiffusionModel(**cfg), seed=0)
+    dargs = dict(original_num_steps=1000, rescaled_num_steps=1000, beta_schedule='cosine',
+                 sampling_var_type='learned_interpolation', loss_type='hybrid', guidance_method='classifier_free',
+                 guidance_strength=0.8)
+    trainer = Trainer(model=model, diffusion_args=dargs, dataloader=None, iterations=0, batch_size=B, lr=1e-4,
+                      weight_decay=0.001, device=dev, ema_clone=True)
+    g = torch.Generator().manual_seed(100 + rank)
+    x_host = (torch.rand(B, cfg['in_channels'], cfg['resolution'], cfg['resolution'], generator=g) * 2 - 1).pin_memory()
+    y_host = torch.randint(1, cfg['num_classes'], (B,), generator=g).pin_memory()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step(i):
+        x = x_host.to(dev, non_blocking=True)
+        y = y_host.to(dev, non_blocking=True)
+        return trainer.train_step(x, y, step=i)
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    loss = None
+    for i in range(args.steps):
+        loss = step(i)
+    loss_host = float(loss.item())                 # the step's result crosses back to the host inside the timed region
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    ms_per_step = ms / args.steps
+    # the gradient exchange alone (same buckets, nothing to overlap with): achieved bus bandwidth
+    ar = None
+    if dist is not None:
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        a0.record()
+        for _ in range(reps):
+            works = [dist.all_reduce(b['flat'], async_op=True) for b in trainer.buckets.buckets]
+            for w in works:
+                w.wait()
+        a1.record()
+        barrier()
+        ar_ms = a0.elapsed_time(a1) / reps
+        nbytes = trainer.buckets.bytes
+        ar = {'bytes': nbytes, 'buckets': len(trainer.buckets.buckets), 'ms': ar_ms,
+              'bus_gbs': 2.0 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9,
+              'what': 'all-reduce of the fp32 gradient buckets alone; bus bandwidth = 2 (N-1)/N x bytes / time'}
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    fwd = count_flops(model, B)
+    tflops = 3.0 * fwd / (ms_per_step * 1e-3) / 1e12
+    value = world * B / (ms_per_step * 1e-3)
+    line = {'metric': 'images/sec (hybrid-loss training step, {} UNet)'.format(preset), 'value': value, 'unit': 'images/sec',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 (torch defaults: cuDNN convolutions may use TF32, matmuls fp32)', 'data': 'synthetic',
+            'config': {'workload': '{}: hybrid loss, T = R = 1000, cosine schedule, AdamW, EMA, per-GPU batch {} (global {})'.format(
+                args.config, B, B * world), 'per_gpu_batch': B, 'global_batch': B * world,
+                'parallelism': 'data parallel x{}: replicas, bucketed NCCL all-reduce of {} MB of fp32 gradients overlapped '
+                               'with backward'.format(world, trainer.buckets.bytes >> 20),
+                'forward': 'differentiable torch forward over the model parameters (train_forward.py) + fused ndb200 loss kernel',
+                'l2': 'weights + activations >> L2'},
+            'clocks': clk,
+            'e2e': {'value': value, 'unit': 'images/sec', 'h2d_bytes_per_step': x_host.numel() * 4 + y_host.numel() * 8,
+                    'd2h_bytes_per_step': 4, 'what': 'the timed loop IS the public API (Trainer.train_step) fed from pinned host '
+                                                     'batches; the last loss is read back inside the timed region'},
+            'gpu_launches': ops.LAUNCHES - launches0,
+            'roofline': {'bound': 'tensor', 'achieved': tflops, 'peak': pk['bf16_sustained'], 'unit': 'TFLOP/s',
+                         'frac': tflops / pk['bf16_sustained'], 'traffic': None,
+                         'what': '3 x forward FLOPs (forward + input- and weight-gradient GEMMs) / step time; fp32 torch '
+                                 'kernels, so the bf16 tensor peak is an upper bound they cannot reach'},
+            'allreduce': ar, 'loss': loss_host, 'cpu_baseline': None}
+    _emit(line)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 _REAL_STDOUT = None
 
 
@@ -285,7 +405,7 @@ def main():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', type=str, default='ndb200', choices=['ndb200', 'reference'])
-    ap.add_argument('--config', type=str, default='in64', choices=sorted(WORKLOADS))
+    ap.add_argument('--config', type=str, default='in64', choices=sorted(WORKLOADS) + sorted(TRAIN_WORKLOADS))
     ap.add_argument('--batch', type=int, default=None, help='per-GPU batch (default: the BASELINE value)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--eager', action='store_true', help='launch kernels one by one instead of replaying CUDA graphs (profiling)')
@@ -300,6 +420,14 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.config in TRAIN_WORKLOADS:
+        if args.impl == 'reference':
+            if rank == 0:
+                _emit({'impl': 'reference', 'unavailable': 'the training configs have no CPU reference arm (use --config in64)'})
+            return
+        if not torch.cuda.is_available():
+            raise SystemExit('bench.py: no CUDA device')
+        return train_arm(args, rank, world, local_rank)
     cname, dkw, B, per_image = WORKLOADS[args.config]
     if args.batch:
         B = args.batch

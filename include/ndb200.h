@@ -222,7 +222,9 @@ int ndb_im2col_s2(const float* x, void* out, int N, int H, int W, int C, int ope
 #define NDB_TAB_ABAR 6
 #define NDB_TAB_ABAR_PREV 7
 #define NDB_TAB_SQRT_1M_ABAR 8
-#define NDB_TAB_COUNT 9
+#define NDB_TAB_LOG_POST_VAR_CLIPPED 9   /* log_posterior_var_clipped for every variance type (the true log-variance of the
+                                            variational bound, diffusion.py:409); sampling does not read it */
+#define NDB_TAB_COUNT 10
 
 #define NDB_VAR_FIXED 0          /* 'small' / 'large': log_var = tables[LOGVAR_MIN][t] */
 #define NDB_VAR_LEARNED 1        /* log_var = v */
@@ -269,6 +271,26 @@ int ndb_qsample(const float* x0, const float* noise, const float* t, const float
  * gray_invert (C == 1 only): the byte the reference CLI ends up storing for one-channel models -- it inverts the float
  * image (sample.py:98-100), truncates (:168) and inverts again (:170-171): 255 - trunc(255 - v). */
 int ndb_to_uint8(const float* x_nchw, uint8_t* out_nhwc, int B, int C, int H, int W, int gray_invert, void* stream);
+
+/* ---- fused training loss, forward + gradient ------------------------------------------------------------------------
+ * Replaces Diffusion.loss / variational_lower_bound / kl_div / log_likelihood / approx_cdf / mean_flat
+ * (diffusion.py:375-438, 499-549) GIVEN the model output: per-sample loss[b] and grad_out = d loss[b] / d model_out.
+ * x0, x_t, noise: [B][C][H][W]; model_out: [B][Cm][H][W] (Cm = 2C with a learned variance); t: [B] fp32 step index into
+ * the tables (the trainer draws it in [0, original_num_steps), diffusion.py:88 of trainer.py -- tables must be that long).
+ * loss_type: 0 simple, 1 KL, 2 KL_rescaled, 3 hybrid (eps detached inside the bound, weight 0.001 * rescaled_num_steps). */
+typedef struct {
+    const float* x0; const float* x_t; const float* noise; const float* model_out;
+    const float* t; const float* tables;
+    int32_t R, B, C, HW, Cm;
+    int32_t var_type;              /* NDB_VAR_* */
+    int32_t loss_type;
+    int32_t rescaled_num_steps;
+    float* loss;                   /* [B] */
+    float* grad_out;               /* [B][Cm][HW] or NULL */
+} ndb_loss_params;
+int ndb_diffusion_loss(const ndb_loss_params* p, void* stream);
+/* g[r][:] *= upstream[r]: chain rule of the per-sample loss vector (backward of ndb_diffusion_loss) */
+int ndb_scale_rows(float* g, const float* upstream, int64_t rows, int64_t per_row, void* stream);
 
 /* measurement aid: writes the device's %globaltimer (ns) to *dst when everything enqueued before it on `stream` has
  * completed (scripts/timeline.py brackets every launch of a step with these, inside the step's CUDA graph). */

@@ -19,7 +19,8 @@ OUT_F32_NHWC, OUT_F16_NHWC, OUT_F32_NCHW = 0, 1, 2
 RESAMPLE_NONE, RESAMPLE_UP2, RESAMPLE_DOWN2 = 0, 1, 2
 VAR_FIXED, VAR_LEARNED, VAR_LEARNED_INTERP = 0, 1, 2
 (TAB_SQRT_RECIP_ABAR, TAB_SQRT_RECIPM1_ABAR, TAB_POST_COEF_X0, TAB_POST_COEF_XT, TAB_LOGVAR_MIN,
- TAB_LOGVAR_MAX, TAB_ABAR, TAB_ABAR_PREV, TAB_SQRT_1M_ABAR, TAB_COUNT) = range(10)
+ TAB_LOGVAR_MAX, TAB_ABAR, TAB_ABAR_PREV, TAB_SQRT_1M_ABAR, TAB_LOG_POST_VAR_CLIPPED, TAB_COUNT) = range(11)
+LOSS_SIMPLE, LOSS_KL, LOSS_KL_RESCALED, LOSS_HYBRID = 0, 1, 2, 3
 
 FMT_FP16, FMT_BF16 = 0, 1
 # fp32-class mode of the model (DiffusionModel.operand_format): every tensor-core operand is an fp16 (hi, lo) pair and every
@@ -71,6 +72,14 @@ class StepParams(C.Structure):
                 ('x_prev', C.c_void_p), ('x_prev2', C.c_void_p), ('pred_x0', C.c_void_p)]
 
 
+class LossParams(C.Structure):
+    _fields_ = [('x0', C.c_void_p), ('x_t', C.c_void_p), ('noise', C.c_void_p), ('model_out', C.c_void_p),
+                ('t', C.c_void_p), ('tables', C.c_void_p),
+                ('R', C.c_int32), ('B', C.c_int32), ('C', C.c_int32), ('HW', C.c_int32), ('Cm', C.c_int32),
+                ('var_type', C.c_int32), ('loss_type', C.c_int32), ('rescaled_num_steps', C.c_int32),
+                ('loss', C.c_void_p), ('grad_out', C.c_void_p)]
+
+
 # name -> (restype, argtypes); must list every symbol include/ndb200.h declares (tests check this)
 _I, _P, _I64, _U64 = C.c_int, C.c_void_p, C.c_int64, C.c_uint64
 SIGNATURES = {
@@ -99,6 +108,8 @@ SIGNATURES = {
     'ndb_qsample': (_I, [_P, _P, _P, _P, _P, _P, _I, _I64, _P]),
     'ndb_to_uint8': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     'ndb_timestamp': (_I, [_P, _P]),
+    'ndb_diffusion_loss': (_I, [C.POINTER(LossParams), _P]),
+    'ndb_scale_rows': (_I, [_P, _P, _I64, _I64, _P]),
 }
 
 _lib = None

@@ -14,7 +14,8 @@ assertion behaviour. Underneath:
     generates it inside the step kernel keyed by (seed, global sample id, step) so that sharding the batch over
     GPUs does not change any sample; an explicit `[R,B,C,H,W]` tensor injects noise (parity tests).
 
-Training (`loss`) is not part of this path yet and raises NotImplementedError.
+Training: `loss` (fused loss + gradient kernel over a differentiable model forward) and `trainer.Trainer`
+(data-parallel gradient exchange over NCCL), SURVEY.md section 8 f-1 / e-2.
 """
 import math
 
@@ -147,6 +148,7 @@ class Diffusion:
             rows[L.TAB_ABAR] = self.alphas_cumprod
             rows[L.TAB_ABAR_PREV] = self.alphas_cumprod_prev
             rows[L.TAB_SQRT_1M_ABAR] = self.sqrt_one_minus_alphas_cumprod
+            rows[L.TAB_LOG_POST_VAR_CLIPPED] = self.log_posterior_var_clipped
             tab = np.stack([np.asarray(r, dtype=np.float64) for r in rows]).reshape(L.TAB_COUNT, n)
             cached = self._tables_dev[self.sampling_var_type] = dict(
                 tab=torch.from_numpy(tab).float().to(self.device).contiguous(),
@@ -342,8 +344,54 @@ class Diffusion:
 
     # ------------------------------------------------------------------------------------------
     def loss(self, x_0, t, kwargs=None, noise=None):
-        raise NotImplementedError('training loss (reference diffusion.py:375-438) is outside the sampling hot path '
-                                  'built so far (SURVEY.md section 8 f-1)')
+        """Training loss per sample (diffusion.py:375-406): q-sample x_t (ndb_qsample), differentiable model forward
+        (train_forward.py when the model is in training mode), then ONE fused kernel for the simple / KL / KL_rescaled /
+        hybrid loss and its gradient w.r.t. the model output (`_FusedLoss`). `t` indexes this object's tables directly, like
+        the reference's `extract` -- a t beyond the respaced schedule raises IndexError there and here (the shipped
+        trainer draws t in [0, original_num_steps): it needs rescaled_num_steps == original_num_steps)."""
+        if kwargs is None:
+            kwargs = {}
+        x_0 = x_0.to(self.device, torch.float32).contiguous()
+        if noise is None:
+            noise = torch.randn_like(x_0).to(self.device)
+        noise = noise.to(self.device, torch.float32).contiguous()
+        t = t.to(self.device)
+        self._check_step_index(t, 'loss')
+        x_t = self.diffusion_step(x_0=x_0, t=t, noise=noise)
+        out = self.model(x_t, self.timestep_map[t.long()], **kwargs)
+        return _FusedLoss.apply(out, x_0, x_t, noise, t.float().contiguous(), self._tables()['tab'], self._var_code(),
+                                _LOSS_TYPES.index(self.loss_type), int(self.rescaled_num_steps))
+
+    def variational_lower_bound(self, x_0, x_t, t, eps_pred, log_var):
+        """diffusion.py:408-438, for callers that already hold eps / log_var (bits per dimension, per sample): the fused
+        kernel evaluated as the 'KL' loss on a (eps, log_var) pair presented as a learned-variance model output."""
+        out = torch.cat([eps_pred, log_var.expand_as(eps_pred)], dim=1).contiguous().float()
+        t = t.to(self.device)
+        self._check_step_index(t, 'variational_lower_bound')
+        return _FusedLoss.apply(out, x_0.contiguous().float(), x_t.contiguous().float(), torch.zeros_like(x_0),
+                                t.float().contiguous(), self._tables()['tab'], L.VAR_LEARNED, L.LOSS_KL,
+                                int(self.rescaled_num_steps))
+
+
+class _FusedLoss(torch.autograd.Function):
+    """loss[b] = ndb_diffusion_loss(...); backward: grad_out = (d loss_b / d model_out, written by the same kernel) times the
+    upstream gradient of loss[b]."""
+
+    @staticmethod
+    def forward(ctx, out, x_0, x_t, noise, t, tables, var_code, loss_code, steps):
+        out = out.contiguous()
+        need = out.requires_grad
+        loss, grad = ops.diffusion_loss(x_0, x_t, noise, out.detach(), t, tables, var_code, loss_code, steps, want_grad=need)
+        ctx.grad = grad
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        grad = ctx.grad
+        ctx.grad = None
+        if grad is None:
+            return (None,) * 9
+        return (ops.scale_rows_(grad, g_loss.contiguous().float()),) + (None,) * 8
 
 
 class _StepRunner:

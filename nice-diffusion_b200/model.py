@@ -10,7 +10,8 @@ What is mirrored from the reference:
     zero-initialised out_conv / proj_out / head conv, model.py:177,253,448,507-510);
   * `forward(x, timestep, y=None)`: NCHW fp32 in, `[B,out_channels,H,W]` fp32 out, the same two AssertionErrors.
 
-What is different: torch layers below are *parameter containers only* -- their forward is never called.
+What is different: in the sampling path the torch layers below are *parameter containers only* -- their forward is never
+called (the training step, `train_forward.py`, is the one place that evaluates them, to get autograd's backward).
 `forward` executes a static plan of ndb200 kernels (NHWC, fp16 tensor-core operands, fp32 accumulate / residual
 stream), captured into a CUDA graph per batch size. Parameters are snapshotted into a packed weight arena; the
 snapshot is refreshed automatically when any parameter's storage or version changes (load_state_dict, EMA
@@ -79,6 +80,7 @@ class ResidualBlock(UsesSteps):
         out_channels = out_channels if out_channels is not None else in_channels
         self.in_channels, self.out_channels = in_channels, out_channels
         self.use_adaptive_gn = use_adaptive_gn
+        self.dropout_p = dropout                # applied after the second SiLU in training mode only (model.py:182,208)
         self.mode = 'up' if upsample else ('down' if downsample else 'same')
         if out_channels == in_channels:
             self.skip = nn.Identity()
@@ -124,6 +126,7 @@ class DiffusionModel(nn.Module):
         step_embed_dim = 4 * model_channels
         self.model_channels = model_channels
         self.use_adaptive_gn = use_adaptive_gn
+        self.use_grad_checkpoints = use_grad_checkpoints
         self.step_embed = nn.Sequential(nn.Linear(model_channels, step_embed_dim), nn.SiLU(),
                                         nn.Linear(step_embed_dim, step_embed_dim))
         if num_classes is not None:
@@ -218,8 +221,10 @@ class DiffusionModel(nn.Module):
         assert x.shape[2] == self.resolution and x.shape[3] == self.resolution, \
             'incorrect resolution: {}'.format(x.shape[2:])
         if self.training and torch.is_grad_enabled():
-            raise NotImplementedError('ndb200 implements the sampling (inference) forward only; '
-                                      'call model.eval() / torch.no_grad()')
+            # training step: differentiable walk over the same parameters; sampling -- eval mode
+            # or no_grad, the path BASELINE measures -- always runs the kernel plan below
+            from .train_forward import train_forward
+            return train_forward(self, x, timestep, y)
         return self.engine_for(x).forward(x, timestep, y)
 
     def engine_for(self, x):

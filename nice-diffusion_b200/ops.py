@@ -463,3 +463,36 @@ def to_uint8(x_nchw, out=None, gray_invert=False):
 def timestamp(buf, index):
     """buf: int64 device tensor; element `index` <- %globaltimer once the stream has drained (not counted in LAUNCHES)."""
     L.check(L.load().ndb_timestamp(C.c_void_p(buf.data_ptr() + 8 * index), L.stream_ptr()), 'ndb_timestamp')
+
+
+def diffusion_loss(x0, x_t, noise, model_out, t, tables, var_type, loss_type, rescaled_num_steps, want_grad=True):
+    """Fused training loss: -> (loss [B], grad [B,Cm,H,W] = d loss_b / d model_out or None). See ndb_diffusion_loss."""
+    L.require_device(model_out, 'diffusion_loss')
+    B, Cc, H, W = x0.shape
+    for tns in (x0, x_t, noise, model_out):
+        assert tns.is_contiguous() and tns.dtype == torch.float32
+    assert t.dtype == torch.float32 and tables.dtype == torch.float32 and tables.shape[0] == L.TAB_COUNT
+    p = L.LossParams()
+    p.x0, p.x_t, p.noise, p.model_out = x0.data_ptr(), x_t.data_ptr(), noise.data_ptr(), model_out.data_ptr()
+    p.t, p.tables = t.data_ptr(), tables.data_ptr()
+    p.R, p.B, p.C, p.HW, p.Cm = tables.shape[1], B, Cc, H * W, model_out.shape[1]
+    p.var_type, p.loss_type, p.rescaled_num_steps = var_type, loss_type, int(rescaled_num_steps)
+    loss = torch.empty((B,), dtype=torch.float32, device=x0.device)
+    grad = torch.empty_like(model_out) if want_grad else None
+    p.loss = loss.data_ptr()
+    p.grad_out = grad.data_ptr() if grad is not None else None
+    _begin()
+    L.check(L.load().ndb_diffusion_loss(C.byref(p), L.stream_ptr()), 'ndb_diffusion_loss')
+    _count('diffusion_loss', 0, '', 4 * (4 * x0.numel() + model_out.numel() * (2 if want_grad else 1)))
+    return loss, grad
+
+
+def scale_rows_(g, upstream):
+    """g[b] *= upstream[b] in place (g: [B, ...] fp32 contiguous)."""
+    L.require_device(g, 'scale_rows')
+    assert g.is_contiguous() and upstream.is_contiguous() and upstream.dtype == torch.float32
+    _begin()
+    L.check(L.load().ndb_scale_rows(L.ptr(g), L.ptr(upstream), g.shape[0], g.numel() // g.shape[0], L.stream_ptr()),
+            'ndb_scale_rows')
+    _count('scale_rows')
+    return g

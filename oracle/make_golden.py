@@ -283,9 +283,89 @@ def main_big(only=None):
         print('big trajectory', name, 'bit-exact; emu16 final err', float((xe - x).abs().max()), flush=True)
 
 
+LOSS_CASES = {
+    # name: (config, diffusion kwargs incl. loss_type)
+    'hybrid_interp': ('tiny', dict(original_num_steps=100, rescaled_num_steps=100, beta_schedule='cosine',
+                                   sampling_var_type='learned_interpolation', loss_type='hybrid')),
+    'kl_learned': ('tiny', dict(original_num_steps=100, rescaled_num_steps=100, beta_schedule='linear',
+                                sampling_var_type='learned', loss_type='KL')),
+    'klr_interp': ('tiny', dict(original_num_steps=100, rescaled_num_steps=50, beta_schedule='cosine',
+                                sampling_var_type='learned_interpolation', loss_type='KL_rescaled')),
+    'simple_small': ('tiny_legacy', dict(original_num_steps=100, rescaled_num_steps=100, beta_schedule='linear',
+                                         sampling_var_type='small', loss_type='simple')),
+    'kl_large': ('tiny_legacy', dict(original_num_steps=100, rescaled_num_steps=100, beta_schedule='cosine',
+                                     sampling_var_type='large', loss_type='KL')),
+    'hybrid_emnist': ('emnist', dict(original_num_steps=1000, rescaled_num_steps=1000, beta_schedule='cosine',
+                                     sampling_var_type='learned_interpolation', loss_type='hybrid')),
+}
+
+
+def loss_case_inputs(name):
+    """Seeded inputs of a loss case (shared with the tests): x_0 in [-1, 1] with saturated pixels (the +-0.999 branches of
+    the discretised likelihood), t including 0 (the NLL branch), labels, injected noise."""
+    from oracle import CONFIGS
+    from oracle.big_cases import hash_name
+    cname, dkw = LOSS_CASES[name]
+    cfg = CONFIGS[cname]
+    rs = np.random.RandomState(hash_name('loss_' + name) % (2 ** 31))
+    B = 4
+    shape = (B, cfg['in_channels'], cfg['resolution'], cfg['resolution'])
+    x0 = np.clip(rs.uniform(-1.3, 1.3, shape), -1, 1).astype(np.float32)
+    noise = rs.standard_normal(shape).astype(np.float32)
+    R = dkw['rescaled_num_steps']
+    t = np.array([0, 1, R // 2, R - 1], dtype=np.int64)
+    y = rs.randint(1, cfg['num_classes'], size=(B,)).astype(np.int64) if cfg.get('num_classes') else None
+    return dict(x0=torch.from_numpy(x0), noise=torch.from_numpy(noise), t=torch.from_numpy(t),
+                y=torch.from_numpy(y) if y is not None else None)
+
+
+def main_loss():
+    """Training loss + gradients of the reference (train mode, dropout 0 or seeded) on seeded inputs; the oracle
+    (oracle/loss.py) asserted bit-exact for the loss values."""
+    from oracle import CONFIGS
+    from oracle.loss import LossOracle
+    from oracle.unet import unet_forward
+    from oracle.weights import random_state_dict
+    rm, rd = import_reference()
+    torch.set_num_threads(8)
+    dev = torch.device('cpu')
+    for name, (cname, dkw) in LOSS_CASES.items():
+        cfg = dict(CONFIGS[cname])
+        cfg['dropout'] = 0.0                      # dropout draws are not part of the parity contract
+        sd = random_state_dict(cfg, seed=777)
+        ref_model = rm.DiffusionModel(**cfg)
+        ref_model.load_state_dict(sd, strict=True)
+        ref = rd.Diffusion(model=ref_model, device=dev, **dkw)
+        ref_model.train()
+        inp = loss_case_inputs(name)
+        kwargs = {'y': inp['y']} if inp['y'] is not None else None
+        loss = ref.loss(x_0=inp['x0'], t=inp['t'], kwargs=kwargs, noise=inp['noise'])
+        total = loss.mean()
+        names = [n for n, _ in ref_model.named_parameters()]
+        grads = torch.autograd.grad(total, list(ref_model.parameters()), allow_unused=True)
+        # the model output the loss saw, and d loss.mean() / d out, for the kernel-level check
+        x_t = ref.diffusion_step(x_0=inp['x0'], t=inp['t'], noise=inp['noise'])
+        out = ref_model(x_t, ref.timestep_map[inp['t'].long()], **(kwargs or {})).detach().requires_grad_(True)
+        okw = {k: v for k, v in dkw.items() if k != 'loss_type'}
+        ora = LossOracle(lambda xx, tt, y=None: unet_forward(cfg, sd, xx, tt, y), dkw['loss_type'], **okw)
+        l2 = ora.loss_from_output(inp['x0'], x_t, inp['t'], out, inp['noise'])
+        assert torch.equal(l2.detach(), loss.detach()), (name, l2, loss)
+        g_out = torch.autograd.grad(l2.mean(), out)[0]
+        save = dict(loss=loss.detach().numpy(), out=out.detach().numpy(), x_t=x_t.numpy(), g_out=g_out.numpy())
+        # a few parameter gradients (first / middle / last tensors) as end-to-end anchors
+        pick = [0, len(names) // 2, len(names) - 2, len(names) - 1]
+        for i in pick:
+            if grads[i] is not None:
+                save['grad/' + names[i]] = grads[i].numpy()
+        np.savez_compressed(os.path.join(OUT, 'loss_{}.npz'.format(name)), **save)
+        print('loss', name, 'bit-exact;', loss.detach().numpy())
+
+
 if __name__ == '__main__':
     import sys
-    if len(sys.argv) > 1 and sys.argv[1] == 'big':
+    if len(sys.argv) > 1 and sys.argv[1] == 'loss':
+        main_loss()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'big':
         main_big(only=sys.argv[2].split(',') if len(sys.argv) > 2 else None)
     else:
         main(only_unet=sys.argv[1].split(',') if len(sys.argv) > 1 else None)
