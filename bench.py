@@ -34,17 +34,23 @@ WORKLOADS = {
     'emnist': ('emnist', dict(original_num_steps=1000, rescaled_num_steps=25, beta_schedule='cosine',
                               sampling_var_type='learned_interpolation', loss_type='hybrid',
                               guidance_method='classifier_free', guidance_strength=0.8), 16, 25),
+    # BASELINE config 4: classifier-guided ImageNet-64 sampling -- the gradient of an ADM-style noisy classifier (random-init,
+    # 41 M parameters; torch autograd, forward + input-backward) is taken every step INSIDE the per-step CUDA graph
+    'in64_clf': ('in64', dict(original_num_steps=1000, rescaled_num_steps=250, beta_schedule='cosine',
+                              sampling_var_type='learned_interpolation', loss_type='hybrid',
+                              guidance_method='classifier', guidance_strength=1.0), 32, 250),
     'in128': ('in128', dict(original_num_steps=1000, rescaled_num_steps=50, beta_schedule='linear',
                             sampling_var_type='learned_interpolation', loss_type='hybrid', use_ddim=True, ddim_eta=0.0,
                             guidance_method='classifier_free', guidance_strength=0.8), 8, 50),
 }
 # algorithmic FLOPs per image per UNet forward (counted on the reference modules)
-FLOPS_PER_FWD = {'in64': 219356037120, 'emnist': 3998584832, 'in128': 613855789056}
+FLOPS_PER_FWD = {'in64': 219356037120, 'emnist': 3998584832, 'in128': 613855789056, 'in64_clf': 219356037120}
 
 
 def model_config(name):
     from nice_diffusion_b200 import default_args as da
-    cfg = dict({'in64': da.OPENAI_64_MODEL_ARGS, 'emnist': da.EMNIST_MODEL_ARGS, 'in128': da.OPENAI_128_MODEL_ARGS}[name])
+    cfg = dict({'in64': da.OPENAI_64_MODEL_ARGS, 'emnist': da.EMNIST_MODEL_ARGS, 'in128': da.OPENAI_128_MODEL_ARGS,
+                'in64_clf': da.OPENAI_64_MODEL_ARGS}[name])
     if name == 'in128':
         cfg['num_classes'] = 1001  # CFG adds the null class (utils.py:211-212)
     return cfg
@@ -153,12 +159,17 @@ def real_reference_arm(ref, workload, steps, warmup, sample_batch):
     cname, dkw, _, per_image = WORKLOADS[workload]
     cfg = model_config(workload)
     if sample_batch is None:
-        sample_batch = {'in64': 2, 'emnist': 16, 'in128': 1}[workload]
+        sample_batch = {'in64': 2, 'emnist': 16, 'in128': 1, 'in64_clf': 2}[workload]
     torch.set_num_threads(max(1, host_cores()))
     torch.manual_seed(0)
     model = rm.DiffusionModel(**cfg)
     randomize_zero_init_(model, seed=0)
     cpu = torch.device('cpu')
+    if dkw.get('guidance_method') == 'classifier':
+        # the reference ships no classifier; its API takes any torch module -- the same NoisyClassifier the GPU arm uses
+        from nice_diffusion_b200.classifier import NoisyClassifier
+        dkw = dict(dkw, classifier=NoisyClassifier(64, 3, 128, 1000, 2, (32, 16, 8), channel_mult=(1, 2, 3, 4), num_head_channels=64,
+                                                   steps_scale=dkw['original_num_steps'] / dkw['rescaled_num_steps']))
     diff = rd.Diffusion(model=model, device=cpu, **dkw)
     x = torch.randn(sample_batch, cfg['in_channels'], cfg['resolution'], cfg['resolution'])
     y = torch.randint(1, cfg['num_classes'], (sample_batch,))
@@ -228,7 +239,7 @@ def oracle_port_arm(workload, steps, warmup, sample_batch=None):
     if workload == 'in128':
         cfg = dict(cfg); cfg['num_classes'] = 1001
     if sample_batch is None:
-        sample_batch = {'in64': 2, 'emnist': 16, 'in128': 1}[workload]
+        sample_batch = {'in64': 2, 'emnist': 16, 'in128': 1, 'in64_clf': 2}[workload]
     torch.set_num_threads(max(1, host_cores()))
     sd = random_state_dict(cfg, seed=0)
     okw = {k: v for k, v in dkw.items() if k != 'loss_type'}
@@ -432,7 +443,7 @@ def main():
     if args.batch:
         B = args.batch
     metric = 'images/sec ({} UNet, {}-step {} sampling)'.format(
-        {'in64': 'ImageNet-64', 'emnist': 'EMNIST', 'in128': 'ImageNet-128'}[args.config], per_image,
+        {'in64': 'ImageNet-64', 'emnist': 'EMNIST', 'in128': 'ImageNet-128', 'in64_clf': 'ImageNet-64 + noisy-classifier guidance'}[args.config], per_image,
         'DDIM' if dkw.get('use_ddim') else 'DDPM')
     config = {'workload': '{}: {} steps/image, {}, per-GPU batch {} (global {}), {}'.format(
         args.config, per_image, dkw['sampling_var_type'], B, B * world,
@@ -448,7 +459,7 @@ def main():
             return
         small = args.steps > 40
         r = cpu_reference_arm(args.config, args.steps, args.warmup,
-                              sample_batch=({'in64': 1, 'emnist': 16, 'in128': 1}[args.config] if small else None))
+                              sample_batch=({'in64': 1, 'emnist': 16, 'in128': 1, 'in64_clf': 1}[args.config] if small else None))
         # this arm's TRUE batch: a bounded sample of the workload on the host (one process, no GPUs)
         config = dict(config, workload=config['workload'] + ' -- CPU arm: bounded sample at batch {} on {} host threads'.format(
             r['batch'], r['cores']), per_gpu_batch=r['batch'], global_batch=r['batch'],
@@ -487,6 +498,11 @@ def main():
         config['operands'] = 'fp32-class: fp16 (hi, lo) operand pairs, three tensor-core products per multiply, K accumulated ' \
                              'in 128-element chunks added in fp32 round-to-nearest, fp32 residual stream'
     model.use_cuda_graph = not args.eager
+    if dkw.get('guidance_method') == 'classifier':
+        from nice_diffusion_b200.classifier import NoisyClassifier
+        dkw = dict(dkw, classifier=NoisyClassifier(64, 3, 128, 1000, 2, (32, 16, 8), channel_mult=(1, 2, 3, 4), num_head_channels=64,
+                                                   steps_scale=dkw['original_num_steps'] / dkw['rescaled_num_steps']))
+        config['classifier'] = 'ADM-style encoder + attention pooling, 41 M parameters, fp32 torch autograd inside the step graph'
     diff = Diffusion(model=model, device=dev, **dkw)
     diff.noise, diff.seed = 'philox', 1234
     ids = torch.arange(rank * B, (rank + 1) * B, device=dev, dtype=torch.long)   # global sample indices

@@ -116,6 +116,9 @@ class Diffusion:
         self.noise = 'torch'      # 'torch' | 'philox'
         self.seed = 0             # philox seed
         self.sample_ids = None    # LongTensor [B] of global sample indices (philox keying); default arange(B)
+        # classifier guidance: capture the classifier's forward + input-gradient inside the per-step CUDA graph (between the
+        # UNet plan and the fused step kernel). False: reference-shaped host loop over the public step functions.
+        self.classifier_in_graph = True
         self._tables_dev = {}     # sampling_var_type -> device tables (the fixed-variance row depends on it)
 
     # ------------------------------------------------------------------------------------------
@@ -229,6 +232,15 @@ class Diffusion:
             grabbed = log_probs[range(log_probs.shape[0]), torch.flatten(y)]
             return torch.autograd.grad(grabbed.sum(), x)[0].float().contiguous()
 
+    def _classifier_grad_static(self, x_t, t, y):
+        """The same gradient with device-resident arguments only (no host-built index tensors): safe to capture in a CUDA
+        graph. `log_probs[range(B), y]` of the reference is a gather along the class axis."""
+        with torch.enable_grad():
+            x = x_t.detach().clone().requires_grad_(True)
+            log_probs = torch.log_softmax(self.classifier(x, t), dim=-1)
+            grabbed = log_probs.gather(1, y.reshape(-1, 1))
+            return torch.autograd.grad(grabbed.sum(), x)[0].float().contiguous()
+
     def _step(self, x_t, t, kwargs, clip_x, ddim, noise=None):
         x_t = x_t.contiguous()
         t = t.to(self.device).float().contiguous()
@@ -303,7 +315,7 @@ class Diffusion:
             if steps_to_do == 0:
                 return x
             self._check_step_index(steps_to_do - 1, 'denoise')
-            if self.guidance == 'classifier':
+            if self.guidance == 'classifier' and not self.classifier_in_graph:
                 x = self._denoise_stepwise(x, kwargs, steps_to_do, progress, noise)
             else:
                 x = self._denoise_graph(x, kwargs, steps_to_do, progress, noise)
@@ -403,8 +415,7 @@ class _StepRunner:
         self.diff = diff
         self.B = B = x.shape[0]
         self.cfg = cfg = diff.guidance == 'classifier_free'
-        if diff.guidance == 'classifier':
-            raise L.NdbError('classifier guidance runs through the step-wise path (needs autograd each step)')
+        self.clf = diff.guidance == 'classifier'
         self.model_batch = Bm = 2 * B if cfg else B
         model, dev = diff.model, diff.device
         self.eng = eng = model.engine_for(torch.empty((Bm, 0), device=dev))
@@ -438,7 +449,7 @@ class _StepRunner:
         self.use_philox = noise is None and diff.noise == 'philox'
         # every scalar below is a kernel argument frozen at capture time; the reference reads them live each step
         self.gkey = (self.use_philox, int(diff.seed) if self.use_philox else 0, cfg, bool(diff.use_ddim),
-                     diff.sampling_var_type, float(diff.strength) if cfg else 0.0,
+                     diff.sampling_var_type, float(diff.strength) if (cfg or self.clf) else 0.0, id(diff.classifier) if self.clf else 0,
                      float(diff.ddim_eta) if diff.use_ddim else 0.0, self.tabs['tab'].data_ptr(),
                      self.tabs['tmap_f32'].data_ptr())
         self.kernels_per_step = eng.num_kernels + 2
@@ -447,9 +458,15 @@ class _StepRunner:
         d, eng, st, B = self.diff, self.eng, self.st, self.B
         eng._launch_all()
         out = eng.out
+        grad = None
+        if self.clf:
+            # d log p(y | x_t, t) / d x_t through the user's classifier: torch autograd, captured with the rest of the step.
+            # The classifier sees the RESPACED step index, like the reference's (diffusion.py:301)
+            grad = d._classifier_grad_static(eng.x_in[:B], st['t_step'], eng.y_in[:B])
         ops.sampler_step(eng.x_in[:B], out[:B], st['t_step'], self.tabs['tab'], d._var_code(), ddim=d.use_ddim,
                          eta=d.ddim_eta if d.use_ddim else 0.0, null_out=out[B:] if self.cfg else None,
                          cfg_strength=d.strength if self.cfg else 0.0, clip_x0=True,
+                         grad=grad, clf_strength=d.strength if self.clf else 0.0,
                          noise=None if self.use_philox else st['noise'], seed=d.seed, sample_ids=st['ids'],
                          x_prev=eng.x_in[:B], x_prev2=eng.x_in[B:] if self.cfg else None)
         ops.advance_step(st['t_step'], eng.t_in, self.tabs['tmap_f32'])

@@ -21,8 +21,16 @@ from torch.utils.checkpoint import checkpoint as _ckpt
 from .model import AttentionBlock, Downsample, ResidualBlock, Upsample, timestep_embedding_freqs
 
 
+_FREQS = {}
+
+
 def _sinusoid(timestep, dim):
-    f = timestep_embedding_freqs(dim).to(timestep.device)
+    # the frequency vector is built on the CPU in fp32 like the reference's (model.py:515-517) but uploaded once per
+    # (dim, device): the reference's per-call host-to-device copy would also be illegal inside a CUDA graph capture
+    key = (dim, timestep.device)
+    f = _FREQS.get(key)
+    if f is None:
+        f = _FREQS[key] = timestep_embedding_freqs(dim).to(timestep.device)
     ang = timestep[:, None].float() * f[None]
     e = torch.cat([torch.cos(ang), torch.sin(ang)], dim=1)
     return F.pad(e, (0, 1, 0, 0)) if dim % 2 == 1 else e

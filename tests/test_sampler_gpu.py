@@ -464,3 +464,51 @@ def test_trajectory_fp32_class_is_tight(cuda_dev, name):
     print(name, 'fp32-class free-running err', err, 'teacher-forced', worst)
     assert worst < 2e-5 * max(1.0, float(np.abs(g['traj_x']).max()))
     assert err < 1e-3
+
+
+def test_noisy_classifier_guidance_in_graph_matches_oracle(cuda_dev):
+    """f-2: the ADM-style NoisyClassifier guides a 10-step chain; its forward + input-gradient are captured inside the
+    per-step CUDA graph. Checked against the oracle sampler running the SAME classifier weights on the CPU (which receives
+    the respaced index t like the reference's, diffusion.py:301), DDPM and DDIM, and against the host-loop path."""
+    import copy
+    from oracle.sampler import Sampler
+    from oracle.unet import unet_forward
+    from nice_diffusion_b200.classifier import NoisyClassifier
+    from nice_diffusion_b200.diffusion import Diffusion
+    cfg, sd, model = _build('tiny', cuda_dev)
+    torch.manual_seed(3)
+    clf = NoisyClassifier(16, 3, 64, cfg['num_classes'], 1, (8,), channel_mult=(1, 2), num_head_channels=32).eval()
+    clf_cpu = copy.deepcopy(clf)
+    rs = np.random.RandomState(21)
+    B, R = 3, 10
+    x_T = torch.from_numpy(rs.standard_normal((B, 3, 16, 16)).astype(np.float32))
+    noises = torch.from_numpy(rs.standard_normal((R, B, 3, 16, 16)).astype(np.float32))
+    y = torch.tensor([1, 4, 7])
+    for ddim in (False, True):
+        dkw = dict(original_num_steps=1000, rescaled_num_steps=R, beta_schedule='cosine', sampling_var_type='learned_interpolation',
+                   guidance_method='classifier', guidance_strength=3.0, use_ddim=ddim, ddim_eta=0.0 if ddim else None)
+        ora = Sampler(lambda xx, tt, y=None: unet_forward(cfg, sd, xx, tt, y), classifier=clf_cpu, **dkw)
+        traj = []
+        want = ora.denoise(x_T.clone(), {'y': y}, lambda t: noises[t], trajectory=traj)
+        # guidance must matter in this test
+        plain = Sampler(lambda xx, tt, y=None: unet_forward(cfg, sd, xx, tt, y),
+                        **{k: v for k, v in dkw.items() if k not in ('guidance_method', 'guidance_strength')})
+        assert float((plain.denoise(x_T.clone(), {'y': y}, lambda t: noises[t]) - want).abs().max()) > 1e-3
+        diff = Diffusion(model=model, loss_type='hybrid', classifier=clf, device=cuda_dev, **dkw)
+        d = cuda_dev
+        got = diff.denoise(x=x_T.to(d), kwargs={'y': y.to(d)}, batch_size=B, progress=False, noise=noises.to(d))
+        eng = model.engine_for(torch.empty((B, 0), device=d))
+        assert any(isinstance(k, tuple) and k[0] == 'state' for k in eng.step_graphs), 'the chain did not run as a step graph'
+        err = float((got.cpu() - want).abs().max())
+        diff.classifier_in_graph = False
+        host = diff.denoise(x=x_T.to(d), kwargs={'y': y.to(d)}, batch_size=B, progress=False, noise=noises.to(d))
+        print('classifier-guided chain ddim', ddim, 'err', err, 'graph vs host loop', float((got - host).abs().max()))
+        assert err < (1e-1 if ddim else 3e-2)
+        # same math on both paths; cuDNN may pick different fp32 algorithms under capture, and the chain amplifies that
+        assert float((got - host).abs().max()) < (1e-1 if ddim else 2e-2)
+        # teacher-forced single steps stay tight
+        step = diff.ddim_denoising_step if ddim else diff.denoising_step
+        for i, t in enumerate(reversed(range(R))):
+            x_in = x_T if i == 0 else traj[i - 1][1]
+            xo, _ = step(x_in.to(d), t=torch.full((B,), float(t), device=d), kwargs={'y': y.to(d)}, noise=noises[t].to(d))
+            assert float((xo.cpu() - traj[i][1]).abs().max()) < 1.5e-2, (ddim, t)
