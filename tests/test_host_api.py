@@ -94,8 +94,13 @@ def test_diffusion_argument_checks():
         Diffusion(model=uncond, sampling_var_type='small', guidance_method='classifier_free', **kw)
     d = Diffusion(model=m, sampling_var_type='learned', **kw)
     assert not m.training
-    with pytest.raises(NotImplementedError):
+    # the training loss is a CUDA kernel: on a CPU tensor it fails loudly (no CPU fallback), and a step index outside the
+    # respaced schedule raises like the reference's gather
+    from nice_diffusion_b200 import _lib
+    with pytest.raises(_lib.NdbError):
         d.loss(torch.zeros(1, 3, 16, 16), torch.zeros(1))
+    with pytest.raises(IndexError):
+        d.loss(torch.zeros(1, 3, 16, 16), torch.full((1,), 10.0))
 
 
 def test_no_cpu_fallback():
