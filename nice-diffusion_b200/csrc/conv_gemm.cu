@@ -30,8 +30,17 @@ namespace ndb {
 
 #ifdef NDB_BRINGUP
 #define NDB_DBG_BIT(p, b) ((p).dbg & (b))
+// phase trace of the last launch (bring-up builds only): g_trace[cta][phase] = %globaltimer when that CTA reached the phase
+__device__ unsigned long long g_trace[160][12];
+#define NDB_TRACE(ph)                                                                            \
+    do {                                                                                         \
+        unsigned long long t_;                                                                   \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                   \
+        if (blockIdx.x < 160) g_trace[blockIdx.x][ph] = t_;                                      \
+    } while (0)
 #else
 #define NDB_DBG_BIT(p, b) 0
+#define NDB_TRACE(ph) do {} while (0)
 #endif
 
 constexpr int kMaxSeg = NDB_MAX_SEGMENTS;
@@ -141,6 +150,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) NDB_TRACE(0);
     // work items: (m tile, n tile) per CTA, or (pair of adjacent m tiles, n tile) per CTA pair
     const uint32_t rank = k2 ? cluster_ctarank() : 0u;
     const int worker = k2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -150,26 +160,33 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
     const int tile_end = tile_start(worker + 1, num_tiles, n_workers);
     auto m_tile_of = [&](int item) { return k2 ? 2 * (item / p.num_n_tiles) + (int)rank : item / p.num_n_tiles; };
 
-    if (warp == 0 && lane == 0) {
-        for (int s = 0; s < p.num_seg; ++s) {
-            prefetch_tmap(&maps.a[s]);
-            prefetch_tmap(&maps.b[s]);
+    if (warp == 0) {
+        // descriptor prefetches and barrier initialisation spread over the lanes (one thread doing all ~50 of them was
+        // 0.5 us of every launch's prologue)
+        if (lane < p.num_seg) {
+            prefetch_tmap(&maps.a[lane]);
+            prefetch_tmap(&maps.b[lane]);
         }
-        if (p.epi_bulk) prefetch_tmap(&maps.out);
-        if (p.epi_bulk && p.res_mode == NDB_RES_SAME) prefetch_tmap(&maps.res);
-        for (int s = 0; s < p.stages; ++s) {
-            mbar_init(&full_bar[s], k2 ? 2 : 1);   // pair mode: both CTAs' producers arrive on the leader's barrier
-            mbar_init(&empty_bar[s], 1);
+        if (lane == 31 && p.epi_bulk) {
+            prefetch_tmap(&maps.out);
+            if (p.res_mode == NDB_RES_SAME) prefetch_tmap(&maps.res);
         }
-        for (int s = 0; s < 2; ++s) {
+        if (lane < p.stages) {
+            mbar_init(&full_bar[lane], k2 ? 2 : 1);   // pair mode: both CTAs' producers arrive on the leader's barrier
+            mbar_init(&empty_bar[lane], 1);
+        }
+        if (lane >= 8 && lane < 10) {
+            const int s = lane - 8;
             mbar_init(&tmem_full_bar[s], 1);
             mbar_init(&tmem_empty_bar[s], k2 ? 2 * kEpiWarps : kEpiWarps);  // one arrive per epilogue warp (of both CTAs)
             mbar_init(&stat_full_bar[s], kEpiWarps);
             mbar_init(&stat_empty_bar[s], 1);
         }
-        if (p.epi_bulk)     // per epilogue warp: three "residual box has landed" barriers (inside its row-table slot)
-            for (int w = 0; w < kEpiWarps; ++w)
-                for (int b = 0; b < 3; ++b) mbar_init(reinterpret_cast<uint64_t*>(epi_rows + w * 128 + 64) + b, 1);
+        if (p.epi_bulk && lane >= 8) {        // 3 * kEpiWarps = 24 barriers on lanes 8..31
+            // per epilogue warp: three "residual box has landed" barriers (inside its row-table slot)
+            const int i = lane - 8;
+            mbar_init(reinterpret_cast<uint64_t*>(epi_rows + (i / 3) * 128 + 64) + (i % 3), 1);
+        }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -181,8 +198,10 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
     if (k2) cluster_sync_all();    // the peer's barriers must be initialised before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    if (threadIdx.x == 0) NDB_TRACE(1);
     pdl_launch_dependents();   // the next kernel may begin its prologue as SM resources free up
     pdl_wait();                // everything above overlapped the previous kernel's tail; its outputs are visible from here
+    if (threadIdx.x == 0) NDB_TRACE(2);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -259,6 +278,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
+                    if (lane == 0 && tile == tile_begin && kb == 0) NDB_TRACE(3);
                     const uint32_t a_lo = desc_lo0 + (uint32_t)stage * desc_step;
                     if (elect_one()) {
                         const uint64_t adesc = kDescHi | a_lo;
@@ -284,6 +304,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                     if (k2) umma_commit_2sm(&tmem_full_bar[acc]); else umma_commit(&tmem_full_bar[acc]);
                 }
                 __syncwarp();
+                if (lane == 0 && tile + 1 == tile_end && kb1 == p.total_kblocks) NDB_TRACE(4);
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1;
@@ -433,6 +454,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                 drain_chunks();
                 mbar_wait(&tmem_full_bar[acc], acc_phase);
                 tc_fence_after();
+                if (warp == 2 && lane == 0 && tile + 1 == tile_end) NDB_TRACE(5);
                 if (kStats) mbar_wait(&stat_empty_bar[stat_buf], stat_phase ^ 1);   // part_smem buffer free
                 const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * p.acc_stride;
                 for (int ch = ch_begin; ch < ch_end; ++ch, ++ci) {
@@ -559,8 +581,10 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                     if ((stat_buf ^= 1) == 0) stat_phase ^= 1;
                 }
             }
+            if (warp == 2 && lane == 0) NDB_TRACE(6);
             if (elect_one()) bulk_wait_all();     // shared memory must outlive the last store's reads
             __syncwarp();
+            if (warp == 2 && lane == 0) NDB_TRACE(7);
         } else {
         // ----------------------------------------------------------------------------------------------------
         // legacy path
@@ -707,23 +731,32 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
         uint32_t stat_phase = 0;
         const int warps_per_slot = 4 / p.TN;                  // TN in {1, 2, 4} (host-checked)
         int cur_group = -1;
+        int cur_slot = 0;        // slot this CTA writes for cur_group: computed when the group starts, off the critical path
         // group of images a work item belongs to, and the slot this CTA writes for that group (see stats_slots())
         auto group_of = [&](int item) {
             if (!k2) return item / p.tiles_per_group;
             if (p.TN == 1) return item / (p.tiles_per_group >> 1);      // both CTAs of a pair sweep the same images
             return m_tile_of(item);                                      // one tile == one group of TN images
         };
-        auto flush = [&](int group) {
-            int slot_idx;
-            if (!k2) slot_idx = worker - cta_of_tile(group * p.tiles_per_group, num_tiles, n_workers);
-            else if (p.TN == 1)
-                slot_idx = 2 * (worker - cta_of_tile(group * (p.tiles_per_group >> 1), num_tiles, n_workers)) + (int)rank;
-            else slot_idx = worker - cta_of_tile((group >> 1) * p.num_n_tiles, num_tiles, n_workers);
+        auto slot_of = [&](int group) {
+            if (!k2) return worker - cta_of_tile(group * p.tiles_per_group, num_tiles, n_workers);
+            if (p.TN == 1) return 2 * (worker - cta_of_tile(group * (p.tiles_per_group >> 1), num_tiles, n_workers)) + (int)rank;
+            return worker - cta_of_tile((group >> 1) * p.num_n_tiles, num_tiles, n_workers);
+        };
+        // the tail of the kernel waits for this: two channels (16 bytes) per lane and trip, trips independent
+        auto flush = [&](int group, int slot_idx) {
             for (int sl = 0; sl < p.TN; ++sl) {
                 const int img = group * p.TN + sl;
                 if (img >= p.N) break;
                 float2* dst = p.stat_parts + ((size_t)img * p.stat_smax + slot_idx) * p.cout;
-                for (int c = lane; c < p.cout; c += 32) dst[c] = stat_acc[sl * p.cout + c];
+                const float2* src = stat_acc + sl * p.cout;
+                if ((p.cout & 1) == 0 && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0) {
+#pragma unroll 4
+                    for (int c = 2 * lane; c < p.cout; c += 64)
+                        *reinterpret_cast<float4*>(dst + c) = *reinterpret_cast<const float4*>(src + c);
+                } else {
+                    for (int c = lane; c < p.cout; c += 32) dst[c] = src[c];
+                }
             }
         };
         for (int tile = tile_begin; tile < tile_end; ++tile) {
@@ -731,40 +764,47 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             const int group = group_of(tile);
             const int col0 = n_tile * p.block_n;
             if (group != cur_group) {
-                if (cur_group >= 0) flush(cur_group);
+                if (cur_group >= 0) flush(cur_group, cur_slot);
                 for (int i = lane; i < p.TN * p.cout; i += 32) stat_acc[i] = make_float2(0.f, 0.f);
                 cur_group = group;
+                cur_slot = slot_of(group);
                 __syncwarp();
             }
             mbar_wait(&stat_full_bar[stat_buf], stat_phase);
+            if (lane == 0 && tile + 1 == tile_end) NDB_TRACE(10);
             const float2* ps = part_smem + stat_buf * 4 * p.block_n;
-            for (int i = lane; i < p.TN * p.block_n; i += 32) {
-                const int sl = i / p.block_n, c = i - sl * p.block_n;
-                float sx = 0.f, sy = 0.f;
-                for (int qq = sl * warps_per_slot; qq < (sl + 1) * warps_per_slot; ++qq) {
-                    const float2 v = ps[qq * p.block_n + c];
-                    sx += v.x; sy += v.y;
-                }
-                if (col0 + c < p.cout) {
-                    float2 a = stat_acc[sl * p.cout + col0 + c];
-                    a.x += sx; a.y += sy;
-                    stat_acc[sl * p.cout + col0 + c] = a;
+            for (int sl = 0; sl < p.TN; ++sl) {
+                float2* acc_row = stat_acc + sl * p.cout + col0;
+                for (int c = lane; c < p.block_n; c += 32) {
+                    float sx = 0.f, sy = 0.f;
+                    for (int qq = sl * warps_per_slot; qq < (sl + 1) * warps_per_slot; ++qq) {
+                        const float2 v = ps[qq * p.block_n + c];
+                        sx += v.x; sy += v.y;
+                    }
+                    if (col0 + c < p.cout) {
+                        float2 a = acc_row[c];
+                        a.x += sx; a.y += sy;
+                        acc_row[c] = a;
+                    }
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&stat_empty_bar[stat_buf]);
             if ((stat_buf ^= 1) == 0) stat_phase ^= 1;
         }
-        if (cur_group >= 0) flush(cur_group);
+        if (cur_group >= 0) flush(cur_group, cur_slot);
+        if (lane == 0) NDB_TRACE(11);
     }
 
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) NDB_TRACE(8);
     if (k2) cluster_sync_all();    // the peer may still be reading this CTA's half of the weights / signalling its barriers
     if (warp == 1) {
         tc_fence_after();
         if (k2) tmem_dealloc_2sm(tmem_base, p.tmem_cols); else tmem_dealloc(tmem_base, p.tmem_cols);
     }
+    if (threadIdx.x == 32) NDB_TRACE(9);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1136,6 +1176,13 @@ extern "C" int ndb_conv_stats_layout(int N, int H, int W, int cout_pad, int bloc
     const WorkGeom w = work_geom(g, n_tiles, bn, true, kblocks);
     return stats_slots(g.tiles_n, g.tiles_w * g.tiles_h * n_tiles, n_tiles, g.TN, w.pair, w.items, w.workers, counts, N);
 }
+
+#ifdef NDB_BRINGUP
+// bring-up builds only (not declared in ndb200.h): copies the phase trace of the last conv launch to host memory [160][12]
+extern "C" int ndb_debug_conv_trace(unsigned long long* host_out) {
+    return cudaMemcpyFromSymbol(host_out, g_trace, sizeof(g_trace)) == cudaSuccess ? NDB_OK : NDB_ERR_CUDA;
+}
+#endif
 
 // 1 when the epilogue can produce per-image channel statistics for this geometry (else use ndb_gn_stats).
 extern "C" int ndb_conv_stats_supported(int N, int H, int W) {
