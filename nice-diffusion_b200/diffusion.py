@@ -25,6 +25,7 @@ import tqdm
 
 from . import _lib as L
 from . import ops
+from .engine import capture_guard
 
 
 def get_beta_schedule(schedule_method, num_steps, beta_0, beta_T):
@@ -490,7 +491,7 @@ class _StepRunner:
             torch.cuda.synchronize(d.device)
             eng.x_in.copy_(saved[0]); st['t_step'].copy_(saved[1]); eng.t_in.copy_(saved[2])
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with capture_guard(), torch.cuda.graph(g):
                 self._launch()
             st['graphs'][self.gkey] = g
         g.replay()
@@ -523,7 +524,7 @@ class _StepRunner:
         tail()
         torch.cuda.synchronize(d.device)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with capture_guard(), torch.cuda.graph(g):
             tail()
         g.replay()
         torch.cuda.synchronize(d.device)

@@ -15,6 +15,8 @@ Every tensor-core operand is written once in 16-bit NHWC by the consuming norm's
 path never materialises in fp32: the apply kernel reads both sources (model.py:474). All step-embedding Linear
 layers run as ONE GEMM per forward.
 """
+import contextlib
+import gc
 import os
 
 import torch
@@ -22,6 +24,21 @@ import torch
 from . import _lib as L
 from . import ops
 from .model import (AttentionBlock, Downsample, ResidualBlock, Upsample, timestep_embedding_freqs)
+
+
+@contextlib.contextmanager
+def capture_guard():
+    """Around every CUDA-graph capture: Python's cyclic garbage collector must not run INSIDE a capture -- if it finalises
+    an old torch.cuda.CUDAGraph there (a dropped plan, a previous model), the `reset` it issues is "not permitted when stream
+    is capturing" and invalidates the capture in progress. Collect first, keep the collector off until the capture ends."""
+    gc.collect()
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was:
+            gc.enable()
 
 
 class _Pool:
@@ -593,7 +610,7 @@ class UNetEngine:
                 torch.cuda.current_stream(self.device).wait_stream(s)
                 torch.cuda.synchronize(self.device)
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with capture_guard(), torch.cuda.graph(g):
                     self._launch_all()
                 self.graph = g
             self.graph.replay()
@@ -642,7 +659,7 @@ class UNetEngine:
             torch.cuda.synchronize(dev)
             ops.PROFILE = None
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with capture_guard(), torch.cuda.graph(g):
                 run(False)
             acc = torch.zeros(n + 3, dtype=torch.float64)
             for _ in range(replays):

@@ -2,7 +2,7 @@ import json, sys
 lines = [l for l in open(sys.argv[1]).read().splitlines() if l.startswith('{')]
 d = json.loads(lines[-1])
 r = d['roofline']
-print('ms/step %.3f  value %.2f img/s  e2e %.2f  conv frac %.3f (%.0f TF)  unet fwd frac %.3f  clocks %s' % (
+print('ms/step %.3f  value %.2f img/s  e2e %.2f  conv frac %.3f (%.0f TF)  step frac %.3f (%.0f TF)  gn %.0f GB/s  attn %.0f TF  clocks %s' % (
     d['ms_per_step'], d['value'], d['e2e']['value'] if d.get('e2e') else float('nan'), r['frac'], r['achieved'],
-    r['unet_forward']['frac'], d['clocks']))
-print('other kernels ms:', {k: round(v, 3) for k, v in r['other_kernels_ms'].items()}, 'conv ms', round(r['ms_per_step_in_kernel'], 3))
+    r.get('step_frac', float('nan')), r.get('step_tflops', float('nan')), r.get('gn_apply_gbs') or float('nan'),
+    r.get('attention_tflops') or float('nan'), d['clocks']))
