@@ -998,7 +998,7 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     a.tiles_w = cg.tiles_w; a.tiles_h = cg.tiles_h; a.tiles_n = cg.tiles_n;
     a.num_m_tiles = cg.num_m_tiles;
     int kblocks_total = 0;
-    for (int s = 0; s < prm->num_segments; ++s) kblocks_total += prm->seg[s].taps * (prm->seg[s].C / kBlockK);
+    for (int s = 0; s < prm->num_segments; ++s) kblocks_total += prm->seg[s].taps * ((prm->seg[s].C + kBlockK - 1) / kBlockK);
     a.block_n = prm->block_n > 0 ? prm->block_n
                                  : pick_block_n(prm->cout_pad, cg, prm->stat_parts != nullptr, kblocks_total,
                                                 prm->acc_chunk_kblocks > 0 ? 192 : 256);
@@ -1042,10 +1042,12 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     for (int s = 0; s < prm->num_segments; ++s) {
         const ndb_conv_segment& sg = prm->seg[s];
         NDB_CHECK_ARG(sg.act && sg.weight);
-        NDB_CHECK_ARG(sg.C > 0 && sg.C % kBlockK == 0);
+        // channels need not fill whole 64-wide K blocks: TMA zero-fills the rest of the last block of BOTH operands (the
+        // 16-byte stride rule of tensor maps asks for a multiple of 8)
+        NDB_CHECK_ARG(sg.C > 0 && sg.C % 8 == 0);
         NDB_CHECK_ARG(sg.taps == 1 || sg.taps == 9);
         a.seg_taps[s] = sg.taps;
-        a.seg_chunks[s] = sg.C / kBlockK;
+        a.seg_chunks[s] = (sg.C + kBlockK - 1) / kBlockK;
         a.total_kblocks += sg.taps * a.seg_chunks[s];
         {
             uint64_t dims[4] = {(uint64_t)sg.C, (uint64_t)prm->W, (uint64_t)prm->H, (uint64_t)prm->N};
@@ -1167,8 +1169,8 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
 // stat_parts must hold N * stat_smax * cout float2.
 extern "C" int ndb_conv_stats_layout(int N, int H, int W, int cout_pad, int block_n, int k_total, int acc_chunk_kblocks,
                                      int32_t* counts) {
-    if (N <= 0 || H <= 0 || W <= 0 || cout_pad <= 0 || k_total <= 0 || k_total % kBlockK != 0) return NDB_ERR_INVALID;
-    const int kblocks = k_total / kBlockK;
+    if (N <= 0 || H <= 0 || W <= 0 || cout_pad <= 0 || k_total <= 0) return NDB_ERR_INVALID;
+    const int kblocks = (k_total + kBlockK - 1) / kBlockK;      // only "at least one" matters to the plan
     const ConvGeom g = conv_geom(N, H, W);
     const int bn = block_n > 0 ? block_n : pick_block_n(cout_pad, g, true, kblocks, acc_chunk_kblocks > 0 ? 192 : 256);
     if (bn <= 0 || cout_pad % bn != 0) return NDB_ERR_INVALID;

@@ -207,9 +207,13 @@ static int launch_stem(const float* x, const float* w, const float* bias, float*
         stem_conv_kernel<CIN, CPT><<<(int)blocks, 256, smem, st>>>(x, w, bias, out, stat_parts, N, H, W);               \
     }
     switch (Cout) {
+        case 32: NDB_STEM_CASE(8) break;
         case 64: NDB_STEM_CASE(16) break;
+        case 96: NDB_STEM_CASE(24) break;
         case 128: NDB_STEM_CASE(32) break;
+        case 160: NDB_STEM_CASE(40) break;
         case 192: NDB_STEM_CASE(48) break;
+        case 224: NDB_STEM_CASE(56) break;
         case 256: NDB_STEM_CASE(64) break;
         default: return NDB_ERR_UNSUPPORTED;
     }

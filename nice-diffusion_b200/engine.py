@@ -238,8 +238,8 @@ class UNetEngine:
         R = m.resolution
         E = 4 * m.model_channels
         for c in self._all_channels():
-            if c % 64 != 0:
-                raise L.NdbError('ndb200 needs every feature-map width to be a multiple of 64 (got {})'.format(c))
+            if c % 32 != 0:        # GroupNorm(32); a last K block of 32 channels is zero-filled by TMA
+                raise L.NdbError('ndb200 needs every feature-map width to be a multiple of 32 (got {})'.format(c))
 
         # static inputs / output
         self.x_in = torch.zeros((B, m.in_channels, R, R), dtype=torch.float32, device=dev)

@@ -38,6 +38,11 @@ CONFIGS = {
                     'num_res_blocks': 1, 'split_qkv_first': False, 'dropout': 0.0,
                     'resblock_updown': False, 'conv_resample': True, 'use_adaptive_gn': False,
                     'num_classes': None},
+    # widths that are multiples of 32 but not of 64 (the reference's --custom --model_channels 96): 96 / 192 channels, heads of 32
+    'tiny96': {'resolution': 16, 'attention_resolutions': (8, 16), 'channel_mult': (1, 2),
+               'num_head_channels': 32, 'in_channels': 3, 'out_channels': 6, 'model_channels': 96,
+               'num_res_blocks': 1, 'split_qkv_first': True, 'dropout': 0.0,
+               'resblock_updown': True, 'use_adaptive_gn': True, 'num_classes': 7},
     # avg-pool / nearest resampling without ResBlocks (conv_resample=False)
     'tiny_pool': {'resolution': 16, 'attention_resolutions': (), 'channel_mult': (1, 1),
                   'num_heads': 1, 'in_channels': 3, 'out_channels': 6, 'model_channels': 64,

@@ -107,7 +107,7 @@ def main(only_unet=None):
 
     # ---- 1. schedules / respacing / tables ------------------------------------------------
     sched = {}
-    unet_cases = (('tiny', 2), ('tiny_legacy', 2), ('tiny_pool', 2), ('emnist', 2), ('in64', 1), ('in128', 1))
+    unet_cases = (('tiny', 2), ('tiny_legacy', 2), ('tiny_pool', 2), ('tiny96', 2), ('emnist', 2), ('in64', 1), ('in128', 1))
     if only_unet:
         SCHEDULE_LOCAL, unet_cases = [], tuple(c for c in unet_cases if c[0] in only_unet)
     else:

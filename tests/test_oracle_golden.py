@@ -46,7 +46,7 @@ def test_schedule_known_answers_from_survey():
     assert len(t.timestep_map) == 334 and len(t.betas) == 333
 
 
-@pytest.mark.parametrize('name', ['tiny', 'tiny_legacy', 'tiny_pool', 'emnist', 'in64', 'in128'])
+@pytest.mark.parametrize('name', ['tiny', 'tiny_legacy', 'tiny_pool', 'tiny96', 'emnist', 'in64', 'in128'])
 def test_unet_forward_matches_reference_output(name):
     cfg = CONFIGS[name]
     sd = random_state_dict(cfg, seed=1234)

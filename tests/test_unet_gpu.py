@@ -32,7 +32,7 @@ def norm_err(a, b):
     return float((a - b).abs().max() / b.abs().max())
 
 
-@pytest.mark.parametrize('name', ['tiny', 'tiny_legacy', 'tiny_pool', 'emnist', 'in64', 'in128'])
+@pytest.mark.parametrize('name', ['tiny', 'tiny_legacy', 'tiny_pool', 'tiny96', 'emnist', 'in64', 'in128'])
 def test_forward_matches_reference_golden(cuda_dev, name):
     cfg, sd, model = build(name, 1234, cuda_dev)
     g = np.load(os.path.join(GOLD, 'unet_{}.npz'.format(name)))
@@ -143,7 +143,7 @@ def test_full_size_batch_properties_in64(cuda_dev):
 TOL32 = 1e-5
 
 
-@pytest.mark.parametrize('name', ['tiny', 'tiny_pool', 'emnist', 'in64'])
+@pytest.mark.parametrize('name', ['tiny', 'tiny_pool', 'tiny96', 'emnist', 'in64'])
 def test_forward_fp32_class_matches_reference_golden(cuda_dev, name):
     """model.operand_format = FMT_FP32X: every tensor-core product as three fp16 MMAs (hi hi + lo hi + hi lo), accurate
     SiLU / softmax exponentials, fp32 everywhere else. Bar: max|out - ref| / max|ref| <= 1e-5 against the reference's own fp32
