@@ -450,7 +450,8 @@ class _StepRunner:
         self.use_philox = noise is None and diff.noise == 'philox'
         # every scalar below is a kernel argument frozen at capture time; the reference reads them live each step
         self.gkey = (self.use_philox, int(diff.seed) if self.use_philox else 0, cfg, bool(diff.use_ddim),
-                     diff.sampling_var_type, float(diff.strength) if (cfg or self.clf) else 0.0, id(diff.classifier) if self.clf else 0,
+                     diff.sampling_var_type, float(diff.strength) if (cfg or self.clf) else 0.0,
+                     diff.classifier if self.clf else None,     # the module itself: the key keeps it alive, so no id() reuse
                      float(diff.ddim_eta) if diff.use_ddim else 0.0, self.tabs['tab'].data_ptr(),
                      self.tabs['tmap_f32'].data_ptr())
         self.kernels_per_step = eng.num_kernels + 2
