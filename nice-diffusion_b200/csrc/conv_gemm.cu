@@ -47,7 +47,7 @@ constexpr int kMaxSeg = NDB_MAX_SEGMENTS;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                        // 64 x 16-bit = one 128-byte swizzle row
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
-constexpr int kThreads = 352;                       // 11 warps: TMA, MMA, 8 epilogue, 1 statistics
+constexpr int kThreads = 384;                       // 12 warps: TMA (A), MMA, 8 epilogue, 1 statistics, TMA (B)
 constexpr int kEpiWarps = 8;
 constexpr int kStageFloats = 32 * 33;               // padded 32x32 transpose tile per epilogue warp
 constexpr int kMaxStages = 8;
@@ -91,6 +91,13 @@ struct ConvArgs {
     int epi_bulk;              // 1: staged TMA-store epilogue
     int epi_bufs;              // staging tiles per epilogue warp (2 for short-K GEMMs whose epilogue is on the critical path)
     int epi_region;            // bytes of the staging region
+    int split_prod;            // 1: warp 11 issues the weight (B) loads, warp 0 only the activation (A) loads
+    // vertical tap reuse (3x3 segments): one activation box of TH + 2 image rows per (dx, channel block) serves the three
+    // dy taps -- their windows start TW pixel rows (a multiple of the 1024-byte swizzle atom) apart inside it
+    int vreuse;
+    int a_slots, b_slots;      // ring depths (activation boxes / weight tiles)
+    int a_slot_bytes;          // (TH + 2) * TW * 128
+    int ring_bytes;            // operand rings in front of the epilogue region
     int dbg;                   // bring-up switches, compiled in with -DNDB_BRINGUP only (env NDB_DBG; results are garbage):
                                // 1 no TMA loads, 2 no MMAs, 4 no TMA stores, 8 no staging writes
 };
@@ -136,7 +143,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
 
     const int b_tile_bytes = p.b_rows * 128;
     const int stage_bytes = kATileBytes + b_tile_bytes;
-    uint8_t* epi_base = smem + p.stages * stage_bytes;   // 1024-aligned: per-warp staging tiles (bulk 4 KB / legacy 33x32 floats)
+    uint8_t* epi_base = smem + p.ring_bytes;   // 1024-aligned: per-warp staging tiles (bulk 4 KB / legacy 33x32 floats)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_base + p.epi_region);
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full_bar = empty_bar + kMaxStages;
@@ -144,6 +151,8 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
     uint64_t* stat_full_bar = tmem_empty_bar + 2;
     uint64_t* stat_empty_bar = stat_full_bar + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(stat_empty_bar + 2);
+    uint64_t* a_full_bar = stat_empty_bar + 3;       // vreuse: activation ring (<= 3 slots)
+    uint64_t* a_empty_bar = a_full_bar + 3;
     long long* epi_rows = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
     float2* part_smem = reinterpret_cast<float2*>(epi_rows + kEpiWarps * 128);  // [2 buffers][4 quarters][block_n]
     float2* stat_acc = part_smem + 2 * 4 * p.block_n;                           // [TN][cout] (statistics warp only)
@@ -172,8 +181,13 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             if (p.res_mode == NDB_RES_SAME) prefetch_tmap(&maps.res);
         }
         if (lane < p.stages) {
-            mbar_init(&full_bar[lane], k2 ? 2 : 1);   // pair mode: both CTAs' producers arrive on the leader's barrier
+            // pair mode: both CTAs' producers arrive on the leader's barrier; split producers arrive separately
+            mbar_init(&full_bar[lane], (k2 ? 2 : 1) * ((p.split_prod && !p.vreuse) ? 2 : 1));
             mbar_init(&empty_bar[lane], 1);
+        }
+        if (p.vreuse && lane >= 16 && lane < 16 + p.a_slots) {
+            mbar_init(&a_full_bar[lane - 16], k2 ? 2 : 1);
+            mbar_init(&a_empty_bar[lane - 16], 1);
         }
         if (lane >= 8 && lane < 10) {
             const int s = lane - 8;
@@ -203,12 +217,78 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
     pdl_wait();                // everything above overlapped the previous kernel's tail; its outputs are visible from here
     if (threadIdx.x == 0) NDB_TRACE(2);
 
-    if (warp == 0) {
-        // ===================== TMA producer =====================
+    if (warp == 0 || warp == kThreads / 32 - 1) {
+        // ===================== TMA producer(s) =====================
         // The WHOLE warp runs the (warp-uniform) loop and one elected lane issues: with the loop inside `if (lane == 0)`
         // ptxas cannot prove the descriptor / coordinate operands uniform and wraps every UTMALDG / UTCHMMA in an
         // ELECT + R2UR "waterfall" loop (~150 cycles per instruction, measured).
-        {
+        // One thread's TMA loads are processed one after the other at ~45 GB/s (scripts/tma_rate_probe.cu: the rate scales
+        // with the number of ISSUING warps, 42 / 83 / 124 GB/s per SM for 1 / 2 / 3 of them), which capped the operand feed
+        // of the 3x3 layers at ~12 TB/s chip-wide, below what the tensor pipe consumes. Split mode: warp 0 streams the
+        // activation boxes, the last warp the weight boxes; both arrive on the stage's barrier with their own byte count.
+        const bool do_a = !p.split_prod || warp == 0;
+        const bool do_b = !p.split_prod || warp != 0;
+        if (p.vreuse) {
+            // Two independent rings. Warp 0 streams activation boxes: per 3x3 segment one box of TH + 2 rows per (dx, channel
+            // block), per 1x1 segment the plain tile. The last warp streams one weight tile per K block, in the order the MMA
+            // warp consumes them: segment, dx, channel block, dy.
+            int slot = 0;
+            uint32_t phase = 0;
+            uint8_t* ring_b = smem + p.a_slots * p.a_slot_bytes;
+            for (int tile = tile_begin; tile < tile_end; ++tile) {
+                const int n_tile = tile % p.num_n_tiles;
+                int m_tile = m_tile_of(tile);
+                const int tw_i = m_tile % p.tiles_w;
+                m_tile /= p.tiles_w;
+                const int th_i = m_tile % p.tiles_h;
+                const int tn_i = m_tile / p.tiles_h;
+                const int w0 = tw_i * p.TW, h0 = th_i * p.TH, n0 = tn_i * p.TN;
+                const int b_row0 = n_tile * p.block_n + (int)rank * p.b_rows;
+                for (int s = 0; s < p.num_seg; ++s) {
+                    const bool k3 = p.seg_taps[s] == 9;
+                    const int chunks = p.seg_chunks[s];
+                    const uint32_t a_bytes = k3 ? (uint32_t)p.a_slot_bytes : p.a_box_bytes;
+                    for (int dxi = 0; dxi < (k3 ? 3 : 1); ++dxi) {
+                        for (int ch = 0; ch < chunks; ++ch) {
+                            if (warp == 0) {
+                                mbar_wait(&a_empty_bar[slot], phase ^ 1);
+                                if (elect_one()) {
+                                    uint8_t* sa = smem + slot * p.a_slot_bytes;
+                                    if (k2) {
+                                        const uint32_t fb = mapa_u32(smem_u32(&a_full_bar[slot]), 0);
+                                        mbar_arrive_expect_tx_cluster(fb, a_bytes);
+                                        tma_load_4d_2sm(sa, &maps.a[s], fb, ch * kBlockK, w0 + (k3 ? dxi - 1 : 0), h0 - (k3 ? 1 : 0), n0);
+                                    } else {
+                                        mbar_arrive_expect_tx(&a_full_bar[slot], a_bytes);
+                                        tma_load_4d(sa, &maps.a[s], &a_full_bar[slot], ch * kBlockK, w0 + (k3 ? dxi - 1 : 0), h0 - (k3 ? 1 : 0), n0);
+                                    }
+                                }
+                                __syncwarp();
+                                if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
+                            } else {
+                                for (int dyi = 0; dyi < (k3 ? 3 : 1); ++dyi) {
+                                    mbar_wait(&empty_bar[slot], phase ^ 1);
+                                    if (elect_one()) {
+                                        uint8_t* sb = ring_b + slot * b_tile_bytes;
+                                        const int tap = k3 ? dyi * 3 + dxi : 0;
+                                        if (k2) {
+                                            const uint32_t fb = mapa_u32(smem_u32(&full_bar[slot]), 0);
+                                            mbar_arrive_expect_tx_cluster(fb, (uint32_t)b_tile_bytes);
+                                            tma_load_3d_2sm(sb, &maps.b[s], fb, ch * kBlockK, b_row0, tap);
+                                        } else {
+                                            mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)b_tile_bytes);
+                                            tma_load_3d(sb, &maps.b[s], &full_bar[slot], ch * kBlockK, b_row0, tap);
+                                        }
+                                    }
+                                    __syncwarp();
+                                    if (++slot == p.b_slots) { slot = 0; phase ^= 1; }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        } else if (p.split_prod || warp == 0) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = tile_begin; tile < tile_end; ++tile) {
@@ -231,18 +311,19 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                             uint8_t* sa = smem + stage * stage_bytes;
                             uint8_t* sb = sa + kATileBytes;
                             if (elect_one()) {
+                                const uint32_t tx = (do_a ? p.a_box_bytes : 0u) + (do_b ? (uint32_t)b_tile_bytes : 0u);
                                 if (NDB_DBG_BIT(p, 1)) {
                                     if (k2) mbar_arrive_cluster(mapa_u32(smem_u32(&full_bar[stage]), 0));
                                     else mbar_arrive(&full_bar[stage]);
                                 } else if (k2) {
                                     const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);   // leader's barrier
-                                    mbar_arrive_expect_tx_cluster(fb, p.a_box_bytes + (uint32_t)b_tile_bytes);
-                                    tma_load_4d_2sm(sa, &maps.a[s], fb, ch * kBlockK, w0 + dx, h0 + dy, n0);
-                                    tma_load_3d_2sm(sb, &maps.b[s], fb, ch * kBlockK, b_row0, tap);
+                                    mbar_arrive_expect_tx_cluster(fb, tx);
+                                    if (do_a) tma_load_4d_2sm(sa, &maps.a[s], fb, ch * kBlockK, w0 + dx, h0 + dy, n0);
+                                    if (do_b) tma_load_3d_2sm(sb, &maps.b[s], fb, ch * kBlockK, b_row0, tap);
                                 } else {
-                                    mbar_arrive_expect_tx(&full_bar[stage], p.a_box_bytes + (uint32_t)b_tile_bytes);
-                                    tma_load_4d(sa, &maps.a[s], &full_bar[stage], ch * kBlockK, w0 + dx, h0 + dy, n0);
-                                    tma_load_3d(sb, &maps.b[s], &full_bar[stage], ch * kBlockK, b_row0, tap);
+                                    mbar_arrive_expect_tx(&full_bar[stage], tx);
+                                    if (do_a) tma_load_4d(sa, &maps.a[s], &full_bar[stage], ch * kBlockK, w0 + dx, h0 + dy, n0);
+                                    if (do_b) tma_load_3d(sb, &maps.b[s], &full_bar[stage], ch * kBlockK, b_row0, tap);
                                 }
                             }
                             __syncwarp();
@@ -267,6 +348,56 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             const uint32_t desc_lo0 = (smem_u32(smem) & 0x3FFFF) >> 4;
             const uint32_t desc_step = (uint32_t)stage_bytes >> 4;
             const int chunk_kb = kChunk ? p.acc_chunk : p.total_kblocks;
+            if (!kChunk && p.vreuse) {
+                int as = 0, bs = 0;
+                uint32_t aph = 0, bph = 0;
+                const uint32_t a_step = (uint32_t)p.a_slot_bytes >> 4;
+                const uint32_t b_lo0 = desc_lo0 + (uint32_t)p.a_slots * a_step;
+                const uint32_t b_step = (uint32_t)b_tile_bytes >> 4;
+                const uint32_t dy_step = (uint32_t)(p.TW * 128) >> 4;      // one image row of the tile: TW pixel rows of 128 B
+                for (int tile = tile_begin; tile < tile_end; ++tile) {
+                    mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
+                    uint32_t started = 0;
+                    for (int s = 0; s < p.num_seg; ++s) {
+                        const bool k3 = p.seg_taps[s] == 9;
+                        const int units = (k3 ? 3 : 1) * p.seg_chunks[s];
+                        for (int u = 0; u < units; ++u) {
+                            mbar_wait(&a_full_bar[as], aph);
+                            const uint32_t a_lo = desc_lo0 + (uint32_t)as * a_step;
+                            for (int dyi = 0; dyi < (k3 ? 3 : 1); ++dyi) {
+                                mbar_wait(&full_bar[bs], bph);
+                                tc_fence_after();
+                                if (lane == 0 && tile == tile_begin && !started) NDB_TRACE(3);
+                                if (elect_one()) {
+                                    const uint64_t adesc = kDescHi | (a_lo + (uint32_t)dyi * dy_step);
+                                    const uint64_t bdesc = kDescHi | (b_lo0 + (uint32_t)bs * b_step);
+#pragma unroll
+                                    for (int k = 0; k < kBlockK / 16; ++k) {
+                                        if (k2) umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (started | k) ? 1u : 0u);
+                                        else umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (started | k) ? 1u : 0u);
+                                    }
+                                    if (k2) umma_commit_2sm(&empty_bar[bs]); else umma_commit(&empty_bar[bs]);
+                                    if (dyi == (k3 ? 2 : 0)) {      // the box has served its last tap
+                                        if (k2) umma_commit_2sm(&a_empty_bar[as]); else umma_commit(&a_empty_bar[as]);
+                                    }
+                                }
+                                __syncwarp();
+                                started = 1;
+                                if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
+                            }
+                            if (++as == p.a_slots) { as = 0; aph ^= 1; }
+                        }
+                    }
+                    if (elect_one()) {
+                        if (k2) umma_commit_2sm(&tmem_full_bar[acc]); else umma_commit(&tmem_full_bar[acc]);
+                    }
+                    __syncwarp();
+                    if (lane == 0 && tile + 1 == tile_end) NDB_TRACE(4);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            } else
             for (int tile = tile_begin; tile < tile_end; ++tile)
             for (int kb0 = 0; kb0 < p.total_kblocks; kb0 += chunk_kb) {
                 const int kb1 = (kb0 + chunk_kb < p.total_kblocks) ? kb0 + chunk_kb : p.total_kblocks;
@@ -431,6 +562,18 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             int ci = 0;                 // chunks processed by this warp
             uint32_t res_phase = 0;     // bit b: parity of the next completion of res_bar[b]
             int sb = 0;
+            // bias values of this lane's columns, fetched one tile ahead (an L2 round trip per tile sat on the epilogue's
+            // critical path of the short-K GEMMs)
+            float bias_r[4];
+            auto fetch_bias = [&](int tile) {
+                const int col0n = (tile % p.num_n_tiles) * p.block_n;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int col = col0n + (ch_begin + c) * 32 + lane;
+                    bias_r[c] = (p.bias != nullptr && ch_begin + c < ch_end && tile < tile_end && col < p.cout) ? __ldg(p.bias + col) : 0.f;
+                }
+            };
+            fetch_bias(tile_begin);
             for (int tile = tile_begin; tile < tile_end; ++tile) {
                 const int col0 = (tile % p.num_n_tiles) * p.block_n;
                 int m_tile = m_tile_of(tile);
@@ -445,11 +588,11 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                     vmask = __ballot_sync(0xffffffffu, (tn < p.TN) && (n < p.N) && (h < p.H) && (w < p.W));
                 }
                 // this tile's bias values for this warp's chunks -> shared memory, while the MMAs of the tile still run
-                for (int ch = ch_begin; ch < ch_end; ++ch) {
-                    const int col = col0 + ch * 32 + lane;
-                    bias_s[(ch - ch_begin) * 32 + lane] = (p.bias != nullptr && col < p.cout) ? __ldg(p.bias + col) : 0.f;
-                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (ch_begin + c < ch_end) bias_s[c * 32 + lane] = bias_r[c];
                 __syncwarp();
+                fetch_bias(tile + 1);
 
                 drain_chunks();
                 mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -457,10 +600,11 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                 if (warp == 2 && lane == 0 && tile + 1 == tile_end) NDB_TRACE(5);
                 if (kStats) mbar_wait(&stat_empty_bar[stat_buf], stat_phase ^ 1);   // part_smem buffer free
                 const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * p.acc_stride;
-                for (int ch = ch_begin; ch < ch_end; ++ch, ++ci) {
+                // one chunk: `racc` was requested from TMEM by the previous call (or before the loop); the request for the
+                // next chunk goes out as soon as this one has landed, so its latency hides under this chunk's arithmetic,
+                // and the accumulator stage is handed back to the MMA warp the moment its last chunk is in registers
+                auto do_chunk = [&](uint32_t (&racc)[32], uint32_t (&rnext)[32], const int ch) {
                     const int c0 = col0 + ch * 32;
-                    uint32_t racc[32];
-                    tmem_ld32(t_row + ch * 32, racc);
                     int b;
                     if (has_res) {
                         b = ci % nbuf;
@@ -478,6 +622,16 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                         if (nbuf == 2) sb ^= 1;
                     }
                     tmem_ld_wait();
+                    if (ch + 1 < ch_end) {
+                        tmem_ld32(t_row + (ch + 1) * 32, rnext);
+                    } else {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (k2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));   // the leader's MMA thread waits
+                            else mbar_arrive(&tmem_empty_bar[acc]);
+                        }
+                    }
                     add_csum(racc, ch);
                     uint8_t* sbuf = sbuf0 + b * 4096;
                     float* sf = reinterpret_cast<float*>(sbuf);
@@ -512,7 +666,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                             *reinterpret_cast<uint4*>(sbuf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = w4;
                         }
                     }
-                    if (kStats) {
+                    if (kStats && !NDB_DBG_BIT(p, 16)) {
                         // the staged values are final: a lanes-along-channels pass READS them for the column sums (for a
                         // 16-bit output these are the sums of the ROUNDED values -- exactly what the consuming norm will read)
                         __syncwarp();
@@ -564,12 +718,15 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                         }
                     }
                     __syncwarp();
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if (k2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));   // the leader's MMA thread waits
-                    else mbar_arrive(&tmem_empty_bar[acc]);
+                    ++ci;
+                };
+                {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(t_row + ch_begin * 32, r0);
+                    for (int ch = ch_begin; ch < ch_end; ch += 2) {
+                        do_chunk(r0, r1, ch);
+                        if (ch + 1 < ch_end) do_chunk(r1, r0, ch + 1);
+                    }
                 }
                 if (++acc == 2) {
                     acc = 0;
@@ -881,6 +1038,13 @@ static ConvGeom conv_geom(int N, int H, int W) {
     g.TH = kBlockM / g.TW;
     if (g.TH > Hv) g.TH = Hv;
     if (g.TH < 1) g.TH = 1;
+    // tall tiles (8 columns x 16 rows) when the image allows: the vertical tap reuse of the 3x3 layers then loads
+    // (16 + 2) / (3 * 16) of the activation bytes; 8 columns = one 1024-byte swizzle atom per image row
+    static const int tall = std::getenv("NDB_TILE_TALL") ? std::atoi(std::getenv("NDB_TILE_TALL")) : 1;
+    if (tall && Wv >= 8 && Hv >= 16) {
+        g.TW = 8;
+        g.TH = 16;
+    }
     g.TN = 1;
     if (g.TH == Hv && g.TW == Wv) {
         g.TN = kBlockM / (Hv * Wv);
@@ -1010,6 +1174,10 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     a.acc_stride = (a.block_n + 31) / 32 * 32;
     a.tmem_cols = a.acc_stride <= 32 ? 64 : a.acc_stride <= 64 ? 128 : a.acc_stride <= 128 ? 256 : 512;
     a.idesc = make_idesc_f16(kBlockM, a.block_n, prm->operand_format, 0, 0);
+    {
+        static const int split = std::getenv("NDB_SPLIT_PRODUCER") ? std::atoi(std::getenv("NDB_SPLIT_PRODUCER")) : 1;
+        a.split_prod = split;
+    }
     a.bias = prm->bias;
     a.residual = prm->residual;
     a.res_mode = prm->residual ? prm->residual_mode : NDB_RES_NONE;
@@ -1037,6 +1205,15 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
         NDB_CHECK_ARG(prm->stat_smax == a.stat_smax);
     }
 
+    {
+        static const int off = std::getenv("NDB_DISABLE_VREUSE") != nullptr ? 1 : 0;
+        bool any3 = false;
+        for (int s = 0; s < prm->num_segments; ++s) any3 = any3 || prm->seg[s].taps == 9;
+        // worth it from 4 image rows per tile up (box of TH + 2 rows instead of three of TH); the boxes must leave room
+        // for a weight ring (wide flat tiles of short images do not)
+        a.a_slot_bytes = (a.TH + 2) * a.TW * 128;
+        a.vreuse = (!off && any3 && a.TN == 1 && a.TW % 8 == 0 && a.TH >= 4 && a.acc_chunk == 0 && a.a_slot_bytes <= 24 * 1024) ? 1 : 0;
+    }
     TmapPack maps;
     a.total_kblocks = 0;
     for (int s = 0; s < prm->num_segments; ++s) {
@@ -1053,7 +1230,7 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
             uint64_t dims[4] = {(uint64_t)sg.C, (uint64_t)prm->W, (uint64_t)prm->H, (uint64_t)prm->N};
             uint64_t strides[3] = {(uint64_t)sg.C * 2, (uint64_t)prm->W * sg.C * 2,
                                    (uint64_t)prm->H * prm->W * sg.C * 2};
-            uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)a.TW, (uint32_t)a.TH, (uint32_t)a.TN};
+            uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)a.TW, (uint32_t)(a.TH + ((a.vreuse && sg.taps == 9) ? 2 : 0)), (uint32_t)a.TN};
             int rc = encode_tmap_16bit(&maps.a[s], sg.act, 4, dims, strides, box);
             if (rc != NDB_OK) return rc;
         }
@@ -1107,10 +1284,20 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
         return region + kEpiWarps * 128 * (int)sizeof(long long) + 2 * 4 * a.block_n * (int)sizeof(float2) +
                (prm->stat_parts ? a.TN * prm->cout * (int)sizeof(float2) : 0);
     };
+    const int b_tile = a.b_rows * 128;
+    // vreuse: three activation boxes + as many weight tiles as fit (two boxes when that leaves fewer than five tiles)
+    auto vreuse_slots = [&](int bufs, int* a_slots) {
+        const int budget = 227 * 1024 - 1024 - 256 - epi_bytes_for(bufs);
+        int as = 3, bs = (budget - as * a.a_slot_bytes) / b_tile;
+        if (bs < 5) { as = 2; bs = (budget - as * a.a_slot_bytes) / b_tile; }
+        if (a_slots) *a_slots = as;
+        return bs > kMaxStages ? kMaxStages : bs;
+    };
     if (a.epi_bulk && a.res_mode == NDB_RES_SAME) {
-        const int stages3 = (227 * 1024 - 1024 - 256 - epi_bytes_for(3)) / stage_bytes;
+        const int stages3 = a.vreuse ? vreuse_slots(3, nullptr) - 2 : (227 * 1024 - 1024 - 256 - epi_bytes_for(3)) / stage_bytes;
         a.epi_bufs = (a.total_kblocks <= 24 || stages3 >= 5) ? 3 : 2;
     } else {
+        // (two tiles for the long-K layers as well, at the price of one pipeline stage: measured, no gain)
         a.epi_bufs = (a.epi_bulk && a.total_kblocks <= 24) ? 2 : 1;
     }
     a.epi_region = a.epi_bufs >= 2 ? kEpiWarps * a.epi_bufs * 4096 : kEpiWarps * kStageFloats * (int)sizeof(float);
@@ -1121,7 +1308,15 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     if (stages > a.total_kblocks) stages = a.total_kblocks < 2 ? 2 : a.total_kblocks;
     NDB_CHECK_ARG(stages >= 2);
     a.stages = stages;
-    const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 256 + epi_bytes;
+    a.ring_bytes = stages * stage_bytes;
+    if (a.vreuse) {
+        a.b_slots = vreuse_slots(a.epi_bufs, &a.a_slots);
+        if (a.b_slots < 3) a.vreuse = 0;      // (does not happen with the tile shapes above; the maps were encoded for vreuse)
+        NDB_CHECK_ARG(a.vreuse);
+        a.stages = a.b_slots;                 // the weight ring uses full_bar / empty_bar
+        a.ring_bytes = a.a_slots * a.a_slot_bytes + a.b_slots * b_tile;
+    }
+    const size_t smem_bytes = (size_t)a.ring_bytes + 1024 + 256 + epi_bytes;
 
     static PerDeviceOnce attr_once;
     if (attr_once.pending()) {

