@@ -14,6 +14,7 @@
 // K/V tiles are double-buffered; with d <= 64 two CTAs fit per SM so one CTA's softmax overlaps the other's MMAs.
 #include "common.cuh"
 #include "ptx.cuh"
+#include <cstdlib>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 
@@ -34,6 +35,7 @@ struct AttnArgs {
     float scale_log2e;
     uint16_t* out;
     int C;
+    int dbg;       // -DNDB_BRINGUP only (env NDB_ATTN_DBG): 1 = pass 1 without its TMEM reads, 2 = pass 1 reads twice (timing probes)
 };
 
 __device__ __forceinline__ float ex2_fast(float x) {
@@ -247,8 +249,22 @@ attention_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_const
 #pragma unroll 1
             for (int c0 = 0; c0 < 64; c0 += 32) {
                 uint32_t r1[32];
+#ifdef NDB_BRINGUP
+                if (p.dbg == 1) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r1[i] = 0u;
+                } else {
+                    tmem_ld32(tmem_S + lane_addr + key0 + c0, r1);
+                    tmem_ld_wait();
+                    if (p.dbg == 2) {
+                        tmem_ld32(tmem_S + lane_addr + key0 + c0, r1);
+                        tmem_ld_wait();
+                    }
+                }
+#else
                 tmem_ld32(tmem_S + lane_addr + key0 + c0, r1);
                 tmem_ld_wait();
+#endif
                 if (full) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r1[i]));
@@ -439,6 +455,9 @@ static int launch_attention(const void* qkv, const void* qkv_lo, void* out, int 
     a.scale_log2e = (float)(1.4426950408889634 / sqrt((double)d));
     a.out = (uint16_t*)out;
     a.C = C;
+#ifdef NDB_BRINGUP
+    a.dbg = std::getenv("NDB_ATTN_DBG") ? std::atoi(std::getenv("NDB_ATTN_DBG")) : 0;
+#endif
 
     CUtensorMap map, map_lo;
     {
