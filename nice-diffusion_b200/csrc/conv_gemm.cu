@@ -50,7 +50,8 @@ constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kThreads = 384;                       // 12 warps: TMA (A), MMA, 8 epilogue, 1 statistics, TMA (B)
 constexpr int kEpiWarps = 8;
 constexpr int kStageFloats = 32 * 33;               // padded 32x32 transpose tile per epilogue warp
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
+constexpr int kBarBytes = 384;                      // mbarriers + TMEM pointer, in front of the epilogue row tables
 
 struct TmapPack {
     CUtensorMap a[kMaxSeg];
@@ -96,7 +97,8 @@ struct ConvArgs {
     // dy taps -- their windows start TW pixel rows (a multiple of the 1024-byte swizzle atom) apart inside it
     int vreuse;
     int a_slots, b_slots;      // ring depths (activation boxes / weight tiles)
-    int a_slot_bytes;          // (TH + 2) * TW * 128
+    int a_slot_bytes;          // ring pitch: (TH + 2) * TW * 128 (halo: (TH + 2) * (TW + 2) * 128 rounded up to 1024)
+    uint32_t a_k3_bytes;       // bytes of a 3x3 segment's activation box
     int ring_bytes;            // operand rings in front of the epilogue region
     int dbg;                   // bring-up switches, compiled in with -DNDB_BRINGUP only (env NDB_DBG; results are garbage):
                                // 1 no TMA loads, 2 no MMAs, 4 no TMA stores, 8 no staging writes
@@ -153,7 +155,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(stat_empty_bar + 2);
     uint64_t* a_full_bar = stat_empty_bar + 3;       // vreuse: activation ring (<= 3 slots)
     uint64_t* a_empty_bar = a_full_bar + 3;
-    long long* epi_rows = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
+    long long* epi_rows = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(full_bar) + kBarBytes);
     float2* part_smem = reinterpret_cast<float2*>(epi_rows + kEpiWarps * 128);  // [2 buffers][4 quarters][block_n]
     float2* stat_acc = part_smem + 2 * 4 * p.block_n;                           // [TN][cout] (statistics warp only)
 
@@ -247,8 +249,9 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                 for (int s = 0; s < p.num_seg; ++s) {
                     const bool k3 = p.seg_taps[s] == 9;
                     const int chunks = p.seg_chunks[s];
-                    const uint32_t a_bytes = k3 ? (uint32_t)p.a_slot_bytes : p.a_box_bytes;
-                    for (int dxi = 0; dxi < (k3 ? 3 : 1); ++dxi) {
+                    const uint32_t a_bytes = k3 ? (uint32_t)p.a_k3_bytes : p.a_box_bytes;
+                    const bool halo = p.vreuse == 2;      // one (TW + 2) x (TH + 2) box per channel block serves all nine taps
+                    for (int dxi = 0; dxi < ((k3 && !halo) ? 3 : 1); ++dxi) {
                         for (int ch = 0; ch < chunks; ++ch) {
                             if (warp == 0) {
                                 mbar_wait(&a_empty_bar[slot], phase ^ 1);
@@ -257,20 +260,20 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                                     if (k2) {
                                         const uint32_t fb = mapa_u32(smem_u32(&a_full_bar[slot]), 0);
                                         mbar_arrive_expect_tx_cluster(fb, a_bytes);
-                                        tma_load_4d_2sm(sa, &maps.a[s], fb, ch * kBlockK, w0 + (k3 ? dxi - 1 : 0), h0 - (k3 ? 1 : 0), n0);
+                                        tma_load_4d_2sm(sa, &maps.a[s], fb, ch * kBlockK, w0 + (k3 ? (halo ? -1 : dxi - 1) : 0), h0 - (k3 ? 1 : 0), n0);
                                     } else {
                                         mbar_arrive_expect_tx(&a_full_bar[slot], a_bytes);
-                                        tma_load_4d(sa, &maps.a[s], &a_full_bar[slot], ch * kBlockK, w0 + (k3 ? dxi - 1 : 0), h0 - (k3 ? 1 : 0), n0);
+                                        tma_load_4d(sa, &maps.a[s], &a_full_bar[slot], ch * kBlockK, w0 + (k3 ? (halo ? -1 : dxi - 1) : 0), h0 - (k3 ? 1 : 0), n0);
                                     }
                                 }
                                 __syncwarp();
                                 if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
                             } else {
-                                for (int dyi = 0; dyi < (k3 ? 3 : 1); ++dyi) {
+                                for (int t = 0; t < (k3 ? (halo ? 9 : 3) : 1); ++t) {
                                     mbar_wait(&empty_bar[slot], phase ^ 1);
                                     if (elect_one()) {
                                         uint8_t* sb = ring_b + slot * b_tile_bytes;
-                                        const int tap = k3 ? dyi * 3 + dxi : 0;
+                                        const int tap = k3 ? (halo ? t : t * 3 + dxi) : 0;
                                         if (k2) {
                                             const uint32_t fb = mapa_u32(smem_u32(&full_bar[slot]), 0);
                                             mbar_arrive_expect_tx_cluster(fb, (uint32_t)b_tile_bytes);
@@ -354,7 +357,13 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                 const uint32_t a_step = (uint32_t)p.a_slot_bytes >> 4;
                 const uint32_t b_lo0 = desc_lo0 + (uint32_t)p.a_slots * a_step;
                 const uint32_t b_step = (uint32_t)b_tile_bytes >> 4;
-                const uint32_t dy_step = (uint32_t)(p.TW * 128) >> 4;      // one image row of the tile: TW pixel rows of 128 B
+                const bool halo = p.vreuse == 2;
+                // one image row of the box: TW (halo: TW + 2) pixel rows of 128 B. Halo boxes: the eight pixels of an image
+                // row are one swizzle atom, atoms are (TW + 2) * 128 bytes apart (the descriptor's stride byte offset) and a
+                // tap's window starts dx pixel rows into the box, i.e. NOT on a 1024-byte boundary: the swizzle is a
+                // function of the shared-memory address, which the TMA write and the MMA read agree on.
+                const uint32_t dy_step = (uint32_t)((p.TW + (halo ? 2 : 0)) * 128) >> 4;
+                const uint64_t kDescHiA = halo ? ((uint64_t(dy_step) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61) | (uint64_t(1) << 16)) : kDescHi;
                 for (int tile = tile_begin; tile < tile_end; ++tile) {
                     mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                     tc_fence_after();
@@ -362,16 +371,20 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                     uint32_t started = 0;
                     for (int s = 0; s < p.num_seg; ++s) {
                         const bool k3 = p.seg_taps[s] == 9;
-                        const int units = (k3 ? 3 : 1) * p.seg_chunks[s];
+                        const int units = ((k3 && !halo) ? 3 : 1) * p.seg_chunks[s];
+                        const int ntap = k3 ? (halo ? 9 : 3) : 1;
+                        const uint64_t hiA = k3 ? kDescHiA : kDescHi;
                         for (int u = 0; u < units; ++u) {
                             mbar_wait(&a_full_bar[as], aph);
                             const uint32_t a_lo = desc_lo0 + (uint32_t)as * a_step;
-                            for (int dyi = 0; dyi < (k3 ? 3 : 1); ++dyi) {
+                            for (int dyi = 0; dyi < ntap; ++dyi) {
                                 mbar_wait(&full_bar[bs], bph);
                                 tc_fence_after();
                                 if (lane == 0 && tile == tile_begin && !started) NDB_TRACE(3);
                                 if (elect_one()) {
-                                    const uint64_t adesc = kDescHi | (a_lo + (uint32_t)dyi * dy_step);
+                                    // halo: tap t = (dy, dx) starts dy image rows + dx pixels into the box
+                                    const uint32_t a_off = halo ? (uint32_t)(dyi / 3) * dy_step + (uint32_t)(dyi % 3) * 8u : (uint32_t)dyi * dy_step;
+                                    const uint64_t adesc = hiA | (a_lo + a_off);
                                     const uint64_t bdesc = kDescHi | (b_lo0 + (uint32_t)bs * b_step);
 #pragma unroll
                                     for (int k = 0; k < kBlockK / 16; ++k) {
@@ -379,7 +392,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                                         else umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (started | k) ? 1u : 0u);
                                     }
                                     if (k2) umma_commit_2sm(&empty_bar[bs]); else umma_commit(&empty_bar[bs]);
-                                    if (dyi == (k3 ? 2 : 0)) {      // the box has served its last tap
+                                    if (dyi == ntap - 1) {      // the box has served its last tap
                                         if (k2) umma_commit_2sm(&a_empty_bar[as]); else umma_commit(&a_empty_bar[as]);
                                     }
                                 }
@@ -1213,6 +1226,13 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
         // for a weight ring (wide flat tiles of short images do not)
         a.a_slot_bytes = (a.TH + 2) * a.TW * 128;
         a.vreuse = (!off && any3 && a.TN == 1 && a.TW % 8 == 0 && a.TH >= 4 && a.acc_chunk == 0 && a.a_slot_bytes <= 24 * 1024) ? 1 : 0;
+        a.a_k3_bytes = (uint32_t)a.a_slot_bytes;
+        static const int halo = std::getenv("NDB_HALO") ? std::atoi(std::getenv("NDB_HALO")) : 1;
+        if (a.vreuse && halo && a.TW == 8) {
+            a.vreuse = 2;
+            a.a_k3_bytes = (uint32_t)((a.TH + 2) * (a.TW + 2) * 128);
+            a.a_slot_bytes = ((int)a.a_k3_bytes + 1023) / 1024 * 1024;
+        }
     }
     TmapPack maps;
     a.total_kblocks = 0;
@@ -1230,7 +1250,8 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
             uint64_t dims[4] = {(uint64_t)sg.C, (uint64_t)prm->W, (uint64_t)prm->H, (uint64_t)prm->N};
             uint64_t strides[3] = {(uint64_t)sg.C * 2, (uint64_t)prm->W * sg.C * 2,
                                    (uint64_t)prm->H * prm->W * sg.C * 2};
-            uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)a.TW, (uint32_t)(a.TH + ((a.vreuse && sg.taps == 9) ? 2 : 0)), (uint32_t)a.TN};
+            const bool k3 = a.vreuse && sg.taps == 9;
+            uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)(a.TW + ((k3 && a.vreuse == 2) ? 2 : 0)), (uint32_t)(a.TH + (k3 ? 2 : 0)), (uint32_t)a.TN};
             int rc = encode_tmap_16bit(&maps.a[s], sg.act, 4, dims, strides, box);
             if (rc != NDB_OK) return rc;
         }
@@ -1287,14 +1308,14 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     const int b_tile = a.b_rows * 128;
     // vreuse: three activation boxes + as many weight tiles as fit (two boxes when that leaves fewer than five tiles)
     auto vreuse_slots = [&](int bufs, int* a_slots) {
-        const int budget = 227 * 1024 - 1024 - 256 - epi_bytes_for(bufs);
-        int as = 3, bs = (budget - as * a.a_slot_bytes) / b_tile;
+        const int budget = 227 * 1024 - 1024 - kBarBytes - epi_bytes_for(bufs);
+        int as = 3, bs = (budget - as * a.a_slot_bytes) / b_tile;      // (2 vs 3 boxes, 5..8 weight tiles: within noise)
         if (bs < 5) { as = 2; bs = (budget - as * a.a_slot_bytes) / b_tile; }
         if (a_slots) *a_slots = as;
         return bs > kMaxStages ? kMaxStages : bs;
     };
     if (a.epi_bulk && a.res_mode == NDB_RES_SAME) {
-        const int stages3 = a.vreuse ? vreuse_slots(3, nullptr) - 2 : (227 * 1024 - 1024 - 256 - epi_bytes_for(3)) / stage_bytes;
+        const int stages3 = a.vreuse ? vreuse_slots(3, nullptr) - 2 : (227 * 1024 - 1024 - kBarBytes - epi_bytes_for(3)) / stage_bytes;
         a.epi_bufs = (a.total_kblocks <= 24 || stages3 >= 5) ? 3 : 2;
     } else {
         // (two tiles for the long-K layers as well, at the price of one pipeline stage: measured, no gain)
@@ -1302,7 +1323,7 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     }
     a.epi_region = a.epi_bufs >= 2 ? kEpiWarps * a.epi_bufs * 4096 : kEpiWarps * kStageFloats * (int)sizeof(float);
     const int epi_bytes = epi_bytes_for(a.epi_bufs);
-    const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - epi_bytes;
+    const int smem_budget = 227 * 1024 - 1024 /*align slack*/ - kBarBytes - epi_bytes;
     int stages = smem_budget / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages > a.total_kblocks) stages = a.total_kblocks < 2 ? 2 : a.total_kblocks;
@@ -1316,7 +1337,7 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
         a.stages = a.b_slots;                 // the weight ring uses full_bar / empty_bar
         a.ring_bytes = a.a_slots * a.a_slot_bytes + a.b_slots * b_tile;
     }
-    const size_t smem_bytes = (size_t)a.ring_bytes + 1024 + 256 + epi_bytes;
+    const size_t smem_bytes = (size_t)a.ring_bytes + 1024 + kBarBytes + epi_bytes;
 
     static PerDeviceOnce attr_once;
     if (attr_once.pending()) {
