@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libndb200.so')
+# NDB_LIB: another build of the same library (A/B timing of two builds on one GPU box, bring-up builds)
+LIB_PATH = os.environ.get('NDB_LIB') or os.path.join(_HERE, 'libndb200.so')
 
 MAX_SEGMENTS = 9
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3

@@ -153,8 +153,8 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
     uint64_t* stat_full_bar = tmem_empty_bar + 2;
     uint64_t* stat_empty_bar = stat_full_bar + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(stat_empty_bar + 2);
-    uint64_t* a_full_bar = stat_empty_bar + 3;       // vreuse: activation ring (<= 3 slots)
-    uint64_t* a_empty_bar = a_full_bar + 3;
+    uint64_t* a_full_bar = stat_empty_bar + 3;       // vreuse: activation ring (<= 4 slots)
+    uint64_t* a_empty_bar = a_full_bar + 4;
     long long* epi_rows = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(full_bar) + kBarBytes);
     float2* part_smem = reinterpret_cast<float2*>(epi_rows + kEpiWarps * 128);  // [2 buffers][4 quarters][block_n]
     float2* stat_acc = part_smem + 2 * 4 * p.block_n;                           // [TN][cout] (statistics warp only)
@@ -224,10 +224,9 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
         // The WHOLE warp runs the (warp-uniform) loop and one elected lane issues: with the loop inside `if (lane == 0)`
         // ptxas cannot prove the descriptor / coordinate operands uniform and wraps every UTMALDG / UTCHMMA in an
         // ELECT + R2UR "waterfall" loop (~150 cycles per instruction, measured).
-        // One thread's TMA loads are processed one after the other at ~45 GB/s (scripts/tma_rate_probe.cu: the rate scales
-        // with the number of ISSUING warps, 42 / 83 / 124 GB/s per SM for 1 / 2 / 3 of them), which capped the operand feed
-        // of the 3x3 layers at ~12 TB/s chip-wide, below what the tensor pipe consumes. Split mode: warp 0 streams the
-        // activation boxes, the last warp the weight boxes; both arrive on the stage's barrier with their own byte count.
+        // Two producer warps: warp 0 streams the activation boxes, the last warp the weight tiles (in the reuse modes below
+        // these are two independent rings with their own barriers; in the classic mode both arrive on the stage's barrier
+        // with their own byte count -- 0.6 % faster than one warp issuing both, measured on the whole step).
         const bool do_a = !p.split_prod || warp == 0;
         const bool do_b = !p.split_prod || warp != 0;
         if (p.vreuse) {
@@ -1309,8 +1308,15 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     // vreuse: three activation boxes + as many weight tiles as fit (two boxes when that leaves fewer than five tiles)
     auto vreuse_slots = [&](int bufs, int* a_slots) {
         const int budget = 227 * 1024 - 1024 - kBarBytes - epi_bytes_for(bufs);
-        int as = 3, bs = (budget - as * a.a_slot_bytes) / b_tile;      // (2 vs 3 boxes, 5..8 weight tiles: within noise)
-        if (bs < 5) { as = 2; bs = (budget - as * a.a_slot_bytes) / b_tile; }
+        // a halo box lasts nine K blocks, so two of them are plenty and the rest goes to the weight ring (one tile per K
+        // block: its depth is what covers the TMA round trip)
+        // ... unless the layer also has 1x1 segments (the fused skip convolution): their plain tiles occupy a box slot for a
+        // single K block each, so the box ring is their whole look-ahead
+        // (64x64 3x3 192->192 + 1x1 skip over 384 channels: 96.0 / 91.6 / 88.3 us with 2 / 3 / 4 box slots)
+        bool any1 = false;
+        for (int s = 0; s < prm->num_segments; ++s) any1 = any1 || prm->seg[s].taps == 1;
+        int as = a.vreuse == 2 ? (any1 ? 4 : 2) : 3, bs = (budget - as * a.a_slot_bytes) / b_tile;
+        while (bs < 5 && as > 2) { --as; bs = (budget - as * a.a_slot_bytes) / b_tile; }
         if (a_slots) *a_slots = as;
         return bs > kMaxStages ? kMaxStages : bs;
     };

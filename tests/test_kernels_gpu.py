@@ -348,8 +348,11 @@ def test_groupnorm_plain_preadd_nosilu(cuda_dev):
     assert rel_err(out.permute(0, 3, 1, 2), ref) < 1.5e-3
 
 
+# the last three have more work items (B * heads * ceil(T / 128)) than resident CTAs (2 per SM): the persistent path, where a
+# CTA streams several items back to back (5 x 7 x 1024/128 = 280 < 296 is the largest non-persistent one)
 ATTN_CASES = [(2, 64, 4, 64, 0), (2, 256, 3, 64, 0), (1, 1024, 2, 64, 0), (2, 196, 4, 32, 0), (3, 49, 4, 64, 0),
-              (2, 256, 2, 64, 1), (1, 256, 2, 128, 0), (1, 64, 2, 256, 0), (1, 320, 1, 192, 1)]
+              (2, 256, 2, 64, 1), (1, 256, 2, 128, 0), (1, 64, 2, 256, 0), (1, 320, 1, 192, 1),
+              (9, 1024, 6, 64, 0), (25, 256, 9, 64, 1), (11, 784, 5, 32, 0)]
 
 
 @pytest.mark.parametrize('B,T,heads,d,order', ATTN_CASES)
