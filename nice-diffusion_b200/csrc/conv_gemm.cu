@@ -25,6 +25,7 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <cstdlib>
+#include <vector>
 
 namespace ndb {
 
@@ -51,6 +52,7 @@ constexpr int kThreads = 384;                       // 12 warps: TMA (A), MMA, 8
 constexpr int kEpiWarps = 8;
 constexpr int kStageFloats = 32 * 33;               // padded 32x32 transpose tile per epilogue warp
 constexpr int kMaxStages = 12;
+constexpr int kMaxUnits = 96;
 constexpr int kBarBytes = 384;                      // mbarriers + TMEM pointer, in front of the epilogue row tables
 
 struct TmapPack {
@@ -100,6 +102,12 @@ struct ConvArgs {
     int a_slot_bytes;          // ring pitch: (TH + 2) * TW * 128 (halo: (TH + 2) * (TW + 2) * 128 rounded up to 1024)
     uint32_t a_k3_bytes;       // bytes of a 3x3 segment's activation box
     int ring_bytes;            // operand rings in front of the epilogue region
+    // reuse modes: the K loop as a list of UNITS = one activation box each: (segment, channel block, dx index); a 3x3 unit is
+    // 9 (halo) or 3 (vertical) K blocks, a 1x1 unit one. The host interleaves the 1x1 units among the 3x3 ones: a plain
+    // tile occupies a box slot for one K block only, so a run of them is bound by the TMA round trip over the few slots;
+    // spread out, they are requested a 3x3 unit's worth of MMA time ahead.
+    int n_units;
+    uint8_t unit_seg[kMaxUnits], unit_ch[kMaxUnits], unit_dx[kMaxUnits];
     int dbg;                   // bring-up switches, compiled in with -DNDB_BRINGUP only (env NDB_DBG; results are garbage):
                                // 1 no TMA loads, 2 no MMAs, 4 no TMA stores, 8 no staging writes
 };
@@ -245,47 +253,44 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                 const int tn_i = m_tile / p.tiles_h;
                 const int w0 = tw_i * p.TW, h0 = th_i * p.TH, n0 = tn_i * p.TN;
                 const int b_row0 = n_tile * p.block_n + (int)rank * p.b_rows;
-                for (int s = 0; s < p.num_seg; ++s) {
+                const bool halo = p.vreuse == 2;      // one (TW + 2) x (TH + 2) box per channel block serves all nine taps
+                for (int u = 0; u < p.n_units; ++u) {
+                    const int s = p.unit_seg[u], ch = p.unit_ch[u], dxi = p.unit_dx[u];
                     const bool k3 = p.seg_taps[s] == 9;
-                    const int chunks = p.seg_chunks[s];
-                    const uint32_t a_bytes = k3 ? (uint32_t)p.a_k3_bytes : p.a_box_bytes;
-                    const bool halo = p.vreuse == 2;      // one (TW + 2) x (TH + 2) box per channel block serves all nine taps
-                    for (int dxi = 0; dxi < ((k3 && !halo) ? 3 : 1); ++dxi) {
-                        for (int ch = 0; ch < chunks; ++ch) {
-                            if (warp == 0) {
-                                mbar_wait(&a_empty_bar[slot], phase ^ 1);
-                                if (elect_one()) {
-                                    uint8_t* sa = smem + slot * p.a_slot_bytes;
-                                    if (k2) {
-                                        const uint32_t fb = mapa_u32(smem_u32(&a_full_bar[slot]), 0);
-                                        mbar_arrive_expect_tx_cluster(fb, a_bytes);
-                                        tma_load_4d_2sm(sa, &maps.a[s], fb, ch * kBlockK, w0 + (k3 ? (halo ? -1 : dxi - 1) : 0), h0 - (k3 ? 1 : 0), n0);
-                                    } else {
-                                        mbar_arrive_expect_tx(&a_full_bar[slot], a_bytes);
-                                        tma_load_4d(sa, &maps.a[s], &a_full_bar[slot], ch * kBlockK, w0 + (k3 ? (halo ? -1 : dxi - 1) : 0), h0 - (k3 ? 1 : 0), n0);
-                                    }
-                                }
-                                __syncwarp();
-                                if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
+                    if (warp == 0) {
+                        const uint32_t a_bytes = k3 ? (uint32_t)p.a_k3_bytes : p.a_box_bytes;
+                        mbar_wait(&a_empty_bar[slot], phase ^ 1);
+                        if (elect_one()) {
+                            uint8_t* sa = smem + slot * p.a_slot_bytes;
+                            const int cw = w0 + (k3 ? (halo ? -1 : dxi - 1) : 0), chh = h0 - (k3 ? 1 : 0);
+                            if (k2) {
+                                const uint32_t fb = mapa_u32(smem_u32(&a_full_bar[slot]), 0);
+                                mbar_arrive_expect_tx_cluster(fb, a_bytes);
+                                tma_load_4d_2sm(sa, &maps.a[s], fb, ch * kBlockK, cw, chh, n0);
                             } else {
-                                for (int t = 0; t < (k3 ? (halo ? 9 : 3) : 1); ++t) {
-                                    mbar_wait(&empty_bar[slot], phase ^ 1);
-                                    if (elect_one()) {
-                                        uint8_t* sb = ring_b + slot * b_tile_bytes;
-                                        const int tap = k3 ? (halo ? t : t * 3 + dxi) : 0;
-                                        if (k2) {
-                                            const uint32_t fb = mapa_u32(smem_u32(&full_bar[slot]), 0);
-                                            mbar_arrive_expect_tx_cluster(fb, (uint32_t)b_tile_bytes);
-                                            tma_load_3d_2sm(sb, &maps.b[s], fb, ch * kBlockK, b_row0, tap);
-                                        } else {
-                                            mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)b_tile_bytes);
-                                            tma_load_3d(sb, &maps.b[s], &full_bar[slot], ch * kBlockK, b_row0, tap);
-                                        }
-                                    }
-                                    __syncwarp();
-                                    if (++slot == p.b_slots) { slot = 0; phase ^= 1; }
+                                mbar_arrive_expect_tx(&a_full_bar[slot], a_bytes);
+                                tma_load_4d(sa, &maps.a[s], &a_full_bar[slot], ch * kBlockK, cw, chh, n0);
+                            }
+                        }
+                        __syncwarp();
+                        if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
+                    } else {
+                        for (int t = 0; t < (k3 ? (halo ? 9 : 3) : 1); ++t) {
+                            mbar_wait(&empty_bar[slot], phase ^ 1);
+                            if (elect_one()) {
+                                uint8_t* sb = ring_b + slot * b_tile_bytes;
+                                const int tap = k3 ? (halo ? t : t * 3 + dxi) : 0;
+                                if (k2) {
+                                    const uint32_t fb = mapa_u32(smem_u32(&full_bar[slot]), 0);
+                                    mbar_arrive_expect_tx_cluster(fb, (uint32_t)b_tile_bytes);
+                                    tma_load_3d_2sm(sb, &maps.b[s], fb, ch * kBlockK, b_row0, tap);
+                                } else {
+                                    mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)b_tile_bytes);
+                                    tma_load_3d(sb, &maps.b[s], &full_bar[slot], ch * kBlockK, b_row0, tap);
                                 }
                             }
+                            __syncwarp();
+                            if (++slot == p.b_slots) { slot = 0; phase ^= 1; }
                         }
                     }
                 }
@@ -368,39 +373,36 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
                     uint32_t started = 0;
-                    for (int s = 0; s < p.num_seg; ++s) {
-                        const bool k3 = p.seg_taps[s] == 9;
-                        const int units = ((k3 && !halo) ? 3 : 1) * p.seg_chunks[s];
+                    for (int u = 0; u < p.n_units; ++u) {
+                        const bool k3 = p.seg_taps[p.unit_seg[u]] == 9;
                         const int ntap = k3 ? (halo ? 9 : 3) : 1;
                         const uint64_t hiA = k3 ? kDescHiA : kDescHi;
-                        for (int u = 0; u < units; ++u) {
-                            mbar_wait(&a_full_bar[as], aph);
-                            const uint32_t a_lo = desc_lo0 + (uint32_t)as * a_step;
-                            for (int dyi = 0; dyi < ntap; ++dyi) {
-                                mbar_wait(&full_bar[bs], bph);
-                                tc_fence_after();
-                                if (lane == 0 && tile == tile_begin && !started) NDB_TRACE(3);
-                                if (elect_one()) {
-                                    // halo: tap t = (dy, dx) starts dy image rows + dx pixels into the box
-                                    const uint32_t a_off = halo ? (uint32_t)(dyi / 3) * dy_step + (uint32_t)(dyi % 3) * 8u : (uint32_t)dyi * dy_step;
-                                    const uint64_t adesc = hiA | (a_lo + a_off);
-                                    const uint64_t bdesc = kDescHi | (b_lo0 + (uint32_t)bs * b_step);
+                        mbar_wait(&a_full_bar[as], aph);
+                        const uint32_t a_lo = desc_lo0 + (uint32_t)as * a_step;
+                        for (int dyi = 0; dyi < ntap; ++dyi) {
+                            mbar_wait(&full_bar[bs], bph);
+                            tc_fence_after();
+                            if (lane == 0 && tile == tile_begin && !started) NDB_TRACE(3);
+                            if (elect_one()) {
+                                // halo: tap t = (dy, dx) starts dy image rows + dx pixels into the box
+                                const uint32_t a_off = halo ? (uint32_t)(dyi / 3) * dy_step + (uint32_t)(dyi % 3) * 8u : (uint32_t)dyi * dy_step;
+                                const uint64_t adesc = hiA | (a_lo + a_off);
+                                const uint64_t bdesc = kDescHi | (b_lo0 + (uint32_t)bs * b_step);
 #pragma unroll
-                                    for (int k = 0; k < kBlockK / 16; ++k) {
-                                        if (k2) umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (started | k) ? 1u : 0u);
-                                        else umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (started | k) ? 1u : 0u);
-                                    }
-                                    if (k2) umma_commit_2sm(&empty_bar[bs]); else umma_commit(&empty_bar[bs]);
-                                    if (dyi == ntap - 1) {      // the box has served its last tap
-                                        if (k2) umma_commit_2sm(&a_empty_bar[as]); else umma_commit(&a_empty_bar[as]);
-                                    }
+                                for (int k = 0; k < kBlockK / 16; ++k) {
+                                    if (k2) umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (started | k) ? 1u : 0u);
+                                    else umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (started | k) ? 1u : 0u);
                                 }
-                                __syncwarp();
-                                started = 1;
-                                if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
+                                if (k2) umma_commit_2sm(&empty_bar[bs]); else umma_commit(&empty_bar[bs]);
+                                if (dyi == ntap - 1) {      // the box has served its last tap
+                                    if (k2) umma_commit_2sm(&a_empty_bar[as]); else umma_commit(&a_empty_bar[as]);
+                                }
                             }
-                            if (++as == p.a_slots) { as = 0; aph ^= 1; }
+                            __syncwarp();
+                            started = 1;
+                            if (++bs == p.b_slots) { bs = 0; bph ^= 1; }
                         }
+                        if (++as == p.a_slots) { as = 0; aph ^= 1; }
                     }
                     if (elect_one()) {
                         if (k2) umma_commit_2sm(&tmem_full_bar[acc]); else umma_commit(&tmem_full_bar[acc]);
@@ -1231,6 +1233,34 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
             a.vreuse = 2;
             a.a_k3_bytes = (uint32_t)((a.TH + 2) * (a.TW + 2) * 128);
             a.a_slot_bytes = ((int)a.a_k3_bytes + 1023) / 1024 * 1024;
+        }
+        if (a.vreuse) {
+            // unit list: 3x3 units in segment / dx / channel-block order, the 1x1 units spread evenly among them
+            static const int no_mix = std::getenv("NDB_NO_INTERLEAVE") != nullptr ? 1 : 0;
+            struct U { uint8_t s, ch, dx; };
+            std::vector<U> u3, u1;
+            for (int s = 0; s < prm->num_segments; ++s) {
+                const int chunks = (prm->seg[s].C + kBlockK - 1) / kBlockK;
+                if (prm->seg[s].taps == 9) {
+                    for (int dx = 0; dx < (a.vreuse == 2 ? 1 : 3); ++dx)
+                        for (int ch = 0; ch < chunks; ++ch) u3.push_back({(uint8_t)s, (uint8_t)ch, (uint8_t)dx});
+                } else {
+                    for (int ch = 0; ch < chunks; ++ch) u1.push_back({(uint8_t)s, (uint8_t)ch, 0});
+                }
+            }
+            if ((int)(u3.size() + u1.size()) > kMaxUnits) {
+                a.vreuse = 0;       // (very long reductions: the classic path)
+            } else {
+                a.n_units = 0;
+                auto put = [&](const U& u) { a.unit_seg[a.n_units] = u.s; a.unit_ch[a.n_units] = u.ch; a.unit_dx[a.n_units] = u.dx; ++a.n_units; };
+                size_t done1 = 0;
+                for (size_t i = 0; i < u3.size(); ++i) {
+                    put(u3[i]);
+                    const size_t want = no_mix ? 0 : u1.size() * (i + 1) / u3.size();      // 1x1 units due after i + 1 of the 3x3 ones
+                    while (done1 < want) put(u1[done1++]);
+                }
+                while (done1 < u1.size()) put(u1[done1++]);
+            }
         }
     }
     TmapPack maps;
