@@ -1045,7 +1045,7 @@ static int next_pow2(int v) {
     return p;
 }
 
-static ConvGeom conv_geom(int N, int H, int W) {
+static ConvGeom conv_geom(int N, int H, int W, bool allow_tall = true) {
     ConvGeom g;
     const int Wv = next_pow2(W), Hv = next_pow2(H);     // virtual (padded) image extents
     g.TW = Wv < kBlockM ? Wv : kBlockM;
@@ -1054,8 +1054,9 @@ static ConvGeom conv_geom(int N, int H, int W) {
     if (g.TH < 1) g.TH = 1;
     // tall tiles (8 columns x 16 rows) when the image allows: the vertical tap reuse of the 3x3 layers then loads
     // (16 + 2) / (3 * 16) of the activation bytes; 8 columns = one 1024-byte swizzle atom per image row
+    // (the fp32-class GEMMs keep one box per tap and prefer the wide tiles: 825 vs 908 TFLOP/s)
     static const int tall = std::getenv("NDB_TILE_TALL") ? std::atoi(std::getenv("NDB_TILE_TALL")) : 1;
-    if (tall && Wv >= 8 && Hv >= 16) {
+    if (tall && allow_tall && Wv >= 8 && Hv >= 16) {
         g.TW = 8;
         g.TH = 16;
     }
@@ -1171,7 +1172,7 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
 
     ConvArgs a{};
     a.N = prm->N; a.H = prm->H; a.W = prm->W;
-    const ConvGeom cg = conv_geom(prm->N, prm->H, prm->W);
+    const ConvGeom cg = conv_geom(prm->N, prm->H, prm->W, prm->acc_chunk_kblocks == 0);
     a.TW = cg.TW; a.TH = cg.TH; a.TN = cg.TN;
     a.tiles_w = cg.tiles_w; a.tiles_h = cg.tiles_h; a.tiles_n = cg.tiles_n;
     a.num_m_tiles = cg.num_m_tiles;
@@ -1423,7 +1424,7 @@ extern "C" int ndb_conv_stats_layout(int N, int H, int W, int cout_pad, int bloc
                                      int32_t* counts) {
     if (N <= 0 || H <= 0 || W <= 0 || cout_pad <= 0 || k_total <= 0) return NDB_ERR_INVALID;
     const int kblocks = (k_total + kBlockK - 1) / kBlockK;      // only "at least one" matters to the plan
-    const ConvGeom g = conv_geom(N, H, W);
+    const ConvGeom g = conv_geom(N, H, W, acc_chunk_kblocks == 0);
     const int bn = block_n > 0 ? block_n : pick_block_n(cout_pad, g, true, kblocks, acc_chunk_kblocks > 0 ? 192 : 256);
     if (bn <= 0 || cout_pad % bn != 0) return NDB_ERR_INVALID;
     const int n_tiles = cout_pad / bn;
