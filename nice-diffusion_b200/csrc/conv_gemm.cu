@@ -619,6 +619,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                 // and the accumulator stage is handed back to the MMA warp the moment its last chunk is in registers
                 auto do_chunk = [&](uint32_t (&racc)[32], uint32_t (&rnext)[32], const int ch) {
                     const int c0 = col0 + ch * 32;
+                    if (kChunk) tmem_ld32(t_row + ch * 32, racc);      // (no look-ahead next to the 96 running-sum registers)
                     int b;
                     if (has_res) {
                         b = ci % nbuf;
@@ -637,7 +638,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                     }
                     tmem_ld_wait();
                     if (ch + 1 < ch_end) {
-                        tmem_ld32(t_row + (ch + 1) * 32, rnext);
+                        if (!kChunk) tmem_ld32(t_row + (ch + 1) * 32, rnext);
                     } else {
                         tc_fence_before();
                         __syncwarp();
@@ -734,7 +735,10 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                     __syncwarp();
                     ++ci;
                 };
-                {
+                if (kChunk) {
+                    uint32_t r0[32];
+                    for (int ch = ch_begin; ch < ch_end; ++ch) do_chunk(r0, r0, ch);
+                } else {
                     uint32_t r0[32], r1[32];
                     tmem_ld32(t_row + ch_begin * 32, r0);
                     for (int ch = ch_begin; ch < ch_end; ch += 2) {
