@@ -5,6 +5,7 @@ same torch op fed with the fp16-rounded operands (tight bound: accumulation orde
 un-rounded fp32 op (loose bound: operand rounding, 2^-11 relative per operand).
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -185,6 +186,51 @@ def test_conv_epilogue_variants(cuda_dev, N, H, W, Cin, Cout):
             if not res:
                 o16 = ops.conv_gemm([(x16, wp)], N, H, W, Cout, bias=b, out_kind=L.OUT_F16_NHWC, block_n=bn)
                 assert torch.equal(o16, out.half()), bn     # same fp32 value, one rounding
+
+
+_LOOP_PROBE = r'''
+import math, sys, torch, torch.nn.functional as F
+sys.path.insert(0, %r)
+from nice_diffusion_b200 import ops, _lib as L
+dev = torch.device('cuda:0')
+g = torch.Generator(device='cpu').manual_seed(5)
+worst = 0.0
+for (N, H, W, C1, C2, Cout) in [(2, 32, 32, 192, 0, 192), (3, 16, 16, 128, 320, 192), (1, 64, 64, 64, 64, 96), (2, 28, 28, 96, 0, 64)]:
+    x = torch.randn(N, C1, H, W, generator=g).to(dev)
+    w = (torch.randn(Cout, C1, 3, 3, generator=g) / math.sqrt(C1 * 9)).to(dev)
+    b = (0.3 * torch.randn(Cout, generator=g)).to(dev)
+    segs = [(x.permute(0, 2, 3, 1).contiguous().half(), ops.pack_conv_weight(w))]
+    ref = F.conv2d(x.half().float(), w.half().float(), b, padding=1)
+    if C2:     # fused 1x1 skip over a second tensor (the up path's out_conv + skip)
+        x2 = torch.randn(N, C2, H, W, generator=g).to(dev)
+        w2 = (torch.randn(Cout, C2, 1, 1, generator=g) / math.sqrt(C2)).to(dev)
+        segs.append((x2.permute(0, 2, 3, 1).contiguous().half(), ops.pack_conv_weight(w2)))
+        ref = ref + F.conv2d(x2.half().float(), w2.half().float())
+    st = ops.conv_stats_alloc(N, H, W, Cout, dev, C1 * 9 + C2) if ops.conv_stats_supported(N, H, W) else None
+    out = ops.conv_gemm(segs, N, H, W, Cout, bias=b, stats=st).permute(0, 3, 1, 2)
+    worst = max(worst, float((out - ref).abs().max() / ref.abs().max()))
+    if st is not None:
+        tot = ops.stats_totals(st)
+        o = out.double().flatten(2)
+        assert torch.allclose(tot[:, :, 0], o.sum(2), rtol=1e-5, atol=2e-3)
+print('WORST', worst)
+'''
+
+
+@pytest.mark.parametrize('env', [{}, {'NDB_HALO': '0'}, {'NDB_DISABLE_VREUSE': '1'}, {'NDB_TILE_TALL': '0'},
+                                 {'NDB_NO_INTERLEAVE': '1'}, {'NDB_SPLIT_PRODUCER': '0', 'NDB_DISABLE_VREUSE': '1'}])
+def test_conv_operand_loops(cuda_dev, env):
+    """The GEMM has four operand-feed loops -- one halo box per channel block (default), one box per dx, one box per tap,
+    and the wide-tile geometry -- selected per layer by tile shape; the environment switches force each of them onto the
+    same 3x3 (+ fused 1x1 skip) problems, in a fresh process (the switches are read once)."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, '-c', _LOOP_PROBE % root], env=e, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    worst = float(r.stdout.strip().split('WORST')[-1])
+    assert worst < 2e-5, (env, worst)
 
 
 def test_conv_short_k_many_tiles(cuda_dev):
