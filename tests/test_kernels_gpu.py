@@ -394,11 +394,11 @@ def test_groupnorm_plain_preadd_nosilu(cuda_dev):
     assert rel_err(out.permute(0, 3, 1, 2), ref) < 1.5e-3
 
 
-# the last three have more work items (B * heads * ceil(T / 128)) than resident CTAs (2 per SM): the persistent path, where a
-# CTA streams several items back to back (5 x 7 x 1024/128 = 280 < 296 is the largest non-persistent one)
+# T >= 512 with head dims <= 64 runs the two-query-tile kernel (one thread per row); the others the two-threads-per-row one.
+# 784 and 1664 = 13 x 128 leave the last CTA's second query tile empty; 1000 (below) pads the last key block as well
 ATTN_CASES = [(2, 64, 4, 64, 0), (2, 256, 3, 64, 0), (1, 1024, 2, 64, 0), (2, 196, 4, 32, 0), (3, 49, 4, 64, 0),
               (2, 256, 2, 64, 1), (1, 256, 2, 128, 0), (1, 64, 2, 256, 0), (1, 320, 1, 192, 1),
-              (9, 1024, 6, 64, 0), (25, 256, 9, 64, 1), (11, 784, 5, 32, 0)]
+              (9, 1024, 6, 64, 0), (25, 256, 9, 64, 1), (11, 784, 5, 32, 0), (2, 512, 3, 64, 1), (1, 1664, 2, 48, 0)]
 
 
 @pytest.mark.parametrize('B,T,heads,d,order', ATTN_CASES)
@@ -418,7 +418,7 @@ def test_attention(cuda_dev, B, T, heads, d, order):
     assert rel_err(out, ref) < 2e-3
 
 
-@pytest.mark.parametrize('T,gain', [(384, 6.0), (200, 12.0)])
+@pytest.mark.parametrize('T,gain', [(384, 6.0), (200, 12.0), (640, 6.0), (1000, 10.0)])
 def test_attention_peaky_scores(cuda_dev, T, gain):
     """Large, growing scores: every key block raises the running maximum (O is rescaled each block), the two threads of
     a row hold very different partial maxima / sums, and the last block is padded."""
