@@ -3,22 +3,30 @@
 //   M = N*H*W output pixels, tiled as boxes of TN images x TH rows x TW columns (<= 128 pixels),
 //   N = output channels (BLOCK_N <= 256 per tile), K = sum over segments of taps * C.
 //
-// Data path: activations stay NHWC fp16 in HBM; for every (tap, 64-channel chunk) one TMA 4-D box
-// {64ch, TW, TH, TN} shifted by the tap offset lands in shared memory as a 128-row K-major SWIZZLE_128B
-// operand tile (image borders = TMA out-of-bounds zero fill, so there is no im2col buffer and no padding
-// pass). Weights are [tap][cout][cin] fp16 and arrive as {64, BLOCK_N, 1} boxes. One elected thread issues
-// tcgen05.mma (128 x BLOCK_N x 16, fp32 accumulate in TMEM); accumulators are double-buffered in TMEM so
-// the epilogue of tile i overlaps the main loop of tile i+1. Persistent CTAs, one per SM.
+// Data path: activations stay NHWC fp16 in HBM and reach shared memory as TMA 4-D boxes {64ch, w, h, n} in the K-major
+// SWIZZLE_128B operand layout (image borders = TMA out-of-bounds zero fill, so there is no im2col buffer and no padding
+// pass). Three operand loops, chosen per layer (ndb_conv_gemm):
+//   halo     (3x3, tiles of 8 columns x 16 rows): ONE box of (TH+2) x (TW+2) pixels per 64-channel block serves all nine
+//            taps -- the MMA of tap (dy, dx) reads 128 rows through a descriptor that starts (dy*(TW+2) + dx) * 128 bytes
+//            into the box (off the 1024-byte swizzle atom: the swizzle is a function of the smem address, which TMA write
+//            and MMA read share) with a stride byte offset of (TW+2) * 128;
+//   vertical (3x3, other tile widths that are multiples of 8): one (TH+2)-row box per (dx, channel block), the three dy
+//            windows start whole atoms apart;
+//   classic  (1x1 layers, tiles that hold several images, fp32-class mode): one {64ch, TW, TH, TN} box per (tap, channel
+//            block), activation and weight tile of a K block share a pipeline stage.
+// In the first two, boxes and weight tiles ({64, BLOCK_N, 1} boxes of the [tap][cout][cin] weights, one per K block) travel
+// through two independent rings and the K loop walks a host-built list of units (= boxes). One elected thread issues
+// tcgen05.mma (128 x BLOCK_N x 16, fp32 accumulate in TMEM); accumulators are double-buffered in TMEM so the epilogue of
+// tile i overlaps the main loop of tile i+1. Persistent CTAs, one per SM.
 //
-// Warp roles (352 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue,
-// warp 10 = GroupNorm-statistics reducer (only active when chan_stats is requested).
+// Warp roles (384 threads): warp 0 = activation producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue,
+// warp 10 = GroupNorm-statistics reducer (only active when chan_stats is requested), warp 11 = weight producer.
 // Epilogue: each warp owns 32 accumulator rows (its TMEM lane quarter) and half of the tile's 32-column chunks.
-//   bulk path (NHWC outputs; tiles have power-of-two extents, so the 32 rows of a warp always form a {w, h} pixel box): the chunk is pulled out of
-//   TMEM (thread = row) into a per-warp 4 KB SWIZZLE_128B staging tile with conflict-free 16-byte stores; when a residual
-//   or GroupNorm statistics are wanted the warp then walks the tile with lanes along channels (conflict-free again), adds
-//   bias + residual in place and takes the column sums; ONE TMA store writes the box back. Residual values are fetched
-//   with lanes along channels (32 coalesced 128-byte requests in flight per warp) one chunk AHEAD of the chunk being
-//   processed, across tile boundaries, so their latency hides behind the previous chunk.
+//   bulk path (NHWC outputs; tiles have power-of-two extents, so the 32 rows of a warp always form a {w, h} pixel box): the
+//   chunk is pulled out of TMEM (thread = row; the read of chunk i+1 is in flight while chunk i is processed), bias and
+//   -- when there is one -- the residual, which a TMA load has placed in the same 4 KB SWIZZLE_128B staging tile, are added
+//   in that thread = row form with conflict-free 16-byte accesses; when GroupNorm statistics are wanted the warp then
+//   walks the tile with lanes along channels for the column sums; ONE TMA store writes the box back.
 //   legacy path (NCHW head, 2x up/down-sampled residuals): padded transpose tile + per-row stores.
 #include "common.cuh"
 #include "ptx.cuh"
