@@ -76,6 +76,7 @@ struct ConvArgs {
     int tiles_w, tiles_h, tiles_n;
     int num_m_tiles, num_n_tiles;
     int block_n;
+    int n_stride;              // output channels between consecutive N tiles (= block_n, or less: overlapping tiles)
     int cout;
     int num_seg;
     int seg_taps[kMaxSeg];
@@ -260,7 +261,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                 const int th_i = m_tile % p.tiles_h;
                 const int tn_i = m_tile / p.tiles_h;
                 const int w0 = tw_i * p.TW, h0 = th_i * p.TH, n0 = tn_i * p.TN;
-                const int b_row0 = n_tile * p.block_n + (int)rank * p.b_rows;
+                const int b_row0 = n_tile * p.n_stride + (int)rank * p.b_rows;
                 const bool halo = p.vreuse == 2;      // one (TW + 2) x (TH + 2) box per channel block serves all nine taps
                 for (int u = 0; u < p.n_units; ++u) {
                     const int s = p.unit_seg[u], ch = p.unit_ch[u], dxi = p.unit_dx[u];
@@ -314,7 +315,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                 const int th_i = m_tile % p.tiles_h;
                 const int tn_i = m_tile / p.tiles_h;
                 const int w0 = tw_i * p.TW, h0 = th_i * p.TH, n0 = tn_i * p.TN;   // n0 >= N for the odd leftover tile: all zero
-                const int b_row0 = n_tile * p.block_n + (int)rank * p.b_rows;
+                const int b_row0 = n_tile * p.n_stride + (int)rank * p.b_rows;
                 for (int s = 0; s < p.num_seg; ++s) {
                     const int taps = p.seg_taps[s];
                     const int chunks = p.seg_chunks[s];
@@ -565,7 +566,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
                 const int th_i = m_tile % p.tiles_h;
                 const int tn_i = m_tile / p.tiles_h;
                 mbar_arrive_expect_tx(&res_bar[b], 4096u);
-                tma_load_4d(sbuf0 + b * 4096, &maps.res, &res_bar[b], (tile % p.num_n_tiles) * p.block_n + ch * 32,
+                tma_load_4d(sbuf0 + b * 4096, &maps.res, &res_bar[b], (tile % p.num_n_tiles) * p.n_stride + ch * 32,
                             tw_i * p.TW + btw, th_i * p.TH + bth, tn_i * p.TN + btn);
             };
             // position of the chunk two ahead of (tile, ch) in this warp's sequence
@@ -588,7 +589,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             // critical path of the short-K GEMMs)
             float bias_r[4];
             auto fetch_bias = [&](int tile) {
-                const int col0n = (tile % p.num_n_tiles) * p.block_n;
+                const int col0n = (tile % p.num_n_tiles) * p.n_stride;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int col = col0n + (ch_begin + c) * 32 + lane;
@@ -597,7 +598,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             };
             fetch_bias(tile_begin);
             for (int tile = tile_begin; tile < tile_end; ++tile) {
-                const int col0 = (tile % p.num_n_tiles) * p.block_n;
+                const int col0 = (tile % p.num_n_tiles) * p.n_stride;
                 int m_tile = m_tile_of(tile);
                 const int tw_i = m_tile % p.tiles_w;
                 m_tile /= p.tiles_w;
@@ -784,7 +785,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             const int tn_i = m_tile / p.tiles_h;
             const int n = tn_i * p.TN + tn, h = th_i * p.TH + th, w = tw_i * p.TW + tw;
             const bool valid = (tn < p.TN) && (n < p.N) && (h < p.H) && (w < p.W);
-            const int col0 = n_tile * p.block_n;
+            const int col0 = n_tile * p.n_stride;
             // element offsets of this row's pixel (valid rows only)
             long long out_off = 0, res_off = 0;
             if (valid) {
@@ -945,7 +946,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
         for (int tile = tile_begin; tile < tile_end; ++tile) {
             const int n_tile = tile % p.num_n_tiles;
             const int group = group_of(tile);
-            const int col0 = n_tile * p.block_n;
+            const int col0 = n_tile * p.n_stride;
             if (group != cur_group) {
                 if (cur_group >= 0) flush(cur_group, cur_slot);
                 for (int i = lane; i < p.TN * p.cout; i += 32) stat_acc[i] = make_float2(0.f, 0.f);
@@ -958,7 +959,7 @@ conv_gemm_kernel(const __grid_constant__ TmapPack maps, const ConvArgs p) {
             const float2* ps = part_smem + stat_buf * 4 * p.block_n;
             for (int sl = 0; sl < p.TN; ++sl) {
                 float2* acc_row = stat_acc + sl * p.cout + col0;
-                for (int c = lane; c < p.block_n; c += 32) {
+                for (int c = lane; c < p.n_stride; c += 32) {      // (columns past n_stride are the next N tile's)
                     float sx = 0.f, sy = 0.f;
                     for (int qq = sl * warps_per_slot; qq < (sl + 1) * warps_per_slot; ++qq) {
                         const float2 v = ps[qq * p.block_n + c];
@@ -1133,24 +1134,32 @@ static WorkGeom work_geom(const ConvGeom& g, int num_n_tiles, int block_n, bool 
 // BLOCK_N by a small cost model: rounds of tiles per worker x tile cost. Narrow tiles run the tensor pipe at a lower rate
 // (shared-memory operand bandwidth per MMA grows relative to its work; rates measured with scripts/blockn_probe.py), but
 // they fill the machine when a layer has few tiles (the 8x8 levels: 16 M tiles).
-static int pick_block_n(int cout_pad, const ConvGeom& g, bool want_stats, int kblocks, int max_bn = 256) {
-    static const int cand[5] = {256, 192, 128, 96, 64};
-    static const double rate[5] = {1.0, 1.0, 0.78, 0.61, 0.5};
-    int best = 0;
+// One more shape: OVERLAPPING tiles, 160 columns wide every 144 -- for widths like 576 = 4 x 144 whose 3 x 192 tiling leaves a
+// nearly empty last round (16x16 level: 96 work items on 74 CTA pairs). The 16 columns two neighbours share are computed
+// by both with identical operands in identical order, i.e. stored twice with the same bits, and counted in the
+// statistics by their owner only; whole 32-column chunks keep the epilogue unchanged. `*stride` = channels between tiles.
+static int pick_block_n(int cout_pad, const ConvGeom& g, bool want_stats, int kblocks, int max_bn = 256, int* stride = nullptr) {
+    static const int cand[6] = {256, 192, 160, 128, 96, 64};
+    static const int cstride[6] = {256, 192, 144, 128, 96, 64};
+    static const double rate[6] = {1.0, 1.0, 0.95, 0.78, 0.61, 0.5};
+    static const int no_overlap = std::getenv("NDB_NO_OVERLAP_TILES") != nullptr ? 1 : 0;
+    int best = 0, best_stride = 0;
     double best_cost = 0.0;
-    for (int i = 0; i < 5; ++i) {
-        const int bn = cand[i];
-        if (cout_pad % bn != 0 || bn > max_bn) continue;
-        const WorkGeom w = work_geom(g, cout_pad / bn, bn, want_stats, kblocks);
+    for (int i = 0; i < 6; ++i) {
+        const int bn = cand[i], st = cstride[i];
+        if (cout_pad % st != 0 || bn > max_bn) continue;
+        if (bn != st && (no_overlap || stride == nullptr || max_bn < 256 || cout_pad < 2 * st)) continue;
+        const WorkGeom w = work_geom(g, cout_pad / st, bn, want_stats, kblocks);
         const int rounds = (w.items + w.workers - 1) / w.workers;
         double cost = rounds * (double)bn / rate[i];
         if (bn == 256) cost *= 1.02;    // 192 leaves room for one more smem stage: prefer it on ties
-        if (best == 0 || cost < best_cost) { best = bn; best_cost = cost; }
+        if (best == 0 || cost < best_cost) { best = bn; best_stride = st; best_cost = cost; }
     }
-    if (best) return best;
-    for (int bn = max_bn; bn >= 16; bn -= 16)
-        if (cout_pad % bn == 0) return bn;
-    return 0;
+    if (!best)
+        for (int bn = max_bn; bn >= 16; bn -= 16)
+            if (cout_pad % bn == 0) { best = best_stride = bn; break; }
+    if (stride) *stride = best_stride;
+    return best;
 }
 
 }  // namespace ndb
@@ -1190,11 +1199,13 @@ extern "C" int ndb_conv_gemm(const ndb_conv_params* prm, void* stream) {
     a.num_m_tiles = cg.num_m_tiles;
     int kblocks_total = 0;
     for (int s = 0; s < prm->num_segments; ++s) kblocks_total += prm->seg[s].taps * ((prm->seg[s].C + kBlockK - 1) / kBlockK);
+    a.n_stride = prm->block_n;
     a.block_n = prm->block_n > 0 ? prm->block_n
                                  : pick_block_n(prm->cout_pad, cg, prm->stat_parts != nullptr, kblocks_total,
-                                                prm->acc_chunk_kblocks > 0 ? 192 : 256);
-    NDB_CHECK_ARG(a.block_n >= 16 && a.block_n <= 256 && a.block_n % 16 == 0 && prm->cout_pad % a.block_n == 0);
-    a.num_n_tiles = prm->cout_pad / a.block_n;
+                                                prm->acc_chunk_kblocks > 0 ? 192 : 256, &a.n_stride);
+    NDB_CHECK_ARG(a.block_n >= 16 && a.block_n <= 256 && a.block_n % 16 == 0 && a.n_stride > 0 && a.n_stride <= a.block_n &&
+                  prm->cout_pad % a.n_stride == 0);
+    a.num_n_tiles = prm->cout_pad / a.n_stride;
     a.cout = prm->cout;
     a.num_seg = prm->num_segments;
     a.a_box_bytes = (uint32_t)(a.TN * a.TH * a.TW * 128);
@@ -1437,9 +1448,10 @@ extern "C" int ndb_conv_stats_layout(int N, int H, int W, int cout_pad, int bloc
     if (N <= 0 || H <= 0 || W <= 0 || cout_pad <= 0 || k_total <= 0) return NDB_ERR_INVALID;
     const int kblocks = (k_total + kBlockK - 1) / kBlockK;      // only "at least one" matters to the plan
     const ConvGeom g = conv_geom(N, H, W, acc_chunk_kblocks == 0);
-    const int bn = block_n > 0 ? block_n : pick_block_n(cout_pad, g, true, kblocks, acc_chunk_kblocks > 0 ? 192 : 256);
-    if (bn <= 0 || cout_pad % bn != 0) return NDB_ERR_INVALID;
-    const int n_tiles = cout_pad / bn;
+    int st = block_n;
+    const int bn = block_n > 0 ? block_n : pick_block_n(cout_pad, g, true, kblocks, acc_chunk_kblocks > 0 ? 192 : 256, &st);
+    if (bn <= 0 || st <= 0 || cout_pad % st != 0) return NDB_ERR_INVALID;
+    const int n_tiles = cout_pad / st;
     const WorkGeom w = work_geom(g, n_tiles, bn, true, kblocks);
     return stats_slots(g.tiles_n, g.tiles_w * g.tiles_h * n_tiles, n_tiles, g.TN, w.pair, w.items, w.workers, counts, N);
 }

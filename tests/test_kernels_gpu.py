@@ -151,6 +151,7 @@ EPI_CASES = [
     # Cin = 192 -> 27 K blocks: the CTA-pair kernel; Cin = 64 -> 9 K blocks: the single-CTA kernel
     (5, 8, 8, 192, 192), (3, 16, 16, 192, 192), (2, 32, 32, 64, 384), (1, 64, 64, 192, 192), (1, 8, 128, 64, 256),
     (3, 14, 14, 192, 192), (2, 16, 16, 64, 144), (5, 8, 8, 64, 192),
+    (2, 16, 16, 64, 576), (3, 8, 8, 64, 288),      # widths the automatic choice covers with overlapping 160-wide tiles every 144
 ]
 
 
