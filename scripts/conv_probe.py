@@ -11,7 +11,8 @@ shapes = [(32, 32, 32, 384, 1152, 1, 0, 0, 1), (32, 32, 32, 384, 384, 1, 1, 1, 0
           (32, 64, 64, 192, 192, 3, 1, 1, 0), (32, 64, 64, 384, 192, 3, 0, 1, 0), (32, 64, 64, 192, 192, 3, 0, 1, 0),
           (32, 64, 64, 192, 192, 3, 0, 1, 1), (32, 16, 16, 576, 1728, 1, 0, 0, 1), (32, 16, 16, 576, 576, 1, 1, 1, 0),
           # + a fused 1x1 skip segment over C2 channels (10th field): the up-path out_conv + skip(concat) layers
-          (32, 64, 64, 192, 192, 3, 0, 1, 0, 384), (32, 32, 32, 384, 384, 3, 0, 1, 0, 768), (32, 16, 16, 576, 576, 3, 0, 1, 0, 1152)]
+          (32, 64, 64, 192, 192, 3, 0, 1, 0, 384), (32, 32, 32, 384, 384, 3, 0, 1, 0, 768), (32, 16, 16, 576, 576, 3, 0, 1, 0, 1152),
+          (32, 16, 16, 1152, 576, 3, 0, 1, 1), (32, 16, 16, 1152, 192, 3, 0, 1, 1)]
 if len(sys.argv) > 1:
     shapes = [shapes[int(a)] for a in sys.argv[1:]]
 for shp in shapes:
