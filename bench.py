@@ -1,17 +1,20 @@
 #!/usr/bin/env python
 """Benchmark of the sampling hot path (BASELINE.json: images/sec, ImageNet-64 UNet, 250-step respaced DDPM with
-learned-interpolated variance, batch 256 sharded over 8 B200 = 32 images per GPU; weak scaling).
+learned-interpolated variance, batch 256 sharded over the GPUs of the run: 256 / N images per GPU, strong scaling --
+the whole named configuration on one GPU at N = 1, 32 images per GPU at N = 8; `--scaling weak` keeps 32 per GPU at
+every N, the round-1 protocol).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config in64|emnist|in128]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config in64|emnist|in128|in64_clf|train_*]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one denoising step (UNet forward + fused sampler step) over the rank's batch, replayed as one CUDA
 graph. `value` = images/sec of the whole job for the full chain: N * B / (steps_per_image * t_step), device-timed,
 max over ranks. `e2e` = the same metric through the public API (`Diffusion.denoise`) for one complete chain, with
 x_T / labels coming from pinned host memory and the finished images copied back, all inside the timed region.
-`roofline` = algorithmic FLOPs of every implicit-GEMM conv launch / its measured duration (CUDA events around each
-launch of an eager pass of the same plan) against the measured dense bf16 peak. `cpu_baseline` = the oracle port of
-the reference's --cpu path on the host cores (bounded sample). `--impl reference` times that CPU path alone.
+`roofline` = algorithmic FLOPs of every implicit-GEMM conv launch / its duration measured inside the step's CUDA graph
+(%globaltimer stamps between the kernels) against the measured dense bf16 peak, plus the whole-forward fraction.
+`cpu_baseline` / `--impl reference` = the unmodified reference's --cpu path (baseline/_ref) on the host cores, a
+bounded sample of the workload.
 """
 import argparse
 import json
@@ -45,6 +48,24 @@ WORKLOADS = {
 }
 # algorithmic FLOPs per image per UNet forward (counted on the reference modules)
 FLOPS_PER_FWD = {'in64': 219356037120, 'emnist': 3998584832, 'in128': 613855789056, 'in64_clf': 219356037120}
+
+
+# BASELINE.json configs[1]: "batch 256 sharded over 8 x B200"
+IN64_GLOBAL_BATCH = 256
+
+
+def per_gpu_batch(config, world, batch=None, scaling='strong'):
+    """-> (per-GPU batch, value of the line's `scaling` key). ImageNet-64 (the configuration the metric is quoted on) runs
+    the batch the configuration names on however many GPUs the run has: total work fixed, 256 / N images per GPU. An explicit
+    --batch, --scaling weak and the other workloads (single-GPU configurations) keep a fixed per-GPU batch."""
+    if batch:
+        return int(batch), 'weak'
+    if config == 'in64' and scaling == 'strong':
+        if IN64_GLOBAL_BATCH % world != 0:
+            raise SystemExit('bench.py: {} GPUs do not divide the global batch of {}'.format(world, IN64_GLOBAL_BATCH))
+        return IN64_GLOBAL_BATCH // world, 'strong'
+    table = WORKLOADS if config in WORKLOADS else TRAIN_WORKLOADS
+    return (table[config][2] if config in WORKLOADS else table[config][1]), 'weak'
 
 
 def model_config(name):
@@ -417,7 +438,11 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', type=str, default='ndb200', choices=['ndb200', 'reference'])
     ap.add_argument('--config', type=str, default='in64', choices=sorted(WORKLOADS) + sorted(TRAIN_WORKLOADS))
-    ap.add_argument('--batch', type=int, default=None, help='per-GPU batch (default: the BASELINE value)')
+    ap.add_argument('--batch', type=int, default=None, help='per-GPU batch, fixed for every N (default: see --scaling)')
+    ap.add_argument('--scaling', type=str, default='strong', choices=['strong', 'weak'],
+                    help="in64 only. strong (default): the batch BASELINE config 2 names -- 256 images -- on the GPUs of the "
+                         "run, 256 / N per GPU (N=1: the whole configuration on one GPU; N=8: 32 per GPU as the config says). "
+                         "weak: 32 images per GPU at every N (the round-1 protocol)")
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--eager', action='store_true', help='launch kernels one by one instead of replaying CUDA graphs (profiling)')
     ap.add_argument('--operands', type=str, default='fp16', choices=['fp16', 'fp32x'],
@@ -440,13 +465,13 @@ def main():
             raise SystemExit('bench.py: no CUDA device')
         return train_arm(args, rank, world, local_rank)
     cname, dkw, B, per_image = WORKLOADS[args.config]
-    if args.batch:
-        B = args.batch
+    B, scaling = per_gpu_batch(args.config, world, args.batch, args.scaling)
     metric = 'images/sec ({} UNet, {}-step {} sampling)'.format(
         {'in64': 'ImageNet-64', 'emnist': 'EMNIST', 'in128': 'ImageNet-128', 'in64_clf': 'ImageNet-64 + noisy-classifier guidance'}[args.config], per_image,
         'DDIM' if dkw.get('use_ddim') else 'DDPM')
-    config = {'workload': '{}: {} steps/image, {}, per-GPU batch {} (global {}), {}'.format(
+    config = {'workload': '{}: {} steps/image, {}, per-GPU batch {} (global {}{}), {}'.format(
         args.config, per_image, dkw['sampling_var_type'], B, B * world,
+        ': the batch BASELINE config 2 names, sharded over the GPUs of the run' if scaling == 'strong' else '',
         'classifier-free guidance as a doubled batch' if dkw.get('guidance_method') else 'no guidance'),
         'global_batch': B * world, 'per_gpu_batch': B, 'steps_per_image': per_image,
         'parallelism': 'batch-sharded x{} (no collective on the data path)'.format(world),
@@ -466,7 +491,7 @@ def main():
             parallelism='one host process, {} threads'.format(r['cores']), operands='fp32 (PyTorch CPU kernels)', l2='n/a')
         line = {'impl': 'reference', 'metric': metric, 'value': r['value'], 'unit': 'images/sec', 'n_gpus': args.gpus,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
-                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+                'scaling': scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
                 'cpu_baseline': {'value': r['value'], 'unit': 'images/sec', 'cores': r['cores'], 'kind': r['kind'],
                                  'sample': r['sample']},
                 'e2e': {'value': r['value'], 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
@@ -612,8 +637,10 @@ def main():
     # DRAM traffic of the dominant kernel: from the committed ncu pass of the same step (profiles/), not measured live
     try:
         import glob
-        cand = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', '*_conv_traffic.json')))
-        if cand and args.config == 'in64' and B == WORKLOADS['in64'][2]:
+        cand = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', '*_conv_traffic*.json')))
+        # a capture counts for this run when it was taken at the same per-GPU batch (files without the key: 32)
+        cand = [c for c in cand if json.load(open(c)).get('per_gpu_batch', WORKLOADS['in64'][2]) == B]
+        if cand and args.config == 'in64':
             tr = json.load(open(cand[-1]))
             roofline['traffic'] = tr['dram_bytes_per_launch_avg']
             roofline['traffic_unit'] = 'bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the %d ' \
@@ -634,7 +661,7 @@ def main():
         cpu = {'value': r['value'], 'unit': 'images/sec', 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample']}
 
     line = {'metric': metric, 'value': value, 'unit': 'images/sec', 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': scaling,
             'vs_baseline': None, 'dtype': 'fp16' if args.operands == 'fp16' else 'fp32x', 'data': 'synthetic', 'config': config,
             'clocks': clk,
             'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,

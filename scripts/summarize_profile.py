@@ -1,6 +1,7 @@
 """Turn gpurun_out/{launches_TAG.csv, prof_TAG.ncu-rep, bench_TAG.json} into the tracked summaries under profiles/."""
 import collections, csv, json, os, shutil, subprocess, sys
 tag = sys.argv[1] if len(sys.argv) > 1 else 'r01'
+batch = int(sys.argv[2]) if len(sys.argv) > 2 else 32      # per-GPU batch of the profiled run (recorded with the traffic)
 src, dst = 'gpurun_out', 'profiles'
 os.makedirs(dst, exist_ok=True)
 out = []
@@ -38,7 +39,7 @@ for row in rows[2:]:
         if h in hdr:
             txt.append('  %-80s %s' % (h, row[hdr.index(h)][:90]))
 open(os.path.join(dst, '%s_top_kernel_ncu.txt' % tag), 'w').write('\n'.join(txt) + '\n')
-for f in ('bench_%s.json' % tag, 'bench_ref_%s.json' % tag):
+for f in ('bench_%s.json' % tag, 'bench_%s_k20.json' % tag, 'bench_ref_%s.json' % tag):
     if os.path.exists(os.path.join(src, f)):
         shutil.copy(os.path.join(src, f), os.path.join(dst, f))
 print('\n'.join(out)); print('\n'.join(txt))
@@ -64,14 +65,15 @@ if os.path.exists(sec):
         tot_t = tot_b = 0.0
         for i, r in enumerate(rows_):
             w.writerow([i] + [r[h.index(c)] for c in cols])
-            tot_t += float(r[h.index('gpu__time_duration.sum')])
+            tot_t += float(r[h.index('gpu__time_duration.sum')]) * {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 's': 1e6}.get(
+                u[h.index('gpu__time_duration.sum')].replace('second', 's').replace('usecond', 'us'), 1.0)   # -> us
             if 'dram__bytes_read.sum' in h:
                 def tobytes(v, unit):
                     return float(v) * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[unit]
                 tot_b += tobytes(r[h.index('dram__bytes_read.sum')], u[h.index('dram__bytes_read.sum')]) + \
                     tobytes(r[h.index('dram__bytes_write.sum')], u[h.index('dram__bytes_write.sum')])
     n = len(rows_)
-    json.dump({'kernel': 'conv_gemm_kernel', 'launches': n, 'sum_gpu_time_us': tot_t, 'dram_bytes_per_launch_avg': tot_b / max(n, 1),
+    json.dump({'kernel': 'conv_gemm_kernel', 'per_gpu_batch': batch, 'launches': n, 'sum_gpu_time_us': tot_t, 'dram_bytes_per_launch_avg': tot_b / max(n, 1),
                'dram_bytes_per_step': tot_b, 'source': 'ncu dram__bytes_read.sum + dram__bytes_write.sum over the %d launches of one step' % n},
               open(os.path.join(dst, '%s_conv_traffic.json' % tag), 'w'), indent=1)
     print('conv sections: %d launches, %.1f us, %.1f MB DRAM traffic per launch' % (n, tot_t, tot_b / max(n, 1) / 1e6))
