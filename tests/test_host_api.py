@@ -207,3 +207,22 @@ def test_product_never_imports_the_oracle():
     for f in ('scripts/sample.py', 'nice_diffusion_b200.py'):
         assert not pat.search(open(os.path.join(root, f)).read()), f
     assert checked > 10
+
+
+def test_bench_batch_follows_the_named_configuration():
+    """bench.py: ImageNet-64 (BASELINE config 2: "batch 256 sharded over 8 x B200") runs the named batch on the GPUs of the
+    run -- 256 / N per GPU, strong scaling; --scaling weak and an explicit --batch keep the per-GPU batch fixed."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('ndb_bench', os.path.join(root, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for world, b in ((1, 256), (2, 128), (4, 64), (8, 32)):
+        assert bench.per_gpu_batch('in64', world) == (b, 'strong')
+        assert bench.per_gpu_batch('in64', world, None, 'weak') == (32, 'weak')
+        assert bench.per_gpu_batch('in64', world, 48) == (48, 'weak')
+        assert bench.per_gpu_batch('emnist', world) == (16, 'weak')
+        assert bench.per_gpu_batch('in128', world) == (8, 'weak')
+        assert bench.per_gpu_batch('in64_clf', world) == (32, 'weak')
+    with pytest.raises(SystemExit):
+        bench.per_gpu_batch('in64', 3)
