@@ -9,7 +9,7 @@ mkdir -p gpurun_out
 for rep in 1 2; do
   for v in "$@"; do
     [ "$v" = "-" ] && envs="NDB_AB=0" || envs="$v"
-    env $envs timeout 400 python bench.py --config $CFG --steps 50 --warmup 5 --no-e2e --no-cpu-baseline --no-gpu-reference \
+    env $envs timeout 400 python bench.py --config $CFG ${AB_ARGS:---scaling weak} --steps 50 --warmup 5 --no-e2e --no-cpu-baseline --no-gpu-reference \
         > gpurun_out/ab.json 2> gpurun_out/ab.err || { echo "$v: bench failed"; tail -3 gpurun_out/ab.err; continue; }
     echo -n "[$v] "; python scripts/print_bench.py gpurun_out/ab.json
   done

@@ -5,8 +5,9 @@ TAG=${1:-r02}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q > gpurun_out/tests_$TAG.log 2>&1; echo "tests rc=$?"; tail -2 gpurun_out/tests_$TAG.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-python bench.py --steps 20 --warmup 3 > gpurun_out/bench_${TAG}_k20.json 2> gpurun_out/bench_${TAG}_k20.err; python scripts/print_bench.py gpurun_out/bench_${TAG}_k20.json
-python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; python scripts/print_bench.py gpurun_out/bench_$TAG.json
+python bench.py --steps 20 --warmup 3 > gpurun_out/bench_${TAG}b256_k20.json 2> gpurun_out/bench_${TAG}b256_k20.err; python scripts/print_bench.py gpurun_out/bench_${TAG}b256_k20.json   # default: the named batch of 256
+python bench.py --scaling weak --steps 20 --warmup 3 > gpurun_out/bench_${TAG}_k20.json 2> gpurun_out/bench_${TAG}_k20.err; python scripts/print_bench.py gpurun_out/bench_${TAG}_k20.json   # 32 images per GPU (the 8-GPU shard)
+python bench.py --scaling weak > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; python scripts/print_bench.py gpurun_out/bench_$TAG.json
 python bench.py --config emnist --steps 50 --warmup 5 > gpurun_out/bench_emnist_$TAG.json 2> /dev/null; python scripts/print_bench.py gpurun_out/bench_emnist_$TAG.json
 python bench.py --config in128 --steps 20 --warmup 3 > gpurun_out/bench_in128_$TAG.json 2> /dev/null; python scripts/print_bench.py gpurun_out/bench_in128_$TAG.json
 python scripts/timeline.py --out gpurun_out/timeline_in64_$TAG.txt > /dev/null 2>&1
