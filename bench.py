@@ -634,6 +634,33 @@ def main():
                 'timing': 'per-kernel times: %globaltimer stamps between the launches inside one CUDA graph of the step',
                 'other_kernels_ms': {k: v['ms'] for k, v in prof.items() if isinstance(v, dict) and k != 'conv_gemm'}}
 
+    # informational, N = 1 of the ImageNet-64 line only: the same step at the per-GPU batch of the 8-GPU run (32 images), so
+    # that one line carries both ends of the "batch 256 sharded over 8 GPUs" configuration
+    shard = WORKLOADS['in64'][2]
+    if args.config == 'in64' and world == 1 and B > shard and not args.eager:
+        try:
+            diff.sample_ids = ids[:shard]
+            r32 = diff.make_step_runner(x_host[:shard].to(dev), {'y': labels_host[:shard].to(dev)})
+            for _ in range(max(args.warmup, 3)):
+                r32.step()
+            torch.cuda.synchronize(dev)
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(20):
+                r32.step()
+            s1.record()
+            torch.cuda.synchronize(dev)
+            ms32 = s0.elapsed_time(s1) / 20
+            tf32 = FLOPS_PER_FWD[args.config] * r32.model_batch / (ms32 * 1e-3) / 1e12
+            roofline['shard_of_8_gpu_run'] = {'per_gpu_batch': shard, 'steps': 20, 'ms_per_step': ms32,
+                                              'images_per_sec_per_gpu': shard / (per_image * ms32 * 1e-3),
+                                              'step_tflops': tf32, 'step_frac': tf32 / pk['bf16_sustained']}
+            del r32
+        except Exception as e:  # noqa: BLE001  (information only: never lose the line over it)
+            roofline['shard_of_8_gpu_run'] = {'error': repr(e)[:200]}
+        finally:
+            diff.sample_ids = ids
+
     # DRAM traffic of the dominant kernel: from the committed ncu pass of the same step (profiles/), not measured live
     try:
         import glob
