@@ -68,6 +68,25 @@ def per_gpu_batch(config, world, batch=None, scaling='strong'):
     return (table[config][2] if config in WORKLOADS else table[config][1]), 'weak'
 
 
+def conv_traffic_capture(config, batch, profiles_dir=None):
+    """The committed ncu capture (profiles/*_conv_traffic*.json: DRAM bytes of every conv GEMM launch of one step) that
+    matches this run: ImageNet-64 at the same per-GPU batch (files without the key were taken at 32), newest tag last.
+    None when there is none -- `roofline.traffic` is then null rather than a number from another workload."""
+    import glob
+    if config != 'in64':
+        return None
+    d = profiles_dir or os.path.join(ROOT, 'profiles')
+    best = None
+    for path in sorted(glob.glob(os.path.join(d, '*_conv_traffic*.json'))):
+        try:
+            tr = json.load(open(path))
+        except (OSError, ValueError):
+            continue
+        if tr.get('per_gpu_batch', WORKLOADS['in64'][2]) == batch and 'dram_bytes_per_launch_avg' in tr:
+            best = dict(tr, file=os.path.basename(path))
+    return best
+
+
 def model_config(name):
     from nice_diffusion_b200 import default_args as da
     cfg = dict({'in64': da.OPENAI_64_MODEL_ARGS, 'emnist': da.EMNIST_MODEL_ARGS, 'in128': da.OPENAI_128_MODEL_ARGS,
@@ -662,18 +681,11 @@ def main():
             diff.sample_ids = ids
 
     # DRAM traffic of the dominant kernel: from the committed ncu pass of the same step (profiles/), not measured live
-    try:
-        import glob
-        cand = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', '*_conv_traffic*.json')))
-        # a capture counts for this run when it was taken at the same per-GPU batch (files without the key: 32)
-        cand = [c for c in cand if json.load(open(c)).get('per_gpu_batch', WORKLOADS['in64'][2]) == B]
-        if cand and args.config == 'in64':
-            tr = json.load(open(cand[-1]))
-            roofline['traffic'] = tr['dram_bytes_per_launch_avg']
-            roofline['traffic_unit'] = 'bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the %d ' \
-                                       'conv_gemm launches of one step; %s)' % (tr['launches'], os.path.basename(cand[-1]))
-    except Exception:
-        pass
+    tr = conv_traffic_capture(args.config, B)
+    if tr is not None:
+        roofline['traffic'] = tr['dram_bytes_per_launch_avg']
+        roofline['traffic_unit'] = 'bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the %d ' \
+                                   'conv_gemm launches of one step; %s)' % (tr['launches'], tr['file'])
 
     gpu_ref = None
     if not args.no_gpu_reference and world == 1:

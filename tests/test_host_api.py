@@ -226,3 +226,24 @@ def test_bench_batch_follows_the_named_configuration():
         assert bench.per_gpu_batch('in64_clf', world) == (32, 'weak')
     with pytest.raises(SystemExit):
         bench.per_gpu_batch('in64', 3)
+
+
+def test_bench_traffic_capture_matches_the_batch_of_the_run(tmp_path):
+    """`roofline.traffic` comes from a committed ncu capture: only one taken at the run's per-GPU batch may be used."""
+    import importlib.util
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('ndb_bench2', os.path.join(root, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    (tmp_path / 'r01_conv_traffic.json').write_text(json.dumps({'launches': 118, 'dram_bytes_per_launch_avg': 1.0}))
+    (tmp_path / 'r02_conv_traffic.json').write_text(json.dumps({'launches': 118, 'dram_bytes_per_launch_avg': 2.0}))
+    (tmp_path / 'r02b256_conv_traffic.json').write_text(
+        json.dumps({'launches': 118, 'dram_bytes_per_launch_avg': 9.0, 'per_gpu_batch': 256}))
+    assert bench.conv_traffic_capture('in64', 32, str(tmp_path))['dram_bytes_per_launch_avg'] == 2.0     # newest tag wins
+    assert bench.conv_traffic_capture('in64', 256, str(tmp_path))['file'] == 'r02b256_conv_traffic.json'
+    assert bench.conv_traffic_capture('in64', 64, str(tmp_path)) is None
+    assert bench.conv_traffic_capture('emnist', 32, str(tmp_path)) is None
+    # the committed captures of this tree
+    assert bench.conv_traffic_capture('in64', 256)['per_gpu_batch'] == 256
+    assert bench.conv_traffic_capture('in64', 32) is not None
